@@ -1,0 +1,232 @@
+/* map_b200.h — C ABI of libmap_b200.so: the B200 (sm_100a) kernels behind MAP's pretraining / finetuning step.
+ *
+ * The reference (CHIANGEL/MAP-CODE) is pure Python on torch eager; it has no FFI layer.  The boundary that replaces its
+ * ATen / cuBLAS dispatches is this header.  Each entry point cites the reference call site it replaces
+ * (paths relative to the reference root, `code/...:line`).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MAP_E* code on failure; map_last_error() gives the text
+ *     (thread-local).  Nothing here falls back to the CPU: a launch failure is an error, not a slow path.
+ *   - the CALLER owns every buffer.  Device functions never allocate, never synchronise, never touch host memory
+ *     (except the `const map_gemm_args*` struct, read before the launch) and launch only on `stream`:
+ *     they are CUDA-graph capturable and safe to call concurrently on different streams.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - ids are int64 (the reference's dtype), floating point is IEEE fp32.  Tensor-core GEMMs multiply in TF32
+ *     (10-bit mantissa) and accumulate in fp32; see DESIGN.md for the tolerance.
+ *   - RNG: Philox4x32-10, key = seed (lo,hi), counter = (elem_lo, elem_hi, offset_lo, offset_hi): the result for
+ *     element `elem` does not depend on grid shape or on how many GPUs the batch is split over.
+ *     bounded(u64 r, n) = mulhi64(r, n), r = w0 | w1<<32 ; bounded32(w0, n) = (w0*n)>>32 ; u01 = (w2>>8)*2^-24.
+ */
+#ifndef MAP_B200_H
+#define MAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAP_B200_ABI_VERSION 1
+
+#define MAP_OK 0
+#define MAP_EINVAL (-1)   /* bad argument (shape, alignment, null pointer, unsupported size) */
+#define MAP_ECUDA (-2)    /* CUDA runtime / driver error (text in map_last_error) */
+#define MAP_EWORKSPACE (-3) /* workspace too small */
+#define MAP_EUNSUPPORTED (-4)
+
+typedef void* map_stream_t;
+
+int map_abi_version(void);
+const char* map_last_error(void);
+/* number of SMs of the current device (grid sizing on the host side) */
+int map_sm_count(int* out);
+
+/* ------------------------------------------------------------------ K1  embedding gather
+ * replaces nn.Embedding forward: code/layers.py:98 (Embeddings.forward), code/models.py:139 (LR.embed_w),
+ * code/nce/index_linear.py:99-100 (index_select of emb / bias rows).
+ * out[i, :] = table[ids[i], :]  (bit-exact copy).  D % 4 == 0 uses 16-byte lanes; any D >= 1 is accepted.
+ * ids outside [0, V) write a zero row and set *oob_flag = 1 if oob_flag != NULL (the reference raises IndexError). */
+int map_emb_gather_f32(const float* table, int64_t V, int D, const int64_t* ids, int64_t n_ids, float* out,
+                       int32_t* oob_flag, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K2  deduplicated embedding backward
+ * replaces aten::embedding_dense_backward (autograd of code/layers.py:98) and the index_add of the NCE tables
+ * (autograd of code/nce/index_linear.py:99-100).  Pipeline: radix-sort (id, occurrence) -> unique rows + segment
+ * starts -> segmented row sum into a COMPACT gradient [U, D] -> row-wise AdamW on the U touched rows (sparse) or an
+ * exact dense sweep over all V rows (dense_exact = what transformers.AdamW does in the reference, trainer.py:75,140). */
+size_t map_dedup_workspace_bytes(int64_t n_ids);
+/* Sorts ids; writes uniq_ids[U] (ascending), seg_start[U+1] (positions in sorted order), occ_sorted[n] (original
+ * occurrence index of each sorted position) and *n_unique (device int32).  key_bits = bits needed for V-1. */
+int map_dedup_ids(const int64_t* ids, int64_t n_ids, int key_bits, int64_t* uniq_ids, int32_t* seg_start,
+                  int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes, map_stream_t stream);
+/* grad_compact[u, :] = sum over occurrences o of segment u of  scale[o] * rows[(o / group) , :]
+ * rows: [n_rows, D] with row stride ld_rows; scale == NULL means 1; group >= 1 (NCE: group = K+1, rows = input,
+ * scale = dz; embedding: group = 1, rows = dY).  If scalar_out != NULL also scalar_out[u] = sum scale[o] (bias grad). */
+int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
+                            const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
+                            int64_t n_ids, float* grad_compact, float* scalar_out, map_stream_t stream);
+/* dense[uniq_ids[u], :] = grad_compact[u, :]  (dense must be zero-filled by the caller): the `.grad` the reference sees */
+int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const int32_t* n_unique, int64_t max_unique,
+                     int D, float* dense, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K12 / K2  AdamW (transformers==4.26.1 semantics)
+ * replaces transformers.AdamW.step (code/trainer.py:75-76,140):
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= step_size * m / (sqrt(v)+eps) ; p -= lr*wd*p
+ *   step_size = lr * sqrt(1-b2^t)/(1-b1^t).
+ * hyper: device float[8] = {lr, step_size, beta1, beta2, eps, 0,0,0}, produced by map_adamw_hyper_step so that a
+ * captured CUDA graph picks up the new learning rate at every replay without host involvement. */
+#define MAP_SCHED_CONST 0   /* transformers.get_constant_schedule_with_warmup */
+#define MAP_SCHED_COSINE 1  /* transformers.get_cosine_schedule_with_warmup (num_cycles=0.5) */
+/* step_counter (device int64) is incremented; lr = base_lr * lambda(step_counter_before) (trainer.py:141) */
+int map_adamw_hyper_step(float* hyper, int64_t* step_counter, float base_lr, float beta1, float beta2, float eps,
+                         int sched, int64_t warmup_steps, int64_t total_steps, map_stream_t stream);
+/* explicit (host-driven) variant: step = 1-based step count for bias correction */
+int map_adamw_hyper_set(float* hyper, float lr, float beta1, float beta2, float eps, int64_t step, map_stream_t stream);
+
+typedef struct {
+    float* p;        /* parameter */
+    const float* g;  /* gradient  */
+    float* m;        /* exp_avg   */
+    float* v;        /* exp_avg_sq */
+    float* p_t;      /* optional transposed copy of p ([cols, rows]) refreshed by the update, or NULL */
+    int64_t n;       /* element count */
+    int32_t rows, cols; /* only used when p_t != NULL (n == rows*cols) */
+    float weight_decay;
+    int32_t pad_;
+} map_adamw_tensor;
+/* one launch over a device-resident list of tensors (dense parameters) */
+int map_adamw_multi_tensor(const map_adamw_tensor* tensors_dev, int n_tensors, int64_t max_elems_per_tensor,
+                           const float* hyper, map_stream_t stream);
+/* sparse: only the U touched rows (north_star subsystem 1: "fused sparse optimizer update") */
+int map_adamw_sparse_rows(float* table, float* m, float* v, int D, const int64_t* uniq_ids, const float* grad_compact,
+                          const int32_t* n_unique, int64_t max_unique, const float* hyper, float weight_decay,
+                          map_stream_t stream);
+/* dense_exact: all V rows, gradient of untouched rows = 0 (bit-comparable with the reference's dense AdamW) */
+int map_adamw_dense_rows_sparse_grad(float* table, float* m, float* v, int64_t V, int D, const int64_t* uniq_ids,
+                                     const float* grad_compact, const int32_t* n_unique, const float* hyper,
+                                     float weight_decay, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K8 / K9  dynamic_mask
+ * replaces Trainer.dynamic_mask (code/trainer.py:217-266).  One warp per sample row; duplicate masked fields resolve
+ * last-writer-wins like the reference's CPU scatter.  row0 = global index of the first row (row-sharded runs). */
+#define MAP_SAMPLING_RANDINT 0 /* trainer.py:224-225 */
+#define MAP_SAMPLING_NORMAL 1  /* trainer.py:222-223 randperm(F)[:L] */
+int map_mask_index_philox(int64_t* masked_index, int64_t B, int L, int F, int sampling_method, uint64_t seed,
+                          uint64_t offset, int64_t row0, map_stream_t stream);
+/* MFP (trainer.py:229-233): labels[b,l] = ids[b, mi[b,l]] ; ids_out = ids with masked fields set to mask_id (3) */
+int map_mfp_mask_apply(const int64_t* ids, const int64_t* masked_index, int64_t B, int F, int L, int64_t mask_id,
+                       int64_t* ids_out, int64_t* labels, map_stream_t stream);
+#define MAP_RFD_UNIGRAM 0        /* trainer.py:235-240 */
+#define MAP_RFD_UNIFORM 1        /* trainer.py:241-246 */
+#define MAP_RFD_WHOLE_UNIFORM 2  /* trainer.py:247-252 */
+#define MAP_RFD_WHOLE_UNIGRAM 3  /* trainer.py:253-260 */
+/* RFD: draws the replacement per (b,l), scatters it, labels[b,f] = (ids[b,f] != ids_out[b,f]) as float */
+int map_rfd_replace_philox(const int64_t* ids, const int64_t* masked_index, int64_t B, int F, int L, int mode,
+                           const int64_t* x_train, int64_t n_train, const int64_t* idx_low, const int64_t* idx_high,
+                           int64_t input_size, uint64_t seed, uint64_t offset_replace, uint64_t offset_field2,
+                           int64_t row0, int64_t* ids_out, float* labels, int64_t* replace_feat_out /* nullable */,
+                           map_stream_t stream);
+
+/* ------------------------------------------------------------------ K5  alias sampler
+ * map_alias_build replaces the O(V) Python loop of AliasMultinomial.__init__ (code/nce/alias_multinomial.py:40-73):
+ * HOST function, float32 arithmetic, same scan order and LIFO stacks => bit-identical tables. */
+int map_alias_build(const float* probs, int64_t V, float* out_prob, int64_t* out_alias);
+/* replaces AliasMultinomial.draw (code/nce/alias_multinomial.py:81-97): out[e] for e in [0,n), Philox element elem0+e */
+int map_alias_draw_philox(const float* prob, const int64_t* alias, int64_t V, uint64_t seed, uint64_t offset,
+                          int64_t elem0, int64_t n, int64_t* out, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K6 / K7  fused NCE head
+ * replaces NCELoss.forward + IndexLinear._compute_sampled_logit + nce_loss / sampled_softmax_loss
+ * (code/nce/nce_loss.py:79-144,201-244, code/nce/index_linear.py:68-106).  Position n reads input[n*P .. n*P+P).
+ * Outputs (ids_out, d_input, acc_count nullable):
+ *   logits[N,K+1]   = <input, emb[idx]> + bias[idx] - norm_term              (nce_loss.py:171-172)
+ *   ids_out[N,K+1]  = [target | noise]                                        (nce_loss.py:138)
+ *   loss_pos[N]     per-position loss (nce: sum_j BCEWithLogits ; sampled: CE with label 0)
+ *   dz[N,K+1]       grad_scale * d(loss_pos[n])/d(logit[n,j])   (grad_scale = 1/N_global for the mean reduction)
+ *   d_input[N,P]    grad_scale * d(loss_pos[n])/d(input[n,:])
+ *   acc_count       += #positions with argmax_j logits == 0                   (models.py:77)
+ * P in {4,8,16,32,64,128}. */
+#define MAP_NCE_LOSS_NCE 0
+#define MAP_NCE_LOSS_SAMPLED 1
+int map_nce_fwd(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
+                const float* emb, const float* bias, const float* logprob_noise, int64_t V, float norm_term,
+                int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos, float* dz,
+                float* d_input, int32_t* acc_count, map_stream_t stream);
+/* sel[n,:] = enc[(b*F + masked_index[n])*P + :], n = b*L + l   (torch.gather of the masked slices, models.py:75) */
+int map_gather_slices(const float* enc, const int64_t* masked_index, int64_t N, int L, int F, int P, float* sel,
+                      map_stream_t stream);
+/* d_enc[(b*F + masked_index[n])*P + :] += d_input[n, :]   (autograd of torch.gather, models.py:75; d_enc pre-zeroed) */
+int map_scatter_add_slices(const float* d_input, const int64_t* masked_index, int64_t N, int L, int F, int P,
+                           float* d_enc, map_stream_t stream);
+/* deterministic mean/sum: out[0] = scale * sum(x[0..n)) */
+int map_reduce_sum_f32(const float* x, int64_t n, float scale, float* out, void* workspace, size_t workspace_bytes,
+                       map_stream_t stream);
+size_t map_reduce_workspace_bytes(int64_t n);
+
+/* ------------------------------------------------------------------ K10  BCE-with-logits heads
+ * replaces BCEWithLogitsLoss + the accuracy / positive-ratio reductions of the RFD head (code/models.py:80-84) and the
+ * CTR loss (code/models.py:91-92).  stats_out[4] = {mean loss, #correct ((sigmoid>0.5)==label), sum(labels), n};
+ * dlogits[i] = (sigmoid(z_i) - y_i)/n. */
+int map_bce_logits_fwd(const float* logits, const float* labels, int64_t n, float* stats_out, float* dlogits,
+                       void* workspace, size_t workspace_bytes, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K11  FM second-order + LR term (DeepFM)
+ * replaces LR.forward (code/models.py:137-143) + InnerProductLayer product_sum (code/layers.py:125-131):
+ * out[b] = sum_f w[ids[b,f]] + lr_bias + 0.5 * sum_d ((sum_f e[b,f,d])^2 - sum_f e[b,f,d]^2) */
+int map_fm_lr_fwd(const float* feat_embed, const int64_t* ids, const float* lr_w, const float* lr_bias, int64_t B,
+                  int F, int D, float* out, int64_t ld_out, map_stream_t stream);
+/* d_embed[b,f,d] (+)= g[b] * (sum_f' e[b,f',d] - e[b,f,d]) ; d_w_occ[b*F+f] = g[b] (per-occurrence LR grad, fed to the
+ * dedup pipeline) ; g has stride ld_g */
+int map_fm_lr_bwd(const float* feat_embed, const float* g, int64_t ld_g, int64_t B, int F, int D, int accumulate,
+                  float* d_embed, float* d_w_occ, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K3 / K4  GEMMs with fused epilogues
+ * replaces every nn.Linear on the path: CrossNetV2 (code/layers.py:195-200), MLPBlock (code/layers.py:179-188),
+ * feat_encoder / pred_rfd / fc_out (code/models.py:116-123,304) forward and backward.
+ *   acc[m,n] = sum_k A[m,k] * B[n,k]                      (C = A . B^T; "transX" describe the storage of A / B)
+ * A: logical [M,K]; trans_a=0 -> stored row-major [M,K] (lda = row stride); trans_a=1 -> stored [K,M].
+ * B: logical [N,K]; trans_b=0 -> stored row-major [N,K] (an nn.Linear weight); trans_b=1 -> stored [K,N]. */
+#define MAP_EPI_NONE 0          /* C = acc */
+#define MAP_EPI_BIAS 1          /* C = acc + bias[n] */
+#define MAP_EPI_BIAS_RELU 2     /* C = relu(acc + bias[n])                       (MLPBlock) */
+#define MAP_EPI_CROSS 3         /* U = acc + bias[n]; aux_out = U; C = aux0 + aux1 * U   (aux0 = Xi, aux1 = X0) */
+#define MAP_EPI_MUL_RELUMASK 4  /* C = acc * (aux0 > 0)                          (dX through a ReLU, aux0 = fwd output) */
+#define MAP_EPI_ADD 5           /* C = acc + aux0                                 (residual gradient) */
+#define MAP_EPI_ADD_MUL 6       /* C = (acc + aux0) * aux1 ; aux_out = (acc + aux0)  (next cross layer's dU from G) */
+typedef struct {
+    int32_t M, N, K;
+    int32_t trans_a, trans_b;
+    int32_t epilogue;
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    const float* bias;
+    const float* aux0; int64_t ld_aux0;
+    const float* aux1; int64_t ld_aux1;
+    float* aux_out; int64_t ld_aux_out;
+} map_gemm_args;
+/* exact fp32 on CUDA cores: skinny shapes (N < 64: pred_rfd.2, fc_out) and the fp32 cross-check of the TF32 path */
+int map_gemm_f32_simt(const map_gemm_args* args, map_stream_t stream);
+/* tcgen05 (kind::tf32) + TMA + TMEM, fp32 accumulate.  Requires 16-byte aligned base pointers and lda/ldb % 4 == 0. */
+int map_gemm_tf32_tcgen05(const map_gemm_args* args, map_stream_t stream);
+/* 1 if map_gemm_tf32_tcgen05 accepts these arguments (shape / alignment), else 0 */
+int map_gemm_tf32_supported(const map_gemm_args* args);
+
+/* column sums: out[n] = sum_m X[m,n]  (bias gradients).  deterministic two-stage. */
+int map_colsum_f32(const float* X, int64_t ldx, int64_t M, int N, float* out, void* workspace, size_t workspace_bytes,
+                   map_stream_t stream);
+size_t map_colsum_workspace_bytes(int64_t M, int N);
+/* CrossNet backward elementwise stage (autograd of layers.py:200):  dU = G * X0 ; dX0_acc (+)= G * U */
+int map_cross_bwd_pre(const float* G, int64_t ldg, const float* X0, int64_t ldx0, const float* U, int64_t ldu,
+                      int64_t M, int N, int accumulate, float* dU, float* dX0_acc, map_stream_t stream);
+/* out = a + b (+ c)  elementwise over [M,N] with row strides */
+int map_add3_f32(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, int64_t M, int N,
+                 float* out, int64_t ldo, map_stream_t stream);
+/* out[N,M] = in[M,N]^T */
+int map_transpose_f32(const float* in, int64_t ld_in, int64_t M, int64_t N, float* out, int64_t ld_out, map_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAP_B200_H */

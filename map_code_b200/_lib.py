@@ -1,0 +1,124 @@
+"""ctypes binding of ``libmap_b200.so`` (C ABI declared in ``include/map_b200.h``).
+
+There is no fallback: if the library is missing or a call fails, this raises.  Build with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C map_code_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmap_b200.so")
+
+MAP_OK, MAP_EINVAL, MAP_ECUDA, MAP_EWORKSPACE, MAP_EUNSUPPORTED = 0, -1, -2, -3, -4
+
+# enums of the header
+SCHED_CONST, SCHED_COSINE = 0, 1
+SAMPLING_RANDINT, SAMPLING_NORMAL = 0, 1
+RFD_MODES = {"Unigram": 0, "Uniform": 1, "Whole-Uniform": 2, "Whole-Unigram": 3}
+NCE_LOSS = {"nce": 0, "sampled": 1}
+EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_CROSS, EPI_MUL_RELUMASK, EPI_ADD, EPI_ADD_MUL = range(7)
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("trans_a", C.c_int32), ("trans_b", C.c_int32), ("epilogue", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64),
+        ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("bias", C.c_void_p),
+        ("aux0", C.c_void_p), ("ld_aux0", C.c_int64),
+        ("aux1", C.c_void_p), ("ld_aux1", C.c_int64),
+        ("aux_out", C.c_void_p), ("ld_aux_out", C.c_int64),
+    ]
+
+
+class AdamwTensor(C.Structure):
+    _fields_ = [
+        ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_t", C.c_void_p),
+        ("n", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("weight_decay", C.c_float), ("pad_", C.c_int32),
+    ]
+
+
+_p, _i, _l, _f, _u64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
+
+# name -> (restype, argtypes).  Kept in the order of include/map_b200.h; tests/test_abi.py checks it against the header.
+PROTOTYPES = {
+    "map_abi_version": (_i, []),
+    "map_last_error": (C.c_char_p, []),
+    "map_sm_count": (_i, [C.POINTER(C.c_int)]),
+    "map_emb_gather_f32": (_i, [_p, _l, _i, _p, _l, _p, _p, _p]),
+    "map_dedup_workspace_bytes": (_sz, [_l]),
+    "map_dedup_ids": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "map_segment_reduce_rows": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _l, _p, _p, _p]),
+    "map_scatter_rows": (_i, [_p, _p, _p, _l, _i, _p, _p]),
+    "map_adamw_hyper_step": (_i, [_p, _p, _f, _f, _f, _f, _i, _l, _l, _p]),
+    "map_adamw_hyper_set": (_i, [_p, _f, _f, _f, _f, _l, _p]),
+    "map_adamw_multi_tensor": (_i, [_p, _i, _l, _p, _p]),
+    "map_adamw_sparse_rows": (_i, [_p, _p, _p, _i, _p, _p, _p, _l, _p, _f, _p]),
+    "map_adamw_dense_rows_sparse_grad": (_i, [_p, _p, _p, _l, _i, _p, _p, _p, _p, _f, _p]),
+    "map_mask_index_philox": (_i, [_p, _l, _i, _i, _i, _u64, _u64, _l, _p]),
+    "map_mfp_mask_apply": (_i, [_p, _p, _l, _i, _i, _l, _p, _p, _p]),
+    "map_rfd_replace_philox": (_i, [_p, _p, _l, _i, _i, _i, _p, _l, _p, _p, _l, _u64, _u64, _u64, _l, _p, _p, _p, _p]),
+    "map_alias_build": (_i, [_p, _l, _p, _p]),
+    "map_alias_draw_philox": (_i, [_p, _p, _l, _u64, _u64, _l, _l, _p, _p]),
+    "map_nce_fwd": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p, _l, _f, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "map_gather_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
+    "map_scatter_add_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
+    "map_reduce_sum_f32": (_i, [_p, _l, _f, _p, _p, _sz, _p]),
+    "map_reduce_workspace_bytes": (_sz, [_l]),
+    "map_bce_logits_fwd": (_i, [_p, _p, _l, _p, _p, _p, _sz, _p]),
+    "map_fm_lr_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _l, _p]),
+    "map_fm_lr_bwd": (_i, [_p, _p, _l, _l, _i, _i, _i, _p, _p, _p]),
+    "map_gemm_f32_simt": (_i, [C.POINTER(GemmArgs), _p]),
+    "map_gemm_tf32_tcgen05": (_i, [C.POINTER(GemmArgs), _p]),
+    "map_gemm_tf32_supported": (_i, [C.POINTER(GemmArgs)]),
+    "map_colsum_f32": (_i, [_p, _l, _l, _i, _p, _p, _sz, _p]),
+    "map_colsum_workspace_bytes": (_sz, [_l, _i]),
+    "map_cross_bwd_pre": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _i, _p, _p, _p]),
+    "map_add3_f32": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _p, _l, _p]),
+    "map_transpose_f32": (_i, [_p, _l, _l, _l, _p, _l, _p]),
+}
+
+_lib = None
+
+
+class MapB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Loads the library once.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MapB200Error(
+            f"{LIB_PATH} not found: the sm_100a kernels are not built (run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'`).  map_code_b200 has no CPU or eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.map_abi_version() != 1:
+        raise MapB200Error(f"ABI version mismatch: library {lib.map_abi_version()} != binding 1")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().map_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args):
+    """Calls an int-returning entry point and raises MapB200Error(map_last_error()) on a non-zero code.
+    MAP_EUNSUPPORTED is raised as NotImplementedError (mirrors the reference's NotImplementedError sites)."""
+    rc = getattr(load(), name)(*args)
+    if rc != MAP_OK:
+        msg = f"{name} failed ({rc}): {last_error()}"
+        if rc == MAP_EUNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise MapB200Error(msg)

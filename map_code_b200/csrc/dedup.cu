@@ -1,0 +1,425 @@
+// K2 (first half): deduplicate ids and reduce per-occurrence row gradients into a compact [U, D] gradient.
+//   radix sort (id, occurrence)  ->  unique ids + segment starts  ->  segmented row sums.
+// Replaces aten::embedding_dense_backward (thrust sort + dense [V,D] grad) behind code/layers.py:98 and the dense
+// index_add behind code/nce/index_linear.py:99-100.  Everything is integer / HBM-L2 bound; no tensor cores.
+#include "common.cuh"
+
+namespace mapb {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadixBins = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per CTA
+constexpr int kSortWarps = kSortThreads / 32;
+
+// ---------------------------------------------------------------------------------------------- sort
+__global__ void __launch_bounds__(256) sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, uint32_t* keys,
+                                                        uint32_t* vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = (uint32_t)ids[i];
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// hist[bin * nblocks + block] = #keys of this CTA's tile whose digit == bin
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
+                                                                 uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t sh[kRadixBins];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int it = 0; it < kSortItems; ++it) {
+        const int64_t i = base + it * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// In-place exclusive scan of `data[0..len)` by ONE CTA of 1024 threads (len <= a few million: bins*nblocks).
+__global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint32_t* data, int64_t len) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each thread owns 4 consecutive elements per chunk of 4096
+    for (int64_t chunk = 0; chunk < len; chunk += 4096) {
+        const int64_t i0 = chunk + (int64_t)threadIdx.x * 4;
+        uint32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = (i0 + k < len) ? data[i0 + k] : 0u;
+        const uint32_t tsum = x[0] + x[1] + x[2] + x[3];
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            warp_tot[lane] = wi - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        uint32_t excl = carry + warp_tot[warp] + (incl - tsum);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < len) data[i0 + k] = excl;
+            excl += x[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl;  // total so far (thread 1023 owns the chunk's last elements)
+        __syncthreads();
+    }
+}
+
+// Stable scatter of one digit.  Order inside a tile is (item round, thread) == ascending index, ranks are computed per
+// warp with match.any and combined across warps/rounds through shared-memory counters.
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                    const uint32_t* __restrict__ vals_in, int64_t n,
+                                                                    int shift, const uint32_t* __restrict__ hist_scanned,
+                                                                    int nblocks, uint32_t* __restrict__ keys_out,
+                                                                    uint32_t* __restrict__ vals_out) {
+    // counts[round][warp][bin] would be 8*8*256*4 = 64 KB; instead process rounds sequentially with a running
+    // per-bin base (bin_base) and per-round per-warp counts (8*256*4 = 8 KB).
+    __shared__ uint32_t warp_cnt[kSortWarps][kRadixBins];
+    __shared__ uint32_t bin_base[kRadixBins];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bin_base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    for (int it = 0; it < kSortItems; ++it) {
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) warp_cnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t i = base + it * kSortThreads + threadIdx.x;
+        const bool valid = i < n;
+        uint32_t key = 0, val = 0;
+        if (valid) {
+            key = keys_in[i];
+            val = vals_in[i];
+        }
+        const uint32_t digit = valid ? ((key >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank_in_warp == 0) warp_cnt[warp][digit] = __popc(peers);
+        __syncthreads();
+        // thread d: exclusive prefix of bin d over the warps of this round, then advance the running base
+        {
+            uint32_t run = bin_base[threadIdx.x];
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const uint32_t c = warp_cnt[w][threadIdx.x];
+                warp_cnt[w][threadIdx.x] = run;
+                run += c;
+            }
+            bin_base[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const uint32_t pos = warp_cnt[warp][digit] + rank_in_warp;
+            keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- unique / segments
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t head_flag(const uint32_t* keys, int64_t i) {
+    return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(kScanThreads) heads_count_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                   uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t sh[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n) c += head_flag(keys, base + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += sh[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) heads_emit_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                  const uint32_t* __restrict__ tile_offsets,
+                                                                  int64_t* __restrict__ uniq_ids,
+                                                                  int32_t* __restrict__ seg_start,
+                                                                  int32_t* __restrict__ n_unique) {
+    __shared__ uint32_t warp_tot[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t f[kScanItems];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        f[k] = (base + k < n) ? head_flag(keys, base + k) : 0u;
+        tsum += f[k];
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    uint32_t u = tile_offsets[blockIdx.x] + woff + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (f[k]) {
+            uniq_ids[u] = (int64_t)keys[base + k];
+            seg_start[u] = (int32_t)(base + k);
+            ++u;
+        }
+        if (base + k == n - 1) {  // the last element closes the list
+            seg_start[u] = (int32_t)n;
+            *n_unique = (int32_t)u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- segmented row sums
+constexpr int kSegTile = 8;  // sorted positions per lane-group; all 8 row loads are issued before the first add
+
+template <int VEC>
+struct RowVec;
+template <>
+struct RowVec<4> {
+    float4 v;
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+    __device__ __forceinline__ void fma(const RowVec& a, float s) {
+        v.x = fmaf(a.v.x, s, v.x); v.y = fmaf(a.v.y, s, v.y); v.z = fmaf(a.v.z, s, v.z); v.w = fmaf(a.v.w, s, v.w);
+    }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+    __device__ __forceinline__ void atomic_add(float* p) const {
+        atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+    }
+};
+template <>
+struct RowVec<1> {
+    float v;
+    __device__ __forceinline__ void zero() { v = 0.f; }
+    __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+    __device__ __forceinline__ void fma(const RowVec& a, float s) { v = fmaf(a.v, s, v); }
+    __device__ __forceinline__ void store(float* p) const { *p = v; }
+    __device__ __forceinline__ void atomic_add(float* p) const { atomicAdd(p, v); }
+};
+
+// One group of `lanes` threads (lanes = D / VEC) walks kSegTile consecutive sorted positions.  A segment that lies
+// entirely inside the tile is written with a plain store; segments that straddle tiles (hot ids such as <mask>=3) are
+// combined with atomics into the pre-zeroed compact gradient: at most 2 atomics per tile per lane.
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __restrict__ rows, int64_t ld_rows, int lanes,
+                                                             const float* __restrict__ scale, int group,
+                                                             const int32_t* __restrict__ occ_sorted,
+                                                             const int32_t* __restrict__ seg_start,
+                                                             const int32_t* __restrict__ n_unique, int64_t n,
+                                                             float* __restrict__ grad, float* __restrict__ scalar_out,
+                                                             int D) {
+    const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tile = gthread / lanes;
+    const int lane = (int)(gthread - tile * lanes);
+    const int64_t t0 = tile * kSegTile;
+    if (t0 >= n) return;
+    const int64_t t1 = (t0 + kSegTile < n) ? t0 + kSegTile : n;
+    const int U = *n_unique;
+    // segment containing t0: largest s with seg_start[s] <= t0
+    int lo = 0, hi = U - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+    }
+    int s = lo;
+    int64_t s_end = seg_start[s + 1];
+
+    RowVec<VEC> r[kSegTile];
+    float sc[kSegTile];
+#pragma unroll
+    for (int k = 0; k < kSegTile; ++k) {
+        sc[k] = 0.f;
+        r[k].zero();
+        if (t0 + k < t1) {
+            const int64_t occ = occ_sorted[t0 + k];
+            sc[k] = (scale != nullptr) ? __ldg(scale + occ) : 1.f;
+            r[k].load(rows + (occ / group) * ld_rows + lane * VEC);
+        }
+    }
+    RowVec<VEC> acc;
+    acc.zero();
+    float sacc = 0.f;
+    int64_t seg_first_pos = (int64_t)seg_start[s];
+#pragma unroll
+    for (int k = 0; k < kSegTile; ++k) {
+        const int64_t pos = t0 + k;
+        if (pos < t1) {
+            acc.fma(r[k], sc[k]);
+            sacc += sc[k];
+            if (pos + 1 == s_end || pos + 1 == t1) {  // flush
+                const bool whole = (seg_first_pos >= t0) && (s_end <= t1);
+                float* dst = grad + (int64_t)s * D + lane * VEC;
+                if (whole) acc.store(dst); else acc.atomic_add(dst);
+                if (scalar_out != nullptr && lane == 0) {
+                    if (whole) scalar_out[s] = sacc; else atomicAdd(scalar_out + s, sacc);
+                }
+                acc.zero();
+                sacc = 0.f;
+                if (pos + 1 == s_end && pos + 1 < t1) {
+                    ++s;
+                    seg_first_pos = s_end;
+                    s_end = seg_start[s + 1];
+                }
+            }
+        }
+    }
+}
+
+// zero the first U rows of the compact gradient (only these can be touched by atomics)
+__global__ void __launch_bounds__(256) zero_unique_rows_kernel(float* grad, float* scalar_out, int D,
+                                                               const int32_t* __restrict__ n_unique, int64_t max_elems) {
+    const int64_t U = *n_unique;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U * D && i < max_elems; i += stride) grad[i] = 0.f;
+    if (scalar_out != nullptr)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += stride) scalar_out[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ grad, const int64_t* __restrict__ uniq,
+                                                           const int32_t* __restrict__ n_unique, int D,
+                                                           float* __restrict__ dense) {
+    const int64_t U = *n_unique;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U * D; i += stride) {
+        const int64_t u = i / D;
+        dense[uniq[u] * D + (i - u * D)] = grad[i];
+    }
+}
+
+struct DedupLayout {
+    size_t keys_a, keys_b, vals_a, hist, tiles, total;
+    int nblocks_sort, nblocks_scan;
+};
+static DedupLayout dedup_layout(int64_t n) {
+    DedupLayout L;
+    L.nblocks_sort = (int)ceil_div(n > 0 ? n : 1, kSortTile);
+    L.nblocks_scan = (int)ceil_div(n > 0 ? n : 1, kScanTile);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    L.keys_a = off; off += align((size_t)n * 4);
+    L.keys_b = off; off += align((size_t)n * 4);
+    L.vals_a = off; off += align((size_t)n * 4);
+    L.hist = off; off += align((size_t)kRadixBins * L.nblocks_sort * 4);
+    L.tiles = off; off += align((size_t)(L.nblocks_scan + 1) * 4);
+    L.total = off;
+    return L;
+}
+
+}  // namespace mapb
+
+extern "C" size_t map_dedup_workspace_bytes(int64_t n_ids) { return mapb::dedup_layout(n_ids).total; }
+
+extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_t* uniq_ids, int32_t* seg_start,
+                             int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,
+                             map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(ids && uniq_ids && seg_start && occ_sorted && n_unique && workspace, "map_dedup_ids: null pointer");
+    MAP_REQUIRE(n > 0 && n < (int64_t)1 << 31, "map_dedup_ids: n=%lld out of range", (long long)n);
+    MAP_REQUIRE(key_bits >= 1 && key_bits <= 32, "map_dedup_ids: key_bits=%d", key_bits);
+    const DedupLayout L = dedup_layout(n);
+    if (workspace_bytes < L.total) {
+        set_error("map_dedup_ids: workspace %zu < %zu", workspace_bytes, L.total);
+        return MAP_EWORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    char* ws = static_cast<char*>(workspace);
+    uint32_t* keys_a = reinterpret_cast<uint32_t*>(ws + L.keys_a);
+    uint32_t* keys_b = reinterpret_cast<uint32_t*>(ws + L.keys_b);
+    uint32_t* vals_a = reinterpret_cast<uint32_t*>(ws + L.vals_a);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + L.hist);
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(ws + L.tiles);
+    uint32_t* occ = reinterpret_cast<uint32_t*>(occ_sorted);
+    const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+    // ping-pong so that the final values land in occ_sorted
+    uint32_t* vin = (passes % 2 == 0) ? occ : vals_a;
+    uint32_t* vout = (passes % 2 == 0) ? vals_a : occ;
+    uint32_t* kin = keys_a;
+    uint32_t* kout = keys_b;
+    sort_prep_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ids, n, kin, vin);
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * kRadixBits;
+        sort_hist_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, n, shift, hist, L.nblocks_sort);
+        scan_single_cta_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)kRadixBins * L.nblocks_sort);
+        sort_scatter_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, vin, n, shift, hist, L.nblocks_sort, kout, vout);
+        uint32_t* t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    // kin now holds the sorted keys, vin == occ_sorted
+    heads_count_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, tiles);
+    scan_single_cta_kernel<<<1, 1024, 0, st>>>(tiles, L.nblocks_scan);
+    heads_emit_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, tiles, uniq_ids, seg_start, n_unique);
+    return check_launch("map_dedup_ids");
+}
+
+extern "C" int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
+                                       const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
+                                       int64_t n_ids, float* grad_compact, float* scalar_out, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(rows && occ_sorted && seg_start && n_unique && grad_compact, "map_segment_reduce_rows: null pointer");
+    MAP_REQUIRE(D >= 1 && group >= 1 && n_ids > 0, "map_segment_reduce_rows: bad shape D=%d group=%d n=%lld", D, group, (long long)n_ids);
+    cudaStream_t st = as_stream(stream);
+    const bool vec = (D % 4 == 0) && (ld_rows % 4 == 0) && ((uintptr_t)rows % 16 == 0) && ((uintptr_t)grad_compact % 16 == 0);
+    const int lanes = vec ? D / 4 : D;
+    const int64_t max_elems = n_ids * D;
+    {
+        int64_t blocks = ceil_div(max_elems, 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        zero_unique_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad_compact, scalar_out, D, n_unique, max_elems);
+    }
+    const int64_t tiles = ceil_div(n_ids, kSegTile);
+    const int64_t threads = tiles * lanes;
+    const unsigned blocks = (unsigned)ceil_div(threads, 256);
+    if (vec)
+        segment_reduce_kernel<4><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique,
+                                                         n_ids, grad_compact, scalar_out, D);
+    else
+        segment_reduce_kernel<1><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique,
+                                                         n_ids, grad_compact, scalar_out, D);
+    return check_launch("map_segment_reduce_rows");
+}
+
+extern "C" int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const int32_t* n_unique,
+                                int64_t max_unique, int D, float* dense, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(grad_compact && uniq_ids && n_unique && dense && D >= 1, "map_scatter_rows: bad argument");
+    int64_t blocks = ceil_div(max_unique * D, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    scatter_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(grad_compact, uniq_ids, n_unique, D, dense);
+    return check_launch("map_scatter_rows");
+}

@@ -1,0 +1,480 @@
+// K3 / K4: TF32 tensor-core GEMM for sm_100a — tcgen05.mma (kind::tf32, cta_group::1) fed by TMA, accumulator in TMEM,
+// fused epilogues (bias / ReLU / CrossNet / ReLU-mask / residual) read back with tcgen05.ld.
+// Replaces the cuBLAS sgemm behind every nn.Linear of the step (code/layers.py:179-200, code/models.py:116-123), forward
+// and backward:   acc[m,n] = sum_k A[m,k] * B[n,k]
+//   forward  Y  = X  . W^T      A = X  (K-major)            B = W  [N,K] (K-major)
+//   dgrad    dX = dY . W        A = dY (K-major)            B = W  [N,K] read as [K_red=N][N_out=K]  -> trans_b = 1 (MN-major)
+//   wgrad    dW = dY^T . X      A = dY [M,N] read transposed -> trans_a = 1 ; B = X [M,K] read transposed -> trans_b = 1
+// Both majors are consumed straight from the row-major fp32 tensors: K-major tiles are [rows][32 floats] TMA boxes,
+// MN-major tiles are [32 k-rows][32 floats] boxes; all boxes are 128 bytes wide with the 128B swizzle that the UMMA
+// shared-memory descriptor names, so no transposed copies and no conversion passes exist anywhere in the step.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue (TMEM lane quarter = warp%4).
+// One 128 x BLOCK_N output tile per CTA (BLOCK_N runtime, multiple of 16, <= 256, chosen on the host so that the tile count
+// lands on a multiple of the 148 SMs); 2 CTAs are co-resident per SM whenever the stage ring fits in half the shared
+// memory, so one CTA's epilogue overlaps the other's main loop.  Small wgrad grids use split-K with fp32 red.global.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mapb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;               // 32 fp32 = 128 bytes = one swizzle span
+constexpr int kUmmaK = 8;                 // tf32: 32 bytes of K per tcgen05.mma
+constexpr int kGemmThreads = 192;
+constexpr int kATileBytes = kBlockM * kBlockK * 4;  // 16 KiB
+constexpr int kMaxStages = 8;
+
+struct GemmParams {
+    int M, N, K;
+    int block_n;          // multiple of 16
+    int trans_a, trans_b;
+    int num_k_blocks;     // per split
+    int k_blocks_total;
+    int stages;
+    int stage_bytes;      // A tile + B tile, multiple of 1024
+    int b_tile_bytes;
+    int tmem_cols;        // power of two >= block_n, >= 32
+    int epilogue;
+    int split_k;
+    float* C; int64_t ldc;
+    const float* bias;
+    const float* aux0; int64_t ld_aux0;
+    const float* aux1; int64_t ld_aux1;
+    float* aux_out; int64_t ld_aux_out;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A mis-programmed pipeline must not hang the GPU: after ~2 s of SM clocks the CTA traps (the launch then reports an
+// error through the normal CUDA error path) instead of spinning forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("map_gemm_tf32_tcgen05: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {  // arrives on `bar` when all prior tcgen05.mma retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], M = 128, N = block_n, K = 8 (tf32)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// UMMA shared-memory descriptor (PTX ISA "tcgen05 matrix descriptor"): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46)
+// | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 [4,6)=1 | A=tf32 [7,10)=2 | B=tf32 [10,13)=2 | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int block_n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue on 4 columns
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int n, float4 acc) {
+    float4 out = acc;
+    switch (p.epilogue) {
+        case MAP_EPI_BIAS: {
+            const float4 b = ld4(p.bias + n);
+            out = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
+        } break;
+        case MAP_EPI_BIAS_RELU: {
+            const float4 b = ld4(p.bias + n);
+            out = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f));
+        } break;
+        case MAP_EPI_CROSS: {
+            const float4 b = ld4(p.bias + n);
+            const float4 xi = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
+            const float4 x0 = ld4(p.aux1 + (int64_t)m * p.ld_aux1 + n);
+            const float4 u = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
+            *reinterpret_cast<float4*>(p.aux_out + (int64_t)m * p.ld_aux_out + n) = u;
+            out = make_float4(fmaf(x0.x, u.x, xi.x), fmaf(x0.y, u.y, xi.y), fmaf(x0.z, u.z, xi.z), fmaf(x0.w, u.w, xi.w));
+        } break;
+        case MAP_EPI_MUL_RELUMASK: {
+            const float4 y = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
+            out = make_float4(y.x > 0.f ? acc.x : 0.f, y.y > 0.f ? acc.y : 0.f, y.z > 0.f ? acc.z : 0.f, y.w > 0.f ? acc.w : 0.f);
+        } break;
+        case MAP_EPI_ADD: {
+            const float4 r = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
+            out = make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
+        } break;
+        case MAP_EPI_ADD_MUL: {
+            const float4 r = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
+            const float4 x = ld4(p.aux1 + (int64_t)m * p.ld_aux1 + n);
+            const float4 s = make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
+            *reinterpret_cast<float4*>(p.aux_out + (int64_t)m * p.ld_aux_out + n) = s;
+            out = make_float4(s.x * x.x, s.y * x.y, s.z * x.z, s.w * x.w);
+        } break;
+        default: break;
+    }
+    float* dst = p.C + (int64_t)m * p.ldc + n;
+    if (p.split_k > 1) {  // partial sums of a K split: fp32 reductions into the pre-zeroed output (EPI_NONE only)
+        atomicAdd(dst + 0, out.x); atomicAdd(dst + 1, out.y); atomicAdd(dst + 2, out.z); atomicAdd(dst + 3, out.w);
+    } else {
+        *reinterpret_cast<float4*>(dst) = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                         const __grid_constant__ CUtensorMap tmap_b,
+                                                                         const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte aligned tile ring (the 128B swizzle pattern is anchored to 1024-byte boundaries)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kBlockM;
+    const int n0 = blockIdx.x * p.block_n;
+    const int kb0 = blockIdx.z * p.num_k_blocks;
+    int nkb = p.k_blocks_total - kb0;
+    if (nkb > p.num_k_blocks) nkb = p.num_k_blocks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(kATileBytes + p.b_tile_bytes);
+            const int b_chunks = (p.block_n + 31) >> 5;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t round = (uint32_t)(i / p.stages);
+                mbar_wait(smem_u32(&empty_bar[s]), (round & 1u) ^ 1u);  // first pass through the ring falls through
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, tx_bytes);
+                const uint32_t a_dst = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                const uint32_t b_dst = a_dst + kATileBytes;
+                const int k0 = (kb0 + i) * kBlockK;
+                if (!p.trans_a) {
+                    tma_load_2d(a_dst, &tmap_a, fb, k0, m0);                       // box {32 k, 128 m}
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kBlockM / 32; ++c) tma_load_2d(a_dst + c * 4096, &tmap_a, fb, m0 + c * 32, k0);  // box {32 m, 32 k}
+                }
+                if (!p.trans_b) {
+                    tma_load_2d(b_dst, &tmap_b, fb, k0, n0);                       // box {32 k, block_n n}
+                } else {
+                    for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * 4096, &tmap_b, fb, n0 + c * 32, k0);      // box {32 n, 32 k}
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(p.block_n, p.trans_a, p.trans_b);
+            // K-major  : 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of every row -> advance start by 32 B
+            // MN-major : 32-float chunks 4096 B apart (LBO); 8-k-row groups 1024 B apart (SBO) -> advance start by 1024 B
+            const uint32_t a_lbo = p.trans_a ? 4096u : 16u, a_sbo = 1024u, a_adv = p.trans_a ? 1024u : 32u;
+            const uint32_t b_lbo = p.trans_b ? 4096u : 16u, b_sbo = 1024u, b_adv = p.trans_b ? 1024u : 32u;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t round = (uint32_t)(i / p.stages);
+                mbar_wait(smem_u32(&full_bar[s]), round & 1u);
+                tcgen05_fence_after();
+                const uint32_t a_src = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                const uint32_t b_src = a_src + kATileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint64_t da = make_smem_desc(a_src + k * a_adv, a_lbo, a_sbo);
+                    const uint64_t db = make_smem_desc(b_src + k * b_adv, b_lbo, b_sbo);
+                    umma_tf32(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+                }
+                tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs have read it
+            }
+            tcgen05_commit(smem_u32(&tmem_full_bar));     // accumulator complete
+        }
+    } else {
+        // ===================== epilogue warps: TMEM -> registers -> fused epilogue -> global =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;       // output row owned by this thread
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tcgen05_fence_after();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        int c = 0;
+        for (; c + 32 <= p.block_n; c += 32) {
+            float v[32];
+            tmem_ld_x32(lane_addr + (uint32_t)c, v);
+            if (m < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c + j;
+                    if (n < p.N) epilogue_store4(p, m, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            }
+        }
+        if (c < p.block_n) {  // block_n % 32 == 16
+            float v[16];
+            tmem_ld_x16(lane_addr + (uint32_t)c, v);
+            if (m < p.M) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const int n = n0 + c + j;
+                    if (n < p.N) epilogue_store4(p, m, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows of `ld` floats; box = {32 floats, box_rows}
+static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) {
+        set_error("map_gemm_tf32_tcgen05: cuTensorMapEncodeTiled is not available from the driver");
+        return MAP_ECUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("map_gemm_tf32_tcgen05: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box_rows=%d", (int)r,
+                  (long long)inner, (long long)outer, (long long)ld, box_rows);
+        return MAP_ECUDA;
+    }
+    return MAP_OK;
+}
+
+int validate_gemm_args(const map_gemm_args* g, const char* who);  // gemm_simt.cu
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static int tf32_supported(const map_gemm_args* g, bool set_msg) {
+#define UNSUP(...)                       \
+    do {                                 \
+        if (set_msg) set_error(__VA_ARGS__); \
+        return 0;                        \
+    } while (0)
+    if (g->N % 4 != 0 || g->N < 16) UNSUP("map_gemm_tf32_tcgen05: N=%d must be a multiple of 4 and >= 16", g->N);
+    if (g->lda % 4 != 0 || g->ldb % 4 != 0 || g->ldc % 4 != 0) UNSUP("map_gemm_tf32_tcgen05: lda/ldb/ldc must be multiples of 4 floats");
+    if (!aligned16(g->A) || !aligned16(g->B) || !aligned16(g->C)) UNSUP("map_gemm_tf32_tcgen05: A/B/C must be 16-byte aligned");
+    if (g->bias && !aligned16(g->bias)) UNSUP("map_gemm_tf32_tcgen05: bias must be 16-byte aligned");
+    if (g->aux0 && (!aligned16(g->aux0) || g->ld_aux0 % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux0 alignment");
+    if (g->aux1 && (!aligned16(g->aux1) || g->ld_aux1 % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux1 alignment");
+    if (g->aux_out && (!aligned16(g->aux_out) || g->ld_aux_out % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux_out alignment");
+#undef UNSUP
+    return 1;
+}
+
+// BLOCK_N so that (#m-tiles * #n-tiles) lands close to a multiple of the SM count without wasting columns
+static int choose_block_n(int M, int N, bool mn_major_b) {
+    const int m_tiles = (int)ceil_div(M, kBlockM);
+    const int step = mn_major_b ? 32 : 16;  // MN-major B tiles are made of 32-float chunks
+    int best_bn = 128;
+    double best_cost = 1e30;
+    for (int bn = step; bn <= 256; bn += step) {
+        const int n_tiles = (int)ceil_div(N, bn);
+        const int tiles = m_tiles * n_tiles;
+        const int slots = (bn <= 128) ? 2 * kNumSMs : kNumSMs;  // co-resident CTAs (see stage sizing)
+        const int waves = (int)ceil_div(tiles, slots);
+        // time ~ waves * (per-tile work) ; per-tile work ~ bn (MMA) with a floor for operand traffic (A tile is reloaded per n-tile)
+        const double per_tile = (double)bn + 48.0;
+        const double per_wave = (bn <= 128) ? 2.0 * per_tile : per_tile;   // two co-resident CTAs share one SM's tensor pipe
+        const double cost = waves * per_wave;
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best_bn = bn;
+        }
+    }
+    return best_bn;
+}
+
+}  // namespace mapb
+
+extern "C" int map_gemm_tf32_supported(const map_gemm_args* args) {
+    if (args == nullptr || args->M <= 0 || args->N <= 0 || args->K <= 0) return 0;
+    return mapb::tf32_supported(args, false);
+}
+
+extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream) {
+    using namespace mapb;
+    int rc = validate_gemm_args(g, "map_gemm_tf32_tcgen05");
+    if (rc != MAP_OK) return rc;
+    if (!tf32_supported(g, true)) return MAP_EUNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+
+    GemmParams p{};
+    p.M = g->M; p.N = g->N; p.K = g->K;
+    p.trans_a = g->trans_a ? 1 : 0;
+    p.trans_b = g->trans_b ? 1 : 0;
+    p.block_n = choose_block_n(g->M, g->N, p.trans_b != 0);
+    p.epilogue = g->epilogue;
+    p.C = g->C; p.ldc = g->ldc;
+    p.bias = g->bias;
+    p.aux0 = g->aux0; p.ld_aux0 = g->ld_aux0;
+    p.aux1 = g->aux1; p.ld_aux1 = g->ld_aux1;
+    p.aux_out = g->aux_out; p.ld_aux_out = g->ld_aux_out;
+    p.b_tile_bytes = p.trans_b ? ((p.block_n + 31) / 32) * 4096 : p.block_n * 128;
+    p.stage_bytes = (kATileBytes + p.b_tile_bytes + 1023) & ~1023;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
+    p.k_blocks_total = (int)ceil_div(g->K, kBlockK);
+
+    const int m_tiles = (int)ceil_div(g->M, kBlockM);
+    const int n_tiles = (int)ceil_div(g->N, p.block_n);
+    // split-K for small output grids with a long reduction (wgrad): partial tiles are reduced with fp32 atomics
+    p.split_k = 1;
+    if (g->epilogue == MAP_EPI_NONE && m_tiles * n_tiles < kNumSMs && p.k_blocks_total >= 32) {
+        int s = (2 * kNumSMs) / (m_tiles * n_tiles);
+        if (s > p.k_blocks_total / 8) s = p.k_blocks_total / 8;
+        if (s > 16) s = 16;
+        if (s > 1) p.split_k = s;
+    }
+    p.num_k_blocks = (int)ceil_div(p.k_blocks_total, p.split_k);
+    p.split_k = (int)ceil_div(p.k_blocks_total, p.num_k_blocks);
+
+    // stage ring: aim for two co-resident CTAs (<= ~110 KB each); otherwise one CTA with a deeper ring
+    const int budget2 = 110 * 1024, budget1 = 220 * 1024;
+    int stages = budget2 / p.stage_bytes;
+    if (stages < 3) stages = budget1 / p.stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > p.num_k_blocks) stages = p.num_k_blocks > 1 ? p.num_k_blocks : 1;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024;  // + alignment slack
+
+    CUtensorMap tmap_a, tmap_b;
+    if (!p.trans_a) rc = make_tmap(&tmap_a, g->A, g->K, g->M, g->lda, kBlockM);     // [M rows][K contiguous]
+    else rc = make_tmap(&tmap_a, g->A, g->M, g->K, g->lda, kBlockK);                // [K rows][M contiguous]
+    if (rc != MAP_OK) return rc;
+    if (!p.trans_b) rc = make_tmap(&tmap_b, g->B, g->K, g->N, g->ldb, p.block_n);   // [N rows][K contiguous]
+    else rc = make_tmap(&tmap_b, g->B, g->N, g->K, g->ldb, kBlockK);                // [K rows][N contiguous]
+    if (rc != MAP_OK) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048) != cudaSuccess) {
+            set_error("map_gemm_tf32_tcgen05: cannot raise dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+            return MAP_ECUDA;
+        }
+        attr_set = true;
+    }
+    if (p.split_k > 1) {
+        if (cudaMemset2DAsync(g->C, (size_t)g->ldc * sizeof(float), 0, (size_t)g->N * sizeof(float), (size_t)g->M, st) != cudaSuccess) {
+            set_error("map_gemm_tf32_tcgen05: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MAP_ECUDA;
+        }
+    }
+    dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)p.split_k);
+    gemm_tf32_tcgen05_kernel<<<grid, kGemmThreads, smem_bytes, st>>>(tmap_a, tmap_b, p);
+    return check_launch("map_gemm_tf32_tcgen05");
+}

@@ -1,0 +1,359 @@
+"""Functional wrappers: torch CUDA tensors in, C-ABI kernel launches on torch's current stream, torch tensors out.
+
+torch is plumbing here (device memory + streams); every device operation below is one of our sm_100a kernels.
+All functions are CUDA-graph capturable when the caller supplies the output / workspace tensors (`out=` arguments).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, call
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check(t: torch.Tensor, dtype, name: str, contiguous: bool = True):
+    if not t.is_cuda:
+        raise _lib.MapB200Error(f"{name}: expected a CUDA tensor (map_code_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def key_bits(V: int) -> int:
+    return max(1, int(V - 1).bit_length())
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None,
+               oob_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check(table, torch.float32, "table")
+    _check(ids, torch.int64, "ids")
+    V, D = table.shape
+    if out is None:
+        out = torch.empty(*ids.shape, D, dtype=torch.float32, device=table.device)
+    call("map_emb_gather_f32", table.data_ptr(), V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), _ptr(oob_flag), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K2
+class DedupPlan:
+    """Pre-allocated buffers for the dedup pipeline of one id stream of fixed length n (graph-capturable)."""
+
+    def __init__(self, n: int, V: int, device):
+        self.n, self.V = int(n), int(V)
+        self.key_bits = key_bits(V)
+        self.uniq = torch.empty(self.n, dtype=torch.int64, device=device)
+        self.seg_start = torch.empty(self.n + 1, dtype=torch.int32, device=device)
+        self.occ_sorted = torch.empty(self.n, dtype=torch.int32, device=device)
+        self.n_unique = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ws_bytes = int(_lib.load().map_dedup_workspace_bytes(self.n))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+
+    def run(self, ids: torch.Tensor):
+        _check(ids, torch.int64, "ids")
+        assert ids.numel() == self.n
+        call("map_dedup_ids", ids.data_ptr(), self.n, self.key_bits, self.uniq.data_ptr(), self.seg_start.data_ptr(),
+             self.occ_sorted.data_ptr(), self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws_bytes, _stream())
+        return self
+
+    def reduce_rows(self, rows: torch.Tensor, D: int, ld_rows: Optional[int] = None, scale: Optional[torch.Tensor] = None,
+                    group: int = 1, out: Optional[torch.Tensor] = None, scalar_out: Optional[torch.Tensor] = None):
+        if out is None:
+            out = torch.empty(self.n, D, dtype=torch.float32, device=rows.device)
+        call("map_segment_reduce_rows", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
+             self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, out.data_ptr(),
+             _ptr(scalar_out), _stream())
+        return out
+
+    def scatter_dense(self, grad_compact: torch.Tensor, D: int, dense: torch.Tensor):
+        call("map_scatter_rows", grad_compact.data_ptr(), self.uniq.data_ptr(), self.n_unique.data_ptr(), self.n, D,
+             dense.data_ptr(), _stream())
+        return dense
+
+
+# ------------------------------------------------------------------------------------------------ AdamW
+def adamw_hyper_step(hyper, step_counter, base_lr, beta1, beta2, eps, sched: int, warmup: int, total: int):
+    call("map_adamw_hyper_step", hyper.data_ptr(), step_counter.data_ptr(), base_lr, beta1, beta2, eps, sched, warmup, total, _stream())
+
+
+def adamw_hyper_set(hyper, lr, beta1, beta2, eps, step: int):
+    call("map_adamw_hyper_set", hyper.data_ptr(), lr, beta1, beta2, eps, step, _stream())
+
+
+def make_adamw_tensor_list(entries, device) -> Tuple[torch.Tensor, int, int]:
+    """entries: list of (p, g, m, v, weight_decay, p_t or None).  Returns (device descriptor table, n, max_elems)."""
+    arr = (_lib.AdamwTensor * len(entries))()
+    mx = 1
+    for i, (p, g, m, v, wd, p_t) in enumerate(entries):
+        for t in (p, g, m, v):
+            _check(t, torch.float32, "adamw tensor")
+        rows, cols = (p.shape[0], p.shape[1]) if (p_t is not None) else (0, 0)
+        arr[i] = _lib.AdamwTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_t), p.numel(), rows, cols,
+                                  float(wd), 0)
+        mx = max(mx, p.numel())
+    raw = bytes(arr)
+    table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    return table, len(entries), mx
+
+
+def adamw_multi_tensor(table: torch.Tensor, n: int, max_elems: int, hyper: torch.Tensor):
+    call("map_adamw_multi_tensor", table.data_ptr(), n, max_elems, hyper.data_ptr(), _stream())
+
+
+def adamw_sparse_rows(table, m, v, plan: DedupPlan, grad_compact, hyper, weight_decay: float):
+    D = table.shape[1]
+    call("map_adamw_sparse_rows", table.data_ptr(), m.data_ptr(), v.data_ptr(), D, plan.uniq.data_ptr(), grad_compact.data_ptr(),
+         plan.n_unique.data_ptr(), plan.n, hyper.data_ptr(), float(weight_decay), _stream())
+
+
+def adamw_dense_rows_sparse_grad(table, m, v, plan: DedupPlan, grad_compact, hyper, weight_decay: float):
+    V, D = table.shape
+    call("map_adamw_dense_rows_sparse_grad", table.data_ptr(), m.data_ptr(), v.data_ptr(), V, D, plan.uniq.data_ptr(),
+         grad_compact.data_ptr(), plan.n_unique.data_ptr(), hyper.data_ptr(), float(weight_decay), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ K8 / K9
+def mask_index(B: int, L: int, F: int, sampling_method: str, seed: int, offset: int, row0: int = 0, device="cuda",
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if sampling_method == "randint":
+        sm = _lib.SAMPLING_RANDINT
+    elif sampling_method == "normal":
+        sm = _lib.SAMPLING_NORMAL
+    else:
+        raise NotImplementedError(sampling_method)  # reference: trainer.py:226-227
+    if out is None:
+        out = torch.empty(B, L, dtype=torch.int64, device=device)
+    call("map_mask_index_philox", out.data_ptr(), B, L, F, sm, seed, offset, row0, _stream())
+    return out
+
+
+def mfp_mask_apply(ids: torch.Tensor, masked_index: torch.Tensor, mask_id: int = 3, ids_out=None, labels=None):
+    _check(ids, torch.int64, "ids")
+    _check(masked_index, torch.int64, "masked_index")
+    B, F = ids.shape
+    L = masked_index.shape[1]
+    if ids_out is None:
+        ids_out = torch.empty_like(ids)
+    if labels is None:
+        labels = torch.empty(B, L, dtype=torch.int64, device=ids.device)
+    call("map_mfp_mask_apply", ids.data_ptr(), masked_index.data_ptr(), B, F, L, mask_id, ids_out.data_ptr(), labels.data_ptr(), _stream())
+    return ids_out, labels
+
+
+def rfd_replace(ids, masked_index, mode: str, seed: int, offset_replace: int, offset_field2: int = 0, x_train=None,
+                idx_low=None, idx_high=None, input_size: int = 0, row0: int = 0, ids_out=None, labels=None, replace_out=None):
+    if mode not in _lib.RFD_MODES:
+        raise NotImplementedError(mode)  # reference: trainer.py:261-262
+    _check(ids, torch.int64, "ids")
+    _check(masked_index, torch.int64, "masked_index")
+    B, F = ids.shape
+    L = masked_index.shape[1]
+    if ids_out is None:
+        ids_out = torch.empty_like(ids)
+    if labels is None:
+        labels = torch.empty(B, F, dtype=torch.float32, device=ids.device)
+    n_train = 0 if x_train is None else x_train.shape[0]
+    call("map_rfd_replace_philox", ids.data_ptr(), masked_index.data_ptr(), B, F, L, _lib.RFD_MODES[mode], _ptr(x_train), n_train,
+         _ptr(idx_low), _ptr(idx_high), input_size, seed, offset_replace, offset_field2, row0, ids_out.data_ptr(),
+         labels.data_ptr(), _ptr(replace_out), _stream())
+    return ids_out, labels
+
+
+# ------------------------------------------------------------------------------------------------ K5
+def alias_build(probs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """HOST function of the library (native Vose builder, bit-identical to the reference's Python loop)."""
+    p = probs.detach().to("cpu", torch.float32).contiguous()
+    V = p.numel()
+    prob = torch.empty(V, dtype=torch.float32)
+    alias = torch.empty(V, dtype=torch.int64)
+    call("map_alias_build", p.data_ptr(), V, prob.data_ptr(), alias.data_ptr())
+    return prob, alias
+
+
+def alias_draw(prob: torch.Tensor, alias: torch.Tensor, seed: int, offset: int, n: int, elem0: int = 0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check(prob, torch.float32, "prob")
+    _check(alias, torch.int64, "alias")
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=prob.device)
+    call("map_alias_draw_philox", prob.data_ptr(), alias.data_ptr(), prob.numel(), seed, offset, elem0, n, out.data_ptr(), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K6 / K7
+def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: str = "nce", grad_scale: Optional[float] = None,
+            logits=None, ids_out=None, loss_pos=None, dz=None, d_input=None, acc_count=None, want_ids=True, want_d_input=True):
+    """inp [N,P]; target [N]; noise [N,K].  Returns (logits [N,K+1], ids [N,K+1] | None, loss_pos [N], dz [N,K+1], d_input | None)."""
+    if loss_type not in _lib.NCE_LOSS:
+        raise NotImplementedError(f"loss type {loss_type} not implemented")  # reference: nce_loss.py:126-132
+    _check(inp, torch.float32, "input")
+    _check(target, torch.int64, "target")
+    _check(noise, torch.int64, "noise")
+    N, P = inp.shape
+    K = noise.shape[-1]
+    dev = inp.device
+    if logits is None:
+        logits = torch.empty(N, K + 1, dtype=torch.float32, device=dev)
+    if ids_out is None and want_ids:
+        ids_out = torch.empty(N, K + 1, dtype=torch.int64, device=dev)
+    if loss_pos is None:
+        loss_pos = torch.empty(N, dtype=torch.float32, device=dev)
+    if dz is None:
+        dz = torch.empty(N, K + 1, dtype=torch.float32, device=dev)
+    if d_input is None and want_d_input:
+        d_input = torch.empty(N, P, dtype=torch.float32, device=dev)
+    if grad_scale is None:
+        grad_scale = 1.0 / max(N, 1)
+    call("map_nce_fwd", inp.data_ptr(), N, P, K, target.data_ptr(), noise.data_ptr(), emb.data_ptr(), bias.data_ptr(),
+         logq.data_ptr(), emb.shape[0], float(norm_term), _lib.NCE_LOSS[loss_type], float(grad_scale), logits.data_ptr(),
+         _ptr(ids_out), loss_pos.data_ptr(), dz.data_ptr(), _ptr(d_input), _ptr(acc_count), _stream())
+    return logits, ids_out, loss_pos, dz, d_input
+
+
+def gather_slices(enc: torch.Tensor, masked_index: torch.Tensor, F: int, P: int, out=None) -> torch.Tensor:
+    B, L = masked_index.shape
+    if out is None:
+        out = torch.empty(B * L, P, dtype=torch.float32, device=enc.device)
+    call("map_gather_slices", enc.data_ptr(), masked_index.data_ptr(), B * L, L, F, P, out.data_ptr(), _stream())
+    return out
+
+
+def scatter_add_slices(d_sel: torch.Tensor, masked_index: torch.Tensor, F: int, P: int, d_enc: torch.Tensor):
+    B, L = masked_index.shape
+    call("map_scatter_add_slices", d_sel.data_ptr(), masked_index.data_ptr(), B * L, L, F, P, d_enc.data_ptr(), _stream())
+    return d_enc
+
+
+_red_ws = {}
+
+
+def _reduce_ws(device):
+    ws = _red_ws.get(device)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().map_reduce_workspace_bytes(0)), dtype=torch.uint8, device=device)
+        _red_ws[device] = ws
+    return ws
+
+
+def reduce_sum(x: torch.Tensor, scale: float = 1.0, out=None, ws=None) -> torch.Tensor:
+    _check(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = ws if ws is not None else _reduce_ws(x.device)
+    call("map_reduce_sum_f32", x.data_ptr(), x.numel(), float(scale), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def bce_logits(logits: torch.Tensor, labels: torch.Tensor, stats=None, dlogits=None, ws=None, want_grad=True):
+    """stats = [mean loss, #correct, sum(labels), n]; dlogits = (sigmoid(z)-y)/n."""
+    _check(logits, torch.float32, "logits")
+    _check(labels, torch.float32, "labels")
+    n = logits.numel()
+    if stats is None:
+        stats = torch.empty(4, dtype=torch.float32, device=logits.device)
+    if dlogits is None and want_grad:
+        dlogits = torch.empty_like(logits)
+    ws = ws if ws is not None else _reduce_ws(logits.device)
+    call("map_bce_logits_fwd", logits.data_ptr(), labels.data_ptr(), n, stats.data_ptr(), _ptr(dlogits), ws.data_ptr(), ws.numel(), _stream())
+    return stats, dlogits
+
+
+def fm_lr_fwd(feat_embed, ids, lr_w, lr_bias, out=None, ld_out: int = 1):
+    B, F, D = feat_embed.shape
+    if out is None:
+        out = torch.empty(B, 1, dtype=torch.float32, device=feat_embed.device)
+    call("map_fm_lr_fwd", feat_embed.data_ptr(), ids.data_ptr(), lr_w.data_ptr(), lr_bias.data_ptr(), B, F, D, out.data_ptr(), ld_out, _stream())
+    return out
+
+
+def fm_lr_bwd(feat_embed, g, ld_g: int, d_embed, d_w_occ=None, accumulate=False):
+    B, F, D = feat_embed.shape
+    call("map_fm_lr_bwd", feat_embed.data_ptr(), g.data_ptr(), ld_g, B, F, D, 1 if accumulate else 0, d_embed.data_ptr(), _ptr(d_w_occ), _stream())
+    return d_embed
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def gemm_backend() -> str:
+    """'tcgen05' (default: TF32 tensor cores) or 'simt' (exact fp32 on CUDA cores; MAP_B200_GEMM=simt, used by tests)."""
+    return os.environ.get("MAP_B200_GEMM", "tcgen05")
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "matrix operands must be row-major with unit inner stride"
+    return t.stride(0)
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
+         epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, backend: Optional[str] = None):
+    """acc[m,n] = sum_k A[m,k]*B[n,k] with storage transposes; see include/map_b200.h.  Operands are 2-D row-major views
+    (row stride = leading dimension, so column slices of wider buffers work)."""
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.trans_a, g.trans_b, g.epilogue = int(trans_a), int(trans_b), int(epilogue)
+    g.A, g.lda = A.data_ptr(), _ld(A)
+    g.B, g.ldb = B.data_ptr(), _ld(B)
+    g.C, g.ldc = C_out.data_ptr(), _ld(C_out)
+    g.bias = _ptr(bias)
+    g.aux0, g.ld_aux0 = (aux0.data_ptr(), _ld(aux0)) if aux0 is not None else (None, 0)
+    g.aux1, g.ld_aux1 = (aux1.data_ptr(), _ld(aux1)) if aux1 is not None else (None, 0)
+    g.aux_out, g.ld_aux_out = (aux_out.data_ptr(), _ld(aux_out)) if aux_out is not None else (None, 0)
+    backend = backend or gemm_backend()
+    lib = _lib.load()
+    if backend == "tcgen05" and lib.map_gemm_tf32_supported(C.byref(g)):
+        call("map_gemm_tf32_tcgen05", C.byref(g), _stream())
+    else:  # skinny / unaligned shapes (N < 16, N % 4 != 0) and the exact-fp32 test mode
+        call("map_gemm_f32_simt", C.byref(g), _stream())
+    return C_out
+
+
+_colsum_ws = {}
+
+
+def colsum(X: torch.Tensor, out: Optional[torch.Tensor] = None, ws=None) -> torch.Tensor:
+    M, N = X.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=X.device)
+    need = int(_lib.load().map_colsum_workspace_bytes(M, N))
+    if ws is None:
+        key = (X.device, need)
+        ws = _colsum_ws.get(key)
+        if ws is None:
+            ws = torch.empty(need, dtype=torch.uint8, device=X.device)
+            _colsum_ws[key] = ws
+    call("map_colsum_f32", X.data_ptr(), _ld(X), M, N, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
+def cross_bwd_pre(G, X0, U, dU, dX0_acc, accumulate: bool):
+    M, N = G.shape
+    call("map_cross_bwd_pre", G.data_ptr(), _ld(G), X0.data_ptr(), _ld(X0), U.data_ptr(), _ld(U), M, N, 1 if accumulate else 0,
+         dU.data_ptr(), dX0_acc.data_ptr(), _stream())
+
+
+def add3(a, b, c, out):
+    M, N = a.shape
+    call("map_add3_f32", a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), _ptr(c), _ld(c) if c is not None else 0, M, N, out.data_ptr(), _ld(out), _stream())
+    return out
+
+
+def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, M, dtype=torch.float32, device=x.device)
+    call("map_transpose_f32", x.data_ptr(), _ld(x), M, N, out.data_ptr(), _ld(out), _stream())
+    return out

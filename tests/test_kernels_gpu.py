@@ -1,0 +1,533 @@
+"""Kernel-level parity: every C-ABI entry point (include/map_b200.h) against the CPU oracle (oracle/map_oracle.py) on the
+same seeded inputs.  Integer / index / copy work is bit-exact; fp32 reductions within 1e-5 relative; TF32 GEMMs within
+the tolerance stated in test_gemm_tcgen05_*."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import map_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from map_code_b200 import ops as _ops
+    return _ops
+
+
+def dev(t):
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("D", [16, 64, 32, 1, 6])
+def test_emb_gather_bit_exact(ops, D):
+    g = torch.Generator().manual_seed(D)
+    table = torch.randn(1000, D, generator=g)
+    ids = torch.randint(0, 1000, (333, 7), generator=g)
+    ids[0, :] = 3
+    out = ops.emb_gather(dev(table), dev(ids))
+    assert out.shape == (333, 7, D)
+    assert torch.equal(out.cpu(), O.embeddings_forward(table, ids))
+
+
+def test_emb_gather_empty_and_oob(ops):
+    table = dev(torch.randn(10, 16))
+    out = ops.emb_gather(table, dev(torch.zeros(0, 4, dtype=torch.int64)))
+    assert out.shape == (0, 4, 16)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = ops.emb_gather(table, dev(torch.tensor([[1, 10, -1]])), oob_flag=flag)
+    assert flag.item() == 1 and out[0, 1].abs().sum() == 0 and torch.equal(out[0, 0], table[1])
+
+
+def test_emb_gather_large_rows(ops):
+    # C5-like: 64-float rows, table larger than L2 is not needed for parity; 200k rows x 256 B
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(200_000, 64, generator=g)
+    ids = torch.randint(0, 200_000, (65536 * 3,), generator=g)
+    out = ops.emb_gather(dev(table), dev(ids))
+    assert torch.equal(out.cpu(), table[ids])
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("n,V", [(1, 5), (37, 100), (5000, 100), (160_000, 1_085_271), (319_488, 1_085_271), (70_000, 2 ** 27 + 5)])
+def test_dedup_ids(ops, n, V):
+    g = torch.Generator().manual_seed(n)
+    u = torch.rand(n, generator=g)
+    ids = torch.floor(torch.pow(torch.tensor(float(V)), u)).long().clamp_(0, V - 1)  # Zipf-ish: heavy duplicates at small ids
+    ids[::11] = 3  # the <mask> hot row
+    plan = ops.DedupPlan(n, V, "cuda").run(dev(ids))
+    U = plan.n_unique.item()
+    uniq_ref, counts_ref = torch.unique(ids, return_counts=True)
+    assert U == uniq_ref.numel()
+    assert torch.equal(plan.uniq[:U].cpu(), uniq_ref)
+    seg = plan.seg_start[:U + 1].cpu().long()
+    assert seg[0] == 0 and seg[-1] == n
+    assert torch.equal(seg[1:] - seg[:-1], counts_ref)
+    occ = plan.occ_sorted.cpu().long()
+    assert torch.equal(torch.sort(occ).values, torch.arange(n))          # a permutation
+    srt = ids[occ]
+    assert torch.equal(srt, torch.sort(ids, stable=True).values)
+    # stability: inside a segment occurrences stay in ascending original order
+    same = srt[1:] == srt[:-1]
+    assert bool((occ[1:][same] > occ[:-1][same]).all())
+
+
+@pytest.mark.parametrize("D", [16, 32, 1, 6, 64])
+def test_segment_reduce_matches_index_add(ops, D):
+    g = torch.Generator().manual_seed(D)
+    n, V = 20_000, 3000
+    ids = torch.randint(0, V, (n,), generator=g)
+    ids[: n // 3] = 3
+    rows = torch.randn(n, D, generator=g)
+    plan = ops.DedupPlan(n, V, "cuda").run(dev(ids))
+    G = plan.reduce_rows(dev(rows), D)
+    U = plan.n_unique.item()
+    ref = torch.zeros(V, D, dtype=torch.float64).index_add_(0, ids, rows.double())
+    got = torch.zeros(V, D, dtype=torch.float64)
+    got[plan.uniq[:U].cpu()] = G[:U].cpu().double()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)
+    dense = torch.zeros(V, D, device="cuda")
+    plan.scatter_dense(G, D, dense)
+    torch.testing.assert_close(dense.cpu().double(), ref, rtol=1e-5, atol=1e-4)
+
+
+def test_segment_reduce_scaled_grouped(ops):
+    """NCE form: occurrence o = n*(K+1)+j contributes dz[o] * input[n, :] to row ids[o] and dz[o] to its bias."""
+    g = torch.Generator().manual_seed(1)
+    N, K1, P, V = 700, 26, 32, 500
+    ids = torch.randint(0, V, (N * K1,), generator=g)
+    dz = torch.randn(N * K1, generator=g)
+    inp = torch.randn(N, P, generator=g)
+    plan = ops.DedupPlan(N * K1, V, "cuda").run(dev(ids))
+    sc = torch.empty(N * K1, device="cuda")
+    G = plan.reduce_rows(dev(inp), P, scale=dev(dz), group=K1, scalar_out=sc)
+    U = plan.n_unique.item()
+    ref = torch.zeros(V, P, dtype=torch.float64).index_add_(0, ids, (dz[:, None] * inp.repeat_interleave(K1, 0)).double())
+    refb = torch.zeros(V, dtype=torch.float64).index_add_(0, ids, dz.double())
+    u = plan.uniq[:U].cpu()
+    torch.testing.assert_close(G[:U].cpu().double(), ref[u], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(sc[:U].cpu().double(), refb[u], rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ AdamW
+def test_adamw_hyper_schedule(ops):
+    hyper = torch.zeros(8, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lam = O.cosine_schedule_lambda(3, 20)
+    for s in range(25):
+        ops.adamw_hyper_step(hyper, ctr, 1e-3, 0.9, 0.999, 1e-8, 1, 3, 20)
+        h = hyper.cpu()
+        lr = 1e-3 * lam(s)
+        t = s + 1
+        assert abs(h[0].item() - lr) <= 1e-9 + 1e-6 * lr
+        ss = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        assert abs(h[1].item() - ss) <= 1e-10 + 2e-6 * ss
+        assert ctr.item() == t
+    lamc = O.constant_schedule_lambda(4)
+    ctr.zero_()
+    for s in range(8):
+        ops.adamw_hyper_step(hyper, ctr, 2e-3, 0.9, 0.999, 1e-8, 0, 4, 0)
+        assert abs(hyper[0].item() - 2e-3 * lamc(s)) < 1e-9
+
+
+def test_adamw_multi_tensor_matches_hf(ops):
+    g = torch.Generator().manual_seed(0)
+    shapes = [(624, 624), (1000,), (37, 5), (3,)]
+    wds = [5e-2, 0.0, 5e-2, 0.0]
+    ps = [torch.randn(*s, generator=g) for s in shapes]
+    ref_p = [p.clone() for p in ps]
+    ref_m = [torch.zeros_like(p) for p in ps]
+    ref_v = [torch.zeros_like(p) for p in ps]
+    d_p = [dev(p.clone()) for p in ps]
+    d_m = [torch.zeros_like(p) for p in d_p]
+    d_v = [torch.zeros_like(p) for p in d_p]
+    d_g = [torch.zeros_like(p) for p in d_p]
+    d_pt = [torch.zeros(p.shape[1], p.shape[0], device="cuda") if p.dim() == 2 else None for p in d_p]
+    table, n, mx = ops.make_adamw_tensor_list([(d_p[i], d_g[i], d_m[i], d_v[i], wds[i], d_pt[i]) for i in range(len(ps))], "cuda")
+    hyper = torch.zeros(8, device="cuda")
+    for step in range(1, 4):
+        lr = 1e-3 * step
+        gs = [torch.randn(*s, generator=g) for s in shapes]
+        for i in range(len(ps)):
+            d_g[i].copy_(gs[i])
+            O.hf_adamw_update(ref_p[i], gs[i], ref_m[i], ref_v[i], step, lr, 0.9, 0.999, 1e-8, wds[i])
+        ops.adamw_hyper_set(hyper, lr, 0.9, 0.999, 1e-8, step)
+        ops.adamw_multi_tensor(table, n, mx, hyper)
+    for i in range(len(ps)):
+        torch.testing.assert_close(d_p[i].cpu(), ref_p[i], rtol=2e-6, atol=1e-7)
+        torch.testing.assert_close(d_m[i].cpu(), ref_m[i], rtol=2e-6, atol=1e-8)
+        torch.testing.assert_close(d_v[i].cpu(), ref_v[i], rtol=2e-6, atol=1e-10)
+        if d_pt[i] is not None:
+            assert torch.equal(d_pt[i], d_p[i].t().contiguous())
+
+
+@pytest.mark.parametrize("D", [16, 1])
+def test_adamw_rows_sparse_and_dense_exact(ops, D):
+    g = torch.Generator().manual_seed(D)
+    V, n = 2000, 900
+    table = torch.randn(V, D, generator=g)
+    m0 = torch.rand(V, D, generator=g) * 0.01
+    v0 = torch.rand(V, D, generator=g) * 0.001
+    ids = torch.randint(0, V, (n,), generator=g)
+    rows = torch.randn(n, D, generator=g)
+    dense_g = torch.zeros(V, D).index_add_(0, ids, rows)
+    plan = ops.DedupPlan(n, V, "cuda").run(dev(ids))
+    G = plan.reduce_rows(dev(rows), D)
+    hyper = torch.zeros(8, device="cuda")
+    ops.adamw_hyper_set(hyper, 1e-3, 0.9, 0.999, 1e-8, 7)
+    # dense_exact == the reference's dense AdamW over every row
+    rp, rm, rv = table.clone(), m0.clone(), v0.clone()
+    O.hf_adamw_update(rp, dense_g, rm, rv, 7, 1e-3, 0.9, 0.999, 1e-8, 5e-2)
+    p, m, v = dev(table.clone()), dev(m0.clone()), dev(v0.clone())
+    ops.adamw_dense_rows_sparse_grad(p, m, v, plan, G, hyper, 5e-2)
+    torch.testing.assert_close(p.cpu(), rp, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m.cpu(), rm, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(v.cpu(), rv, rtol=1e-5, atol=1e-9)
+    # sparse: touched rows identical to the dense result, untouched rows unchanged
+    p, m, v = dev(table.clone()), dev(m0.clone()), dev(v0.clone())
+    ops.adamw_sparse_rows(p, m, v, plan, G, hyper, 5e-2)
+    touched = torch.zeros(V, dtype=torch.bool)
+    touched[ids] = True
+    torch.testing.assert_close(p.cpu()[touched], rp[touched], rtol=1e-5, atol=1e-6)
+    assert torch.equal(p.cpu()[~touched], table[~touched])
+    assert torch.equal(m.cpu()[~touched], m0[~touched])
+
+
+# ------------------------------------------------------------------------------------------------ K8 / K9
+@pytest.mark.parametrize("method", ["randint", "normal"])
+@pytest.mark.parametrize("B,L,F", [(4096, 3, 39), (4096, 11, 39), (257, 2, 24), (5, 6, 6)])
+def test_mask_index_bit_exact(ops, method, B, L, F):
+    got = ops.mask_index(B, L, F, method, seed=42, offset=8 * 5 + 0)
+    want = O.draw_masked_index(42, 8 * 5 + 0, B, L, F, method)
+    assert torch.equal(got.cpu(), want)
+    got = ops.mask_index(B, L, F, method, seed=2 ** 40 + 7, offset=3, row0=1000)
+    want = O.draw_masked_index(2 ** 40 + 7, 3, B, L, F, method, row0=1000)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_mask_index_unknown_method(ops):
+    with pytest.raises(NotImplementedError):
+        ops.mask_index(4, 2, 6, "bogus", 1, 0)
+
+
+def test_mfp_apply_golden_and_random(ops, golden):
+    g = golden("dynamic_mask")
+    ids, labels = ops.mfp_mask_apply(dev(g["X"][:2].contiguous()), dev(g["masked_index"]))
+    assert torch.equal(ids.cpu(), g["out"]["MFP"]["input_ids"]) and torch.equal(labels.cpu(), g["out"]["MFP"]["labels"])
+    gen = torch.Generator().manual_seed(0)
+    for F, L in [(39, 11), (24, 2), (64, 20), (33, 33)]:
+        X = torch.randint(10, 10 ** 6, (1000, F), generator=gen)
+        mi = torch.randint(0, F, (1000, L), generator=gen)
+        ids, labels = ops.mfp_mask_apply(dev(X), dev(mi))
+        wi, wl = O.dynamic_mask_mfp(X, mi)
+        assert torch.equal(ids.cpu(), wi) and torch.equal(labels.cpu(), wl)
+
+
+@pytest.mark.parametrize("mode", ["Unigram", "Uniform", "Whole-Uniform", "Whole-Unigram"])
+def test_rfd_replace_bit_exact(ops, mode):
+    gen = torch.Generator().manual_seed(3)
+    F, L, B, V = 39, 11, 2048, 50_000
+    Xtr = torch.randint(10, V, (4096, F), generator=gen)
+    X = Xtr[torch.randint(0, 4096, (B,), generator=gen)].contiguous()
+    lo, hi = Xtr.min(0).values, Xtr.max(0).values + 1
+    mi = O.draw_masked_index(42, 0, B, L, F, "randint", row0=64)
+    rep_out = torch.empty(B, L, dtype=torch.int64, device="cuda")
+    ids, labels = ops.rfd_replace(dev(X), dev(mi), mode, 42, 1, 3, x_train=dev(Xtr), idx_low=dev(lo), idx_high=dev(hi),
+                                  input_size=V, row0=64, replace_out=rep_out)
+    rep = O.draw_rfd_replacement(42, 1, 3, mi, mode, x_train=Xtr, idx_low=lo, idx_high=hi, input_size=V, row0=64)
+    assert torch.equal(rep_out.cpu(), rep)
+    wi, wl = O.dynamic_mask_rfd(X, mi, rep)
+    assert torch.equal(ids.cpu(), wi) and torch.equal(labels.cpu(), wl)
+
+
+def test_rfd_golden_last_writer_wins(ops, golden):
+    """duplicate masked field: the later l wins (SURVEY §8c KAT), using Uniform with a degenerate 1-wide range to force values"""
+    g = golden("dynamic_mask")
+    X, mi = g["X"], g["masked_index"]
+    want = g["out"]["RFD-Unigram"]
+    # find Philox-independent check: Unigram with n_train == 1 always samples row 0 -> replacement = X_train[0, f]
+    Xtr = torch.tensor([[142, 0, 120, 0, 0, 111]])
+    ids, labels = ops.rfd_replace(dev(X[:2].contiguous()), dev(mi), "Unigram", 1, 1, x_train=dev(Xtr))
+    assert ids.cpu().tolist() == [[142, 101, 102, 103, 104, 111], [106, 107, 120, 109, 110, 111]]
+    assert torch.equal(labels.cpu(), want["labels"])
+    with pytest.raises(NotImplementedError):
+        ops.rfd_replace(dev(X[:2].contiguous()), dev(mi), "bogus", 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------ K5
+def test_alias_draw_bit_exact(ops, golden):
+    g = golden("alias")["zipf3000"]
+    got = ops.alias_draw(dev(g["prob"]), dev(g["alias"]), 42, 2, 300_000, elem0=77)
+    want = O.alias_draw(g["prob"], g["alias"], 42, 2, 300_000, elem0=77)
+    assert torch.equal(got.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------------ K6 / K7
+def _nce_ref(emb, bias, logq, norm, target, noise, inp, loss_type):
+    emb = emb.clone().requires_grad_(True)
+    bias = bias.clone().requires_grad_(True)
+    inp = inp.clone().requires_grad_(True)
+    loss, logits, ids = O.nce_forward(emb, bias, logq, norm, target, noise, inp, loss_type=loss_type)
+    loss.backward()
+    return loss.detach(), logits.detach(), ids, inp.grad, emb.grad, bias.grad
+
+
+@pytest.mark.parametrize("loss_type", ["nce", "sampled"])
+def test_nce_kat_golden(ops, golden, loss_type):
+    g = golden("nce_kat")
+    out = g["out"][loss_type]
+    B, L, P = g["input"].shape
+    K = g["noise"].shape[-1]
+    acc = torch.zeros(1, dtype=torch.int32, device="cuda")
+    logits, ids, loss_pos, dz, d_in = ops.nce_fwd(dev(g["input"].reshape(-1, P)), dev(g["target"].reshape(-1)), dev(g["noise"].reshape(-1, K)),
+                                                  dev(g["emb"]), dev(g["bias"].reshape(-1)), dev(g["logprob_noise"]), g["norm_term"],
+                                                  loss_type, acc_count=acc)
+    loss = ops.reduce_sum(loss_pos, 1.0 / (B * L))
+    torch.testing.assert_close(loss.cpu()[0], out["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits.cpu().view(B, L, K + 1), out["logits"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(ids.cpu().view(B, L, K + 1), out["ids"])
+    torch.testing.assert_close(d_in.cpu().view(B, L, P), out["d_input"], rtol=1e-4, atol=1e-7)
+    assert acc.item() == int((out["logits"].argmax(dim=2) == 0).sum())
+    # table gradients through the dedup pipeline
+    n = B * L * (K + 1)
+    plan = ops.DedupPlan(n, 16, "cuda").run(ids.view(-1))
+    gb = torch.empty(n, device="cuda")
+    G = plan.reduce_rows(dev(g["input"].reshape(-1, P)), P, scale=dz.view(-1), group=K + 1, scalar_out=gb)
+    dense = torch.zeros(16, P, device="cuda")
+    plan.scatter_dense(G, P, dense)
+    torch.testing.assert_close(dense.cpu(), out["d_emb"], rtol=1e-4, atol=1e-7)
+    dense_b = torch.zeros(16, 1, device="cuda")
+    plan.scatter_dense(gb, 1, dense_b)
+    torch.testing.assert_close(dense_b.cpu(), out["d_bias"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("loss_type", ["nce", "sampled"])
+@pytest.mark.parametrize("P,K", [(32, 25), (8, 5), (64, 25), (128, 7), (16, 40), (4, 3)])
+def test_nce_random_vs_oracle(ops, loss_type, P, K):
+    gen = torch.Generator().manual_seed(P * 100 + K)
+    V, N = 5000, 1537
+    fc = torch.floor(torch.pow(torch.tensor(1000.0), torch.rand(V, generator=gen)))
+    _, logq, norm = O.nce_noise_distribution(fc)
+    emb = (torch.rand(V, P, generator=gen) * 2 - 1) / math.sqrt(P)
+    bias = O.index_linear_init_bias(logq, norm) + 0.1 * torch.randn(V, 1, generator=gen)
+    target = torch.randint(0, V, (N, 1), generator=gen)
+    noise = torch.randint(0, V, (N, 1, K), generator=gen)
+    noise[5, 0, 2] = target[5, 0]  # argmax tie
+    inp = torch.randn(N, 1, P, generator=gen)
+    loss, logits, ids, d_in, d_emb, d_bias = _nce_ref(emb, bias, logq, norm, target, noise, inp, loss_type)
+    acc = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lg, idd, loss_pos, dz, din = ops.nce_fwd(dev(inp.view(N, P)), dev(target.view(-1)), dev(noise.view(N, K)), dev(emb),
+                                             dev(bias.view(-1)), dev(logq), norm, loss_type, acc_count=acc)
+    torch.testing.assert_close(ops.reduce_sum(loss_pos, 1.0 / N).cpu()[0], loss, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(lg.cpu().view(N, 1, K + 1), logits, rtol=1e-5, atol=2e-5)
+    assert torch.equal(idd.cpu().view(N, 1, K + 1), ids)
+    torch.testing.assert_close(din.cpu().view(N, 1, P), d_in, rtol=1e-4, atol=1e-8)
+    assert acc.item() == int((logits.argmax(dim=2) == 0).sum())
+    plan = ops.DedupPlan(N * (K + 1), V, "cuda").run(idd.view(-1))
+    gb = torch.empty(N * (K + 1), device="cuda")
+    G = plan.reduce_rows(dev(inp.view(N, P)), P, scale=dz.view(-1), group=K + 1, scalar_out=gb)
+    dense = torch.zeros(V, P, device="cuda")
+    plan.scatter_dense(G, P, dense)
+    torch.testing.assert_close(dense.cpu(), d_emb, rtol=1e-4, atol=1e-8)
+    dense_b = torch.zeros(V, 1, device="cuda")
+    plan.scatter_dense(gb, 1, dense_b)
+    torch.testing.assert_close(dense_b.cpu(), d_bias, rtol=1e-4, atol=1e-8)
+
+
+def test_nce_unknown_loss_and_proj(ops):
+    x = torch.zeros(2, 12, device="cuda")
+    i = torch.zeros(2, dtype=torch.int64, device="cuda")
+    n = torch.zeros(2, 3, dtype=torch.int64, device="cuda")
+    e = torch.zeros(4, 12, device="cuda")
+    b = torch.zeros(4, device="cuda")
+    with pytest.raises(NotImplementedError):
+        ops.nce_fwd(x, i, n, e, b, b, 1.0, "mix")
+    with pytest.raises(NotImplementedError):
+        ops.nce_fwd(x, i, n, e, b, b, 1.0, "nce")  # P = 12 unsupported
+
+
+def test_gather_scatter_slices(ops):
+    gen = torch.Generator().manual_seed(0)
+    B, F, P, L = 300, 39, 32, 11
+    enc = torch.randn(B, F, P, generator=gen)
+    mi = torch.randint(0, F, (B, L), generator=gen)
+    sel = ops.gather_slices(dev(enc), dev(mi), F, P)
+    want = torch.gather(enc, 1, mi.unsqueeze(-1).repeat(1, 1, P))
+    assert torch.equal(sel.cpu().view(B, L, P), want)
+    d_sel = torch.randn(B, L, P, generator=gen)
+    d_enc = torch.zeros(B, F, P, device="cuda")
+    ops.scatter_add_slices(dev(d_sel.view(-1, P)), dev(mi), F, P, d_enc)
+    ref = torch.zeros(B, F, P).scatter_add_(1, mi.unsqueeze(-1).repeat(1, 1, P), d_sel)
+    torch.testing.assert_close(d_enc.cpu(), ref, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ K10 / K11 / reductions
+@pytest.mark.parametrize("n", [1, 4096, 4096 * 39, 1_000_003])
+def test_bce_logits(ops, n):
+    gen = torch.Generator().manual_seed(n)
+    z = torch.randn(n, generator=gen) * 3
+    y = (torch.rand(n, generator=gen) < 0.2).float()
+    stats, dz = ops.bce_logits(dev(z), dev(y))
+    zz = z.clone().requires_grad_(True)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(zz, y)
+    loss.backward()
+    s = stats.cpu()
+    torch.testing.assert_close(s[0], loss.detach(), rtol=1e-5, atol=1e-6)
+    assert s[1].item() == float(((torch.sigmoid(z) > 0.5).float() == y).sum())
+    assert s[2].item() == float(y.sum()) and s[3].item() == float(n)
+    torch.testing.assert_close(dz.cpu(), zz.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_reduce_sum_and_colsum(ops):
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(1_234_567, generator=gen)
+    torch.testing.assert_close(ops.reduce_sum(dev(x), 0.5).cpu()[0], (x.double().sum() * 0.5).float(), rtol=1e-5, atol=1e-3)
+    X = torch.randn(4096, 1000, generator=gen)
+    torch.testing.assert_close(ops.colsum(dev(X)).cpu(), X.double().sum(0).float(), rtol=1e-5, atol=1e-4)
+    big = dev(torch.randn(300, 1624, generator=gen))
+    view = big[:, 624:]  # strided column slice
+    torch.testing.assert_close(ops.colsum(view).cpu(), big[:, 624:].cpu().double().sum(0).float(), rtol=1e-5, atol=1e-4)
+
+
+def test_fm_lr_fwd_bwd(ops):
+    gen = torch.Generator().manual_seed(0)
+    B, F, D, V = 513, 24, 16, 1000
+    E = torch.randn(B, F, D, generator=gen).requires_grad_(True)
+    ids = torch.randint(0, V, (B, F), generator=gen)
+    w = torch.randn(V, 1, generator=gen).requires_grad_(True)
+    lb = torch.randn(1, generator=gen).requires_grad_(True)
+    ref = O.fm_lr_forward({"lr_layer.embed_w.weight": w, "lr_layer.bias": lb}, ids, E)
+    g = torch.randn(B, 1, generator=gen)
+    ref.backward(g)
+    out = ops.fm_lr_fwd(dev(E.detach()), dev(ids), dev(w.detach().view(-1)), dev(lb.detach()))
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-5, atol=1e-4)
+    dE = torch.empty(B, F, D, device="cuda")
+    docc = torch.empty(B * F, device="cuda")
+    ops.fm_lr_bwd(dev(E.detach()), dev(g), 1, dE, docc)
+    torch.testing.assert_close(dE.cpu(), E.grad, rtol=1e-5, atol=1e-5)
+    dw = torch.zeros(V).index_add_(0, ids.view(-1), docc.cpu())
+    torch.testing.assert_close(dw, w.grad.view(-1), rtol=1e-5, atol=1e-5)
+
+
+def test_cross_bwd_pre_add3_transpose(ops):
+    gen = torch.Generator().manual_seed(0)
+    M, N = 515, 624
+    G, X0, U = (torch.randn(M, N, generator=gen) for _ in range(3))
+    dU = torch.empty(M, N, device="cuda")
+    acc = dev(torch.ones(M, N))
+    ops.cross_bwd_pre(dev(G), dev(X0), dev(U), dU, acc, accumulate=True)
+    assert torch.equal(dU.cpu(), G * X0)
+    torch.testing.assert_close(acc.cpu(), 1 + G * U)
+    ops.cross_bwd_pre(dev(G), dev(X0), dev(U), dU, acc, accumulate=False)
+    assert torch.equal(acc.cpu(), G * U)
+    out = torch.empty(M, N, device="cuda")
+    ops.add3(dev(G), dev(X0), dev(U), out)
+    torch.testing.assert_close(out.cpu(), G + X0 + U)
+    ops.add3(dev(G), dev(X0), None, out)
+    assert torch.equal(out.cpu(), G + X0)
+    assert torch.equal(ops.transpose(dev(G)).cpu(), G.t().contiguous())
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _gemm_case(gen, M, N, K, ta, tb):
+    A = torch.randn(M, K, generator=gen)
+    B = torch.randn(N, K, generator=gen)
+    As = A.t().contiguous() if ta else A
+    Bs = B.t().contiguous() if tb else B
+    return A, B, As, Bs
+
+
+def _epilogue_ref(epi, acc, bias, aux0, aux1):
+    from map_code_b200 import _lib as L
+    if epi == L.EPI_NONE:
+        return acc, None
+    if epi == L.EPI_BIAS:
+        return acc + bias, None
+    if epi == L.EPI_BIAS_RELU:
+        return torch.relu(acc + bias), None
+    if epi == L.EPI_CROSS:
+        u = acc + bias
+        return aux0 + aux1 * u, u
+    if epi == L.EPI_MUL_RELUMASK:
+        return acc * (aux0 > 0), None
+    if epi == L.EPI_ADD:
+        return acc + aux0, None
+    if epi == L.EPI_ADD_MUL:
+        s = acc + aux0
+        return s * aux1, s
+    raise AssertionError
+
+
+def _run_gemm(ops, backend, M, N, K, ta, tb, epi, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    A, B, As, Bs = _gemm_case(gen, M, N, K, ta, tb)
+    bias = torch.randn(N, generator=gen)
+    aux0 = torch.randn(M, N, generator=gen)
+    aux1 = torch.randn(M, N, generator=gen)
+    acc = (A.double() @ B.double().t())
+    want, want_aux = _epilogue_ref(epi, acc, bias.double(), aux0.double(), aux1.double())
+    Cd = torch.full((M, N), float("nan"), device="cuda")
+    auxo = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(dev(As), dev(Bs), Cd, M, N, K, trans_a=ta, trans_b=tb, epilogue=epi, bias=dev(bias), aux0=dev(aux0), aux1=dev(aux1),
+             aux_out=auxo, backend=backend)
+    torch.cuda.synchronize()
+    return Cd.cpu().double(), want, (auxo.cpu().double() if want_aux is not None else None), want_aux, acc
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (130, 39, 1248), (257, 1, 77), (100, 100, 100)])
+def test_gemm_simt_exact_fp32(ops, M, N, K, ta, tb):
+    for epi in range(7):
+        got, want, ga, wa, _ = _run_gemm(ops, "simt", M, N, K, ta, tb, epi, seed=epi)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * math.sqrt(K))
+        if wa is not None:
+            torch.testing.assert_close(ga, wa, rtol=1e-4, atol=1e-4 * math.sqrt(K))
+
+
+# TF32 tolerance: operands are rounded to 10 mantissa bits (rel 2^-11 each), products accumulate in fp32:
+#   |C - C_fp64| <= ~2^-10 * sqrt(K) * rms(a) * rms(b) statistically.  Test: Frobenius-relative error < 1e-3 and
+#   max abs error < 4 * 2^-10 * sqrt(K) (unit-variance operands).
+def _check_tf32(got, want, K, scale=1.0):
+    assert torch.isfinite(got).all(), "NaN/garbage in the output tile (unwritten or corrupted)"
+    rel = (got - want).norm() / want.norm()
+    assert rel < 1e-3, f"frobenius rel err {rel:.3e}"
+    assert (got - want).abs().max() < 4 * 2 ** -10 * math.sqrt(K) * scale + 1e-5
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 128), (256, 256, 96), (4096, 624, 624), (300, 1000, 1000),
+                                   (1000, 624, 4096), (4096, 1248, 1624), (129, 16, 40), (4096, 1624, 1248)])
+def test_gemm_tcgen05_tf32(ops, M, N, K, ta, tb):
+    got, want, _, _, _ = _run_gemm(ops, "tcgen05", M, N, K, ta, tb, 0)
+    _check_tf32(got, want, K)
+
+
+@pytest.mark.parametrize("epi", [1, 2, 3, 4, 5, 6])
+def test_gemm_tcgen05_epilogues(ops, epi):
+    got, want, ga, wa, acc = _run_gemm(ops, "tcgen05", 515, 624, 624, False, epi in (4, 5, 6), epi, seed=epi)
+    # compare through the accumulator error only: the epilogue itself is exact fp32
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max()
+    assert err < 4 * 2 ** -10 * math.sqrt(624) * 4 + 1e-4, f"epilogue {epi}: max err {err}"
+    assert ((got - want).norm() / want.norm()) < 2e-3
+    if wa is not None:
+        assert ((ga - wa).norm() / wa.norm()) < 1e-3
+
+
+def test_gemm_tcgen05_strided_views(ops):
+    """forward writes into column slices of the concatenated [B, 1624] buffer (no torch.cat, models.py:312)"""
+    gen = torch.Generator().manual_seed(0)
+    M = 384
+    X = torch.randn(M, 624, generator=gen)
+    W = torch.randn(1000, 624, generator=gen) / 25
+    b = torch.randn(1000, generator=gen)
+    final = torch.zeros(M, 1624, device="cuda")
+    from map_code_b200 import _lib as L
+    ops.gemm(dev(X), dev(W), final[:, 624:], M, 1000, 624, epilogue=L.EPI_BIAS_RELU, bias=dev(b), backend="tcgen05")
+    want = torch.relu(X.double() @ W.double().t() + b.double())
+    _check_tf32(final[:, 624:].cpu().double(), want, 624, scale=1 / 25)
+    assert final[:, :624].abs().sum() == 0
