@@ -74,15 +74,16 @@ int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const i
  * replaces transformers.AdamW.step (code/trainer.py:75-76,140):
  *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= step_size * m / (sqrt(v)+eps) ; p -= lr*wd*p
  *   step_size = lr * sqrt(1-b2^t)/(1-b1^t).
- * hyper: device float[8] = {lr, step_size, beta1, beta2, eps, 0,0,0}, produced by map_adamw_hyper_step so that a
- * captured CUDA graph picks up the new learning rate at every replay without host involvement. */
+ * hyper: device float[8] = {lr, step_size, beta1, beta2, eps, t, 1-beta1, 1-beta2}, produced by map_adamw_hyper_step so that a
+ * captured CUDA graph picks up the new learning rate at every replay without host involvement.  Scalars are doubles
+ * because the reference evaluates the bias corrections with Python floats (beta2 = 0.999 is not a float32). */
 #define MAP_SCHED_CONST 0   /* transformers.get_constant_schedule_with_warmup */
 #define MAP_SCHED_COSINE 1  /* transformers.get_cosine_schedule_with_warmup (num_cycles=0.5) */
 /* step_counter (device int64) is incremented; lr = base_lr * lambda(step_counter_before) (trainer.py:141) */
-int map_adamw_hyper_step(float* hyper, int64_t* step_counter, float base_lr, float beta1, float beta2, float eps,
+int map_adamw_hyper_step(float* hyper, int64_t* step_counter, double base_lr, double beta1, double beta2, double eps,
                          int sched, int64_t warmup_steps, int64_t total_steps, map_stream_t stream);
 /* explicit (host-driven) variant: step = 1-based step count for bias correction */
-int map_adamw_hyper_set(float* hyper, float lr, float beta1, float beta2, float eps, int64_t step, map_stream_t stream);
+int map_adamw_hyper_set(float* hyper, double lr, double beta1, double beta2, double eps, int64_t step, map_stream_t stream);
 
 typedef struct {
     float* p;        /* parameter */
@@ -223,6 +224,11 @@ int map_cross_bwd_pre(const float* G, int64_t ldg, const float* X0, int64_t ldx0
 /* out = a + b (+ c)  elementwise over [M,N] with row strides */
 int map_add3_f32(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, int64_t M, int N,
                  float* out, int64_t ldo, map_stream_t stream);
+/* out = dy * (y > 0): ReLU backward outside a GEMM epilogue (autograd of nn.ReLU, layers.py:58) */
+int map_relu_bwd_f32(const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t M, int N, float* out, int64_t ldo,
+                     map_stream_t stream);
+/* out[i] = x[i] * scalar_dev[0]: chain rule through a scalar loss whose upstream gradient lives on the device */
+int map_scale_by_scalar_f32(const float* x, const float* scalar_dev, int64_t n, float* out, map_stream_t stream);
 /* out[N,M] = in[M,N]^T */
 int map_transpose_f32(const float* in, int64_t ld_in, int64_t M, int64_t N, float* out, int64_t ld_out, map_stream_t stream);
 

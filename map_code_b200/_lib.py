@@ -42,7 +42,7 @@ class AdamwTensor(C.Structure):
     ]
 
 
-_p, _i, _l, _f, _u64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
+_p, _i, _l, _f, _u64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes).  Kept in the order of include/map_b200.h; tests/test_abi.py checks it against the header.
 PROTOTYPES = {
@@ -54,8 +54,8 @@ PROTOTYPES = {
     "map_dedup_ids": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "map_segment_reduce_rows": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _l, _p, _p, _p]),
     "map_scatter_rows": (_i, [_p, _p, _p, _l, _i, _p, _p]),
-    "map_adamw_hyper_step": (_i, [_p, _p, _f, _f, _f, _f, _i, _l, _l, _p]),
-    "map_adamw_hyper_set": (_i, [_p, _f, _f, _f, _f, _l, _p]),
+    "map_adamw_hyper_step": (_i, [_p, _p, _d, _d, _d, _d, _i, _l, _l, _p]),
+    "map_adamw_hyper_set": (_i, [_p, _d, _d, _d, _d, _l, _p]),
     "map_adamw_multi_tensor": (_i, [_p, _i, _l, _p, _p]),
     "map_adamw_sparse_rows": (_i, [_p, _p, _p, _i, _p, _p, _p, _l, _p, _f, _p]),
     "map_adamw_dense_rows_sparse_grad": (_i, [_p, _p, _p, _l, _i, _p, _p, _p, _p, _f, _p]),
@@ -79,6 +79,8 @@ PROTOTYPES = {
     "map_colsum_workspace_bytes": (_sz, [_l, _i]),
     "map_cross_bwd_pre": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _i, _p, _p, _p]),
     "map_add3_f32": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _p, _l, _p]),
+    "map_relu_bwd_f32": (_i, [_p, _l, _p, _l, _l, _i, _p, _l, _p]),
+    "map_scale_by_scalar_f32": (_i, [_p, _p, _l, _p, _p]),
     "map_transpose_f32": (_i, [_p, _l, _l, _l, _p, _l, _p]),
 }
 

@@ -8,13 +8,15 @@
 namespace mapb {
 
 struct Hyper {
-    float lr, step_size, beta1, beta2, eps;
+    float lr, step_size, beta1, beta2, eps, one_m_beta1, one_m_beta2;
 };
-__device__ __forceinline__ Hyper load_hyper(const float* h) { return Hyper{h[0], h[1], h[2], h[3], h[4]}; }
+// hyper[6], hyper[7] = 1-beta evaluated in double like the reference (`alpha=1.0 - beta1`, `value=1.0 - beta2` are Python
+// floats): float32(1 - 0.999) differs from 1.f - float32(0.999) by 1.3e-5 relative.
+__device__ __forceinline__ Hyper load_hyper(const float* h) { return Hyper{h[0], h[1], h[2], h[3], h[4], h[6], h[7]}; }
 
 __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, const Hyper& h, float lr_wd) {
-    m = h.beta1 * m + (1.f - h.beta1) * g;
-    v = h.beta2 * v + (1.f - h.beta2) * g * g;
+    m = h.beta1 * m + h.one_m_beta1 * g;
+    v = h.beta2 * v + h.one_m_beta2 * g * g;
     const float denom = sqrtf(v) + h.eps;
     p = p - h.step_size * (m / denom);
     p = p - lr_wd * p;  // lr_wd = lr * weight_decay (0 => no-op), applied after the Adam move like HF AdamW
@@ -31,31 +33,35 @@ __device__ __forceinline__ double sched_lambda(int sched, int64_t step, int64_t 
     return 1.0;
 }
 
-__global__ void hyper_step_kernel(float* hyper, int64_t* step_counter, float base_lr, float beta1, float beta2, float eps,
+__global__ void hyper_step_kernel(float* hyper, int64_t* step_counter, double base_lr, double beta1, double beta2, double eps,
                                   int sched, int64_t warmup, int64_t total) {
     const int64_t s = *step_counter;  // steps completed so far == scheduler's current_step
-    const double lr = (double)base_lr * sched_lambda(sched, s, warmup, total);
+    const double lr = base_lr * sched_lambda(sched, s, warmup, total);
     const int64_t t = s + 1;  // optimizer state["step"] after increment
-    const double bc1 = 1.0 - pow((double)beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
     hyper[0] = (float)lr;
     hyper[1] = (float)(lr * sqrt(bc2) / bc1);
-    hyper[2] = beta1;
-    hyper[3] = beta2;
-    hyper[4] = eps;
+    hyper[2] = (float)beta1;
+    hyper[3] = (float)beta2;
+    hyper[4] = (float)eps;
     hyper[5] = (float)t;
+    hyper[6] = (float)(1.0 - beta1);
+    hyper[7] = (float)(1.0 - beta2);
     *step_counter = t;
 }
 
-__global__ void hyper_set_kernel(float* hyper, float lr, float beta1, float beta2, float eps, int64_t t) {
-    const double bc1 = 1.0 - pow((double)beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)beta2, (double)t);
-    hyper[0] = lr;
-    hyper[1] = (float)((double)lr * sqrt(bc2) / bc1);
-    hyper[2] = beta1;
-    hyper[3] = beta2;
-    hyper[4] = eps;
+__global__ void hyper_set_kernel(float* hyper, double lr, double beta1, double beta2, double eps, int64_t t) {
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
+    hyper[0] = (float)lr;
+    hyper[1] = (float)(lr * sqrt(bc2) / bc1);
+    hyper[2] = (float)beta1;
+    hyper[3] = (float)beta2;
+    hyper[4] = (float)eps;
     hyper[5] = (float)t;
+    hyper[6] = (float)(1.0 - beta1);
+    hyper[7] = (float)(1.0 - beta2);
 }
 
 // grid = (chunks, n_tensors); each CTA handles one 4096-element chunk of one tensor
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(256) adamw_dense_rows_kernel(float* __restrict
 
 }  // namespace mapb
 
-extern "C" int map_adamw_hyper_step(float* hyper, int64_t* step_counter, float base_lr, float beta1, float beta2, float eps,
+extern "C" int map_adamw_hyper_step(float* hyper, int64_t* step_counter, double base_lr, double beta1, double beta2, double eps,
                                     int sched, int64_t warmup_steps, int64_t total_steps, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(hyper && step_counter, "map_adamw_hyper_step: null pointer");
@@ -198,7 +204,7 @@ extern "C" int map_adamw_hyper_step(float* hyper, int64_t* step_counter, float b
     return check_launch("map_adamw_hyper_step");
 }
 
-extern "C" int map_adamw_hyper_set(float* hyper, float lr, float beta1, float beta2, float eps, int64_t step, map_stream_t stream) {
+extern "C" int map_adamw_hyper_set(float* hyper, double lr, double beta1, double beta2, double eps, int64_t step, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(hyper && step >= 1, "map_adamw_hyper_set: bad argument");
     hyper_set_kernel<<<1, 1, 0, as_stream(stream)>>>(hyper, lr, beta1, beta2, eps, step);

@@ -64,9 +64,9 @@ __global__ void __launch_bounds__(256) emb_gather_scalar_kernel(const float* __r
 extern "C" int map_emb_gather_f32(const float* table, int64_t V, int D, const int64_t* ids, int64_t n_ids, float* out,
                                   int32_t* oob_flag, map_stream_t stream) {
     using namespace mapb;
-    MAP_REQUIRE(table && ids && out, "map_emb_gather_f32: null pointer");
     MAP_REQUIRE(V > 0 && D > 0 && n_ids >= 0, "map_emb_gather_f32: bad shape V=%lld D=%d n=%lld", (long long)V, D, (long long)n_ids);
-    if (n_ids == 0) return MAP_OK;
+    if (n_ids == 0) return MAP_OK;  // empty batch: nothing to launch (torch hands out null pointers for empty tensors)
+    MAP_REQUIRE(table && ids && out, "map_emb_gather_f32: null pointer");
     const bool vec = (D % 4 == 0) && ((uintptr_t)table % 16 == 0) && ((uintptr_t)out % 16 == 0);
     if (vec) {
         const int vpr = D / 4;

@@ -98,10 +98,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 }
 
 // UMMA shared-memory descriptor (PTX ISA "tcgen05 matrix descriptor"): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46)
-// | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// | version=1 [46,48) | layout_type [61,64): 2 = SWIZZLE_128B (16-byte atoms; K-major tiles),
+//                                           1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only legal layout for MN-major
+//                                               32-bit operands: the tensor core transposes at element granularity)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor: D=f32 [4,6)=1 | A=tf32 [7,10)=2 | B=tf32 [10,13)=2 | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int block_n, int a_mn_major, int b_mn_major) {
@@ -254,10 +256,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
         // ===================== MMA issuer (one elected lane) =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(p.block_n, p.trans_a, p.trans_b);
-            // K-major  : 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of every row -> advance start by 32 B
-            // MN-major : 32-float chunks 4096 B apart (LBO); 8-k-row groups 1024 B apart (SBO) -> advance start by 1024 B
-            const uint32_t a_lbo = p.trans_a ? 4096u : 16u, a_sbo = 1024u, a_adv = p.trans_a ? 1024u : 32u;
-            const uint32_t b_lbo = p.trans_b ? 4096u : 16u, b_sbo = 1024u, b_adv = p.trans_b ? 1024u : 32u;
+            // K-major  (SWIZZLE_128B)        : 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of every row
+            //                                  -> advance the start address by 32 B per K step
+            // MN-major (SWIZZLE_128B_BASE32B): 32-float chunks 4096 B apart (LBO); the swizzle atom is 4 k-rows x 128 B, so
+            //                                  4-row groups are 512 B apart (SBO); one MMA consumes 8 k-rows
+            //                                  -> advance the start address by 1024 B per K step
+            const uint32_t a_lbo = p.trans_a ? 4096u : 16u, a_sbo = p.trans_a ? 512u : 1024u, a_adv = p.trans_a ? 1024u : 32u;
+            const uint32_t b_lbo = p.trans_b ? 4096u : 16u, b_sbo = p.trans_b ? 512u : 1024u, b_adv = p.trans_b ? 1024u : 32u;
+            const uint32_t a_lt = p.trans_a ? 1u : 2u, b_lt = p.trans_b ? 1u : 2u;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % p.stages;
                 const uint32_t round = (uint32_t)(i / p.stages);
@@ -267,8 +273,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
                 const uint32_t b_src = a_src + kATileBytes;
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    const uint64_t da = make_smem_desc(a_src + k * a_adv, a_lbo, a_sbo);
-                    const uint64_t db = make_smem_desc(b_src + k * b_adv, b_lbo, b_sbo);
+                    const uint64_t da = make_smem_desc(a_src + k * a_adv, a_lbo, a_sbo, a_lt);
+                    const uint64_t db = make_smem_desc(b_src + k * b_adv, b_lbo, b_sbo, b_lt);
                     umma_tf32(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
                 }
                 tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs have read it
@@ -333,7 +339,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows of `ld` floats; box = {32 floats, box_rows}
-static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
+static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_rows, bool mn_major) {
     EncodeTiledFn enc = get_encode_fn();
     if (enc == nullptr) {
         set_error("map_gemm_tf32_tcgen05: cuTensorMapEncodeTiled is not available from the driver");
@@ -344,7 +350,8 @@ static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t
     const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("map_gemm_tf32_tcgen05: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box_rows=%d", (int)r,
@@ -453,11 +460,11 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     const size_t smem_bytes = (size_t)stages * p.stage_bytes + 1024;  // + alignment slack
 
     CUtensorMap tmap_a, tmap_b;
-    if (!p.trans_a) rc = make_tmap(&tmap_a, g->A, g->K, g->M, g->lda, kBlockM);     // [M rows][K contiguous]
-    else rc = make_tmap(&tmap_a, g->A, g->M, g->K, g->lda, kBlockK);                // [K rows][M contiguous]
+    if (!p.trans_a) rc = make_tmap(&tmap_a, g->A, g->K, g->M, g->lda, kBlockM, false);     // [M rows][K contiguous]
+    else rc = make_tmap(&tmap_a, g->A, g->M, g->K, g->lda, kBlockK, true);                // [K rows][M contiguous]
     if (rc != MAP_OK) return rc;
-    if (!p.trans_b) rc = make_tmap(&tmap_b, g->B, g->K, g->N, g->ldb, p.block_n);   // [N rows][K contiguous]
-    else rc = make_tmap(&tmap_b, g->B, g->N, g->K, g->ldb, kBlockK);                // [K rows][N contiguous]
+    if (!p.trans_b) rc = make_tmap(&tmap_b, g->B, g->K, g->N, g->ldb, p.block_n, false);   // [N rows][K contiguous]
+    else rc = make_tmap(&tmap_b, g->B, g->N, g->K, g->ldb, kBlockK, true);                // [K rows][N contiguous]
     if (rc != MAP_OK) return rc;
 
     static bool attr_set = false;

@@ -139,6 +139,25 @@ __global__ void __launch_bounds__(256) add3_kernel(const float* __restrict__ a, 
     }
 }
 
+// dZ = dY * (Y > 0): standalone ReLU backward (the graph-captured step fuses this into the producing GEMM's epilogue)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ y,
+                                                       int64_t ldy, int64_t M, int N, float* __restrict__ out, int64_t ldo) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * N; e += stride) {
+        const int64_t m = e / N;
+        const int n = (int)(e - m * N);
+        out[m * ldo + n] = (y[m * ldy + n] > 0.f) ? dy[m * lddy + n] : 0.f;
+    }
+}
+
+// out[i] = x[i] * s[0]   (s lives on the device: upstream gradient of a scalar loss, no host sync)
+__global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s, int64_t n,
+                                                              float* __restrict__ out) {
+    const float sv = s[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] * sv;
+}
+
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t M, int64_t N,
                                                         float* __restrict__ out, int64_t ld_out) {
     __shared__ float tile[32][33];
@@ -294,4 +313,24 @@ extern "C" int map_fm_lr_bwd(const float* feat_embed, const float* g, int64_t ld
     MAP_REQUIRE(feat_embed && g && d_embed && B > 0 && F > 0 && D > 0, "map_fm_lr_bwd: bad argument");
     fm_lr_bwd_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(feat_embed, g, ld_g, B, F, D, accumulate, d_embed, d_w_occ);
     return check_launch("map_fm_lr_bwd");
+}
+
+extern "C" int map_relu_bwd_f32(const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t M, int N, float* out, int64_t ldo,
+                                map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(dy && y && out && M > 0 && N > 0, "map_relu_bwd_f32: bad argument");
+    int64_t blocks = ceil_div(M * N, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    relu_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dy, lddy, y, ldy, M, N, out, ldo);
+    return check_launch("map_relu_bwd_f32");
+}
+
+extern "C" int map_scale_by_scalar_f32(const float* x, const float* scalar_dev, int64_t n, float* out, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(x && scalar_dev && out && n >= 0, "map_scale_by_scalar_f32: bad argument");
+    if (n == 0) return MAP_OK;
+    int64_t blocks = ceil_div(n, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    scale_by_scalar_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, scalar_dev, n, out);
+    return check_launch("map_scale_by_scalar_f32");
 }

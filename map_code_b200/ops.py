@@ -46,6 +46,8 @@ def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tenso
     V, D = table.shape
     if out is None:
         out = torch.empty(*ids.shape, D, dtype=torch.float32, device=table.device)
+    if ids.numel() == 0:
+        return out
     call("map_emb_gather_f32", table.data_ptr(), V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), _ptr(oob_flag), _stream())
     return out
 
@@ -294,8 +296,8 @@ def gemm_backend() -> str:
 
 
 def _ld(t: torch.Tensor) -> int:
-    assert t.dim() == 2 and t.stride(1) == 1, "matrix operands must be row-major with unit inner stride"
-    return t.stride(0)
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "matrix operands must be row-major with unit inner stride"
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
@@ -356,4 +358,20 @@ def transpose(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     if out is None:
         out = torch.empty(N, M, dtype=torch.float32, device=x.device)
     call("map_transpose_f32", x.data_ptr(), _ld(x), M, N, out.data_ptr(), _ld(out), _stream())
+    return out
+
+
+def relu_bwd(dy: torch.Tensor, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, N = dy.shape
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=dy.device)
+    call("map_relu_bwd_f32", dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), M, N, out.data_ptr(), _ld(out), _stream())
+    return out
+
+
+def scale_by_scalar(x: torch.Tensor, scalar_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    call("map_scale_by_scalar_f32", x.data_ptr(), scalar_dev.data_ptr(), x.numel(), out.data_ptr(), _stream())
     return out
