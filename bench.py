@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — MFP / RFD pretrain samples/sec (DCNv2, Criteo shape) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on this box's host cores
+
+One "step" = one pretraining step (dynamic_mask -> forward -> backward -> AdamW -> LR schedule) on one batch of synthetic
+Criteo-shaped ids.  Workload at N=1: BASELINE.json configs[1] — DCNv2 MFP, 39 fields, embed 16, hidden 1000x3, cross 3,
+proj 32, K=25 negatives, mask ratio 0.1, batch 4096 per GPU (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_CRITEO, D, H, NC, NH, P, K, MASK_RATIO, B_PER_GPU = 39, 16, 1000, 3, 3, 32, 25, 0.1, 4096
+N_TRAIN = 1 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--task", default="MFP", choices=["MFP", "RFD"])
+    ap.add_argument("--optimizer-mode", default="sparse", choices=["sparse", "dense_exact"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=5)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+def workload_name(task, batch, n):
+    return (f"DCNv2 {task} pretraining, synthetic Criteo shape (39 fields, V=1085271), embed 16, hidden 1000x3, cross 3, proj 32, "
+            f"K=25, mask_ratio 0.1 (L=3), batch {batch}/GPU x {n} GPU")
+
+
+def config_dict(task):
+    from map_code_b200 import synthetic as S
+    sizes = S.field_sizes("criteo")
+    V = S.vocab_size(sizes)
+    return sizes, V, dict(model_name="DCNv2", embed_size=D, hidden_size=H, num_hidden_layers=NH, num_cross_layers=NC, hidden_act="relu",
+                          hidden_dropout_rate=0.0, embed_dropout_rate=0.0, embed_norm=False, layer_norm_eps=1e-12, pt_neg_num=K,
+                          proj_size=P, input_size=V, num_fields=F_CRITEO, pretrain=True, pt_type=task, RFD_replace="Unigram")
+
+
+# --------------------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, n in enumerate(names):
+                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------------------- CPU arm
+def build_oracle(task, batch, n_train=1 << 16):
+    """The reference's CPU path restated (oracle/map_oracle.py): dense gradients + dense AdamW over every table."""
+    from map_code_b200 import synthetic as S
+    from oracle import map_oracle as O
+    sizes, V, cfgd = config_dict(task)
+    X = S.make_ids(sizes, n_train, seed=0)
+    fc = S.feat_count(X, V)
+    cfg = O.OracleConfig(**cfgd)
+    params = O.init_params(cfg, fc, seed=1)
+    ap = aa = None
+    if task == "MFP":
+        renormed, _, _ = O.nce_noise_distribution(fc)
+        ap, aa = O.alias_build(renormed)
+    tr = O.OracleTrainer(cfg, params, alias_prob=ap, alias_alias=aa, x_train=X, lr=1e-3, weight_decay=5e-2, mask_ratio=MASK_RATIO,
+                         sampling_method="randint", seed=42, lr_lambda=O.cosine_schedule_lambda(0, 100000))
+    return tr, X
+
+
+def run_cpu(task, batch, steps, warmup, budget_s=None):
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr, X = build_oracle(task, batch)
+    times = []
+    t_start = time.perf_counter()
+    i = 0
+    while True:
+        xb = X[(i * batch) % (X.shape[0] - batch):][:batch].contiguous()
+        t0 = time.perf_counter()
+        tr.step(xb)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        i += 1
+        if len(times) >= steps or (budget_s is not None and time.perf_counter() - t_start > budget_s and len(times) >= 3):
+            break
+    tot = sum(times)
+    return dict(value=batch * len(times) / tot, ms_per_step=1e3 * tot / len(times), steps=len(times), cores=torch.get_num_threads())
+
+
+def main_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is pure Python/torch
+    and is restated 1:1 in oracle/map_oracle.py, pinned to it by tests/golden) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_cpu(args.task, args.batch, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": f"{args.task} pretrain samples/sec (DCNv2, Criteo shape)", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.task, args.batch, 1), "device": "host CPU"},
+            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                             "sample": f"{r['steps']} full steps at batch {args.batch} (dense grads + dense AdamW like the reference)"},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------- GPU arm
+def algorithmic(tag):
+    """(bytes, flops) of one launch from its shape tag — the per-unit figures of SURVEY.md §8(d) / DESIGN.md."""
+    if tag is None:
+        return 0.0, 0.0
+    kind = tag[0]
+    if kind == "gemm":
+        _, M, N, Kd = tag[:4]
+        return 4.0 * (M * Kd + N * Kd + M * N), 2.0 * M * N * Kd
+    if kind == "gather":
+        _, n, d = tag
+        return n * (8 + 2 * 4 * d), 0.0
+    if kind == "nce":
+        _, N, Kn, Pn = tag
+        return N * (Kn + 1) * (8 + 4 * Pn + 4 + 4) + N * 4 * Pn, 2.0 * N * (Kn + 1) * Pn * 2
+    if kind == "segred":
+        _, n, d = tag
+        return n * (4 + 4 * d) + n * 4 * d, 0.0
+    if kind == "sparse_adamw":
+        _, n, d = tag
+        return n * (8 + 7 * 4 * d), 0.0
+    return 0.0, 0.0
+
+
+def main_ours(args):
+    import torch.distributed as dist
+    from map_code_b200 import _lib, synthetic as S
+    from map_code_b200.arguments import Config, TrainingArguments
+    from map_code_b200.models import BaseModel
+    from map_code_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} != WORLD_SIZE {world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()  # fail loudly if the sm_100a library is missing
+
+    sizes, V, cfgd = config_dict(args.task)
+    Bg = args.batch * world
+    X_train = S.make_ids(sizes, N_TRAIN, seed=0)
+    fc = S.feat_count(X_train, V)
+    cfgd.update(feat_count=fc, data_dir=None, seed=42, table_grad_mode="sparse")
+    torch.manual_seed(1)
+    model = BaseModel.from_config(Config.from_dict(cfgd)).to(dev)
+
+    class DS:
+        def __init__(self, X):
+            self.X = X
+
+        def __len__(self):
+            return self.X.shape[0]
+
+    targs = TrainingArguments(per_gpu_train_batch_size=args.batch, learning_rate=1e-3, weight_decay=5e-2, lr_sched="cosine",
+                              sampling_method="randint", mask_ratio=MASK_RATIO, pretrain=True, pt_type=args.task, seed=42,
+                              optimizer_mode=args.optimizer_mode)
+    X_dev = X_train.to(dev)
+    trainer = Trainer(model, model.config, targs, DS(X_dev), DS(X_dev))
+    total_steps = 100000
+    if world > 1:
+        from map_code_b200 import dist as mdist
+        eng = mdist.make_sharded_step(trainer, total_steps, 0, world, rank)
+    else:
+        eng = trainer.fused_step(total_steps, 0)
+    eng.use_graph = not args.no_graph
+
+    n_batches = N_TRAIN // Bg
+    def batch(i):  # rank-local slice of global batch i (device resident)
+        r0 = (i % n_batches) * Bg + rank * args.batch
+        return X_dev[r0:r0 + args.batch]
+
+    # ---- warm-up (also captures the CUDA graph)
+    for i in range(max(args.warmup, 3)):
+        eng.step(batch(i))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- timed region: device-resident inputs, CUDA events, no host sync inside
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(args.steps):
+            eng.step(batch(args.warmup + i))
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    loss_after = float(eng.outputs()[0])
+    value = Bg * args.steps / (ms / 1e3)
+
+    # ---- e2e: public API with HOST (pinned) inputs; H2D copy of the ids and D2H read of the loss every step
+    host_batches = [X_train[(i % n_batches) * Bg + rank * args.batch:][:args.batch].contiguous().pin_memory() for i in range(8)]
+    for i in range(3):
+        float(trainer.train_step(host_batches[i % 8])[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        outs = trainer.train_step(host_batches[i % 8])
+        _ = float(outs[0])  # D2H read of the step's loss (synchronises)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = Bg * args.steps / e2e_s
+
+    # ---- per-kernel timing (eager replay of the same schedule, every C-ABI call bracketed by CUDA events on its stream)
+    breakdown, roof, launches = None, None, None
+    pk = peaks()
+    if rank == 0:
+        _lib.LAUNCHES = {}
+        eng.use_graph = False
+        eng.step(batch(0))
+        torch.cuda.synchronize()
+        launches = dict(_lib.LAUNCHES)
+        _lib.LAUNCHES = None
+        _lib.PROFILE = []
+        for i in range(args.profile_steps):
+            eng.step(batch(i + 1))
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, a, b in _lib.PROFILE:
+            key = name
+            d = agg.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, flops=0.0))
+            d["ms"] += a.elapsed_time(b)
+            d["n"] += 1
+            by, fl = algorithmic(tag)
+            d["bytes"] += by
+            d["flops"] += fl
+        _lib.PROFILE = None
+        eng.use_graph = not args.no_graph
+        tot = sum(d["ms"] for d in agg.values())
+        breakdown = []
+        for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            row = {"kernel": name, "calls_per_step": d["n"] / args.profile_steps, "us_per_step": 1e3 * d["ms"] / args.profile_steps,
+                   "share": d["ms"] / tot}
+            if d["flops"] > 0 and "gemm" in name:
+                row["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            if d["bytes"] > 0:
+                row["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            breakdown.append(row)
+        top = breakdown[0]
+        d = agg[top["kernel"]]
+        if "gemm" in top["kernel"]:
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor_sustained"], "traffic": None,
+                    "note": f"TF32 operands (half the bf16 rate); peak = {pk['src']} sustained bf16 cuBLAS; aggregated over all tcgen05 GEMM launches of the step"}
+        else:
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                    "traffic": None, "note": f"peak = {pk['src']} copy bandwidth"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = run_cpu(args.task, args.batch, steps=30, warmup=2, budget_s=15.0)
+        cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} full oracle steps at batch {args.batch} on the host (dense grads + dense AdamW like the reference), {r['ms_per_step']:.0f} ms/step"}
+
+    n_launch = sum(launches.values()) if launches else None
+    line = {
+        "metric": f"{args.task} pretrain samples/sec (DCNv2, Criteo shape)", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (tf32 tensor-core multiplies, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": workload_name(args.task, args.batch, world), "global_batch": Bg, "optimizer_mode": args.optimizer_mode,
+                   "cuda_graph": not args.no_graph, "l2": "inputs larger than L2: tables+optimizer state ~0.9 GB touched at random, a new batch every step; no explicit flush",
+                   "parallelism": "single GPU" if world == 1 else f"row-sharded tables (id mod {world}) + NCCL all-to-all; dense params replicated + allreduce"},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": args.batch * F_CRITEO * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": (n_launch * args.steps) if n_launch else None, "launches_per_step": n_launch,
+        "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown, "loss_after": loss_after,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

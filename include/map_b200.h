@@ -113,8 +113,10 @@ int map_adamw_dense_rows_sparse_grad(float* table, float* m, float* v, int64_t V
  * last-writer-wins like the reference's CPU scatter.  row0 = global index of the first row (row-sharded runs). */
 #define MAP_SAMPLING_RANDINT 0 /* trainer.py:224-225 */
 #define MAP_SAMPLING_NORMAL 1  /* trainer.py:222-223 randperm(F)[:L] */
+/* step_dev (nullable, device int64): offset_eff = offset + 8 * (*step_dev) — lets a captured CUDA graph draw a new
+ * Philox subsequence at every replay (8 = streams per step; the counter is advanced by map_adamw_hyper_step). */
 int map_mask_index_philox(int64_t* masked_index, int64_t B, int L, int F, int sampling_method, uint64_t seed,
-                          uint64_t offset, int64_t row0, map_stream_t stream);
+                          uint64_t offset, int64_t row0, const int64_t* step_dev, map_stream_t stream);
 /* MFP (trainer.py:229-233): labels[b,l] = ids[b, mi[b,l]] ; ids_out = ids with masked fields set to mask_id (3) */
 int map_mfp_mask_apply(const int64_t* ids, const int64_t* masked_index, int64_t B, int F, int L, int64_t mask_id,
                        int64_t* ids_out, int64_t* labels, map_stream_t stream);
@@ -126,8 +128,8 @@ int map_mfp_mask_apply(const int64_t* ids, const int64_t* masked_index, int64_t 
 int map_rfd_replace_philox(const int64_t* ids, const int64_t* masked_index, int64_t B, int F, int L, int mode,
                            const int64_t* x_train, int64_t n_train, const int64_t* idx_low, const int64_t* idx_high,
                            int64_t input_size, uint64_t seed, uint64_t offset_replace, uint64_t offset_field2,
-                           int64_t row0, int64_t* ids_out, float* labels, int64_t* replace_feat_out /* nullable */,
-                           map_stream_t stream);
+                           int64_t row0, const int64_t* step_dev /* nullable */, int64_t* ids_out, float* labels,
+                           int64_t* replace_feat_out /* nullable */, map_stream_t stream);
 
 /* ------------------------------------------------------------------ K5  alias sampler
  * map_alias_build replaces the O(V) Python loop of AliasMultinomial.__init__ (code/nce/alias_multinomial.py:40-73):
@@ -135,7 +137,7 @@ int map_rfd_replace_philox(const int64_t* ids, const int64_t* masked_index, int6
 int map_alias_build(const float* probs, int64_t V, float* out_prob, int64_t* out_alias);
 /* replaces AliasMultinomial.draw (code/nce/alias_multinomial.py:81-97): out[e] for e in [0,n), Philox element elem0+e */
 int map_alias_draw_philox(const float* prob, const int64_t* alias, int64_t V, uint64_t seed, uint64_t offset,
-                          int64_t elem0, int64_t n, int64_t* out, map_stream_t stream);
+                          int64_t elem0, int64_t n, const int64_t* step_dev /* nullable */, int64_t* out, map_stream_t stream);
 
 /* ------------------------------------------------------------------ K6 / K7  fused NCE head
  * replaces NCELoss.forward + IndexLinear._compute_sampled_logit + nce_loss / sampled_softmax_loss
@@ -229,6 +231,12 @@ int map_relu_bwd_f32(const float* dy, int64_t lddy, const float* y, int64_t ldy,
                      map_stream_t stream);
 /* out[i] = x[i] * scalar_dev[0]: chain rule through a scalar loss whose upstream gradient lives on the device */
 int map_scale_by_scalar_f32(const float* x, const float* scalar_dev, int64_t n, float* out, map_stream_t stream);
+/* dst[m, 0..N) = src[m, 0..N) with independent row strides (padding a [N,K] weight to an aligned leading dimension) */
+int map_copy2d_f32(const float* src, int64_t ld_src, int64_t M, int N, float* dst, int64_t ld_dst, map_stream_t stream);
+/* out[i, :] = X[idx[i], :] for an int64 [n_rows, F] matrix — device-resident batcher replacing DataLoader collate +
+ * OurDataset.__getitem__ (code/trainer.py:51-58, code/dataset.py:78-87) */
+int map_gather_rows_i64(const int64_t* X, int64_t n_rows, int F, const int64_t* idx, int64_t n, int64_t* out,
+                        map_stream_t stream);
 /* out[N,M] = in[M,N]^T */
 int map_transpose_f32(const float* in, int64_t ld_in, int64_t M, int64_t N, float* out, int64_t ld_out, map_stream_t stream);
 

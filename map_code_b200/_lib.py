@@ -59,11 +59,11 @@ PROTOTYPES = {
     "map_adamw_multi_tensor": (_i, [_p, _i, _l, _p, _p]),
     "map_adamw_sparse_rows": (_i, [_p, _p, _p, _i, _p, _p, _p, _l, _p, _f, _p]),
     "map_adamw_dense_rows_sparse_grad": (_i, [_p, _p, _p, _l, _i, _p, _p, _p, _p, _f, _p]),
-    "map_mask_index_philox": (_i, [_p, _l, _i, _i, _i, _u64, _u64, _l, _p]),
+    "map_mask_index_philox": (_i, [_p, _l, _i, _i, _i, _u64, _u64, _l, _p, _p]),
     "map_mfp_mask_apply": (_i, [_p, _p, _l, _i, _i, _l, _p, _p, _p]),
-    "map_rfd_replace_philox": (_i, [_p, _p, _l, _i, _i, _i, _p, _l, _p, _p, _l, _u64, _u64, _u64, _l, _p, _p, _p, _p]),
+    "map_rfd_replace_philox": (_i, [_p, _p, _l, _i, _i, _i, _p, _l, _p, _p, _l, _u64, _u64, _u64, _l, _p, _p, _p, _p, _p]),
     "map_alias_build": (_i, [_p, _l, _p, _p]),
-    "map_alias_draw_philox": (_i, [_p, _p, _l, _u64, _u64, _l, _l, _p, _p]),
+    "map_alias_draw_philox": (_i, [_p, _p, _l, _u64, _u64, _l, _l, _p, _p, _p]),
     "map_nce_fwd": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p, _l, _f, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     "map_gather_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
     "map_scatter_add_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
@@ -81,6 +81,8 @@ PROTOTYPES = {
     "map_add3_f32": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _p, _l, _p]),
     "map_relu_bwd_f32": (_i, [_p, _l, _p, _l, _l, _i, _p, _l, _p]),
     "map_scale_by_scalar_f32": (_i, [_p, _p, _l, _p, _p]),
+    "map_copy2d_f32": (_i, [_p, _l, _l, _i, _p, _l, _p]),
+    "map_gather_rows_i64": (_i, [_p, _l, _i, _p, _l, _p, _p]),
     "map_transpose_f32": (_i, [_p, _l, _l, _l, _p, _l, _p]),
 }
 
@@ -115,10 +117,34 @@ def last_error() -> str:
     return load().map_last_error().decode("utf-8", "replace")
 
 
+# number of kernels one entry point launches (for the `gpu_launches` figure of bench.py)
+KERNELS_PER_CALL = {
+    "map_dedup_ids": lambda args: 1 + 3 * ((int(args[2]) + 7) // 8) + 3,   # prep + (hist, scan, scatter) per pass + heads (3)
+    "map_segment_reduce_rows": 2, "map_reduce_sum_f32": 2, "map_bce_logits_fwd": 2, "map_colsum_f32": 2,
+    "map_alias_build": 0,
+}
+PROFILE = None        # set to a list: every call is bracketed by CUDA events -> (name, tag, start_event, end_event)
+CURRENT_TAG = None    # free-form shape tag set by ops.* just before a call (e.g. "4096x1000x624 tn")
+LAUNCHES = None       # set to a dict: name -> number of kernels launched
+
+
 def call(name: str, *args):
     """Calls an int-returning entry point and raises MapB200Error(map_last_error()) on a non-zero code.
     MAP_EUNSUPPORTED is raised as NotImplementedError (mirrors the reference's NotImplementedError sites)."""
-    rc = getattr(load(), name)(*args)
+    global CURRENT_TAG
+    if LAUNCHES is not None:
+        k = KERNELS_PER_CALL.get(name, 1)
+        LAUNCHES[name] = LAUNCHES.get(name, 0) + (k(args) if callable(k) else k)
+    if PROFILE is not None:
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = getattr(load(), name)(*args)
+        ev1.record()
+        PROFILE.append((name, CURRENT_TAG, ev0, ev1))
+        CURRENT_TAG = None
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != MAP_OK:
         msg = f"{name} failed ({rc}): {last_error()}"
         if rc == MAP_EUNSUPPORTED:

@@ -36,7 +36,8 @@ extern "C" int map_alias_build(const float* probs, int64_t V, float* out_prob, i
 namespace mapb {
 __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict__ prob, const int64_t* __restrict__ alias,
                                                          int64_t V, uint64_t seed, uint64_t offset, int64_t elem0, int64_t n,
-                                                         int64_t* __restrict__ out) {
+                                                         const int64_t* __restrict__ step_dev, int64_t* __restrict__ out) {
+    if (step_dev != nullptr) offset += 8ull * (uint64_t)(*step_dev);  // STREAMS_PER_STEP, see mask.cu
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const Philox4 r = philox_elem(seed, offset, (uint64_t)(elem0 + e));
@@ -49,12 +50,12 @@ __global__ void __launch_bounds__(256) alias_draw_kernel(const float* __restrict
 }  // namespace mapb
 
 extern "C" int map_alias_draw_philox(const float* prob, const int64_t* alias, int64_t V, uint64_t seed, uint64_t offset,
-                                     int64_t elem0, int64_t n, int64_t* out, map_stream_t stream) {
+                                     int64_t elem0, int64_t n, const int64_t* step_dev, int64_t* out, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(prob && alias && out && V > 0 && n >= 0 && elem0 >= 0, "map_alias_draw_philox: bad argument");
     if (n == 0) return MAP_OK;
     int64_t blocks = ceil_div(n, 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    alias_draw_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(prob, alias, V, seed, offset, elem0, n, out);
+    alias_draw_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(prob, alias, V, seed, offset, elem0, n, step_dev, out);
     return check_launch("map_alias_draw_philox");
 }

@@ -158,6 +158,26 @@ __global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __res
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] * sv;
 }
 
+__global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, int64_t lds, int64_t M, int N,
+                                                     float* __restrict__ dst, int64_t ldd) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * N; e += stride) {
+        const int64_t m = e / N;
+        const int n = (int)(e - m * N);
+        dst[m * ldd + n] = src[m * lds + n];
+    }
+}
+
+// out[i, :] = X[idx[i], :]  for an int64 [n_rows, F] matrix: the device-resident batcher (replaces DataLoader collate)
+__global__ void __launch_bounds__(256) gather_rows_i64_kernel(const int64_t* __restrict__ X, int F, const int64_t* __restrict__ idx,
+                                                              int64_t n, int64_t* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * F; e += stride) {
+        const int64_t r = e / F;
+        out[e] = X[idx[r] * F + (e - r * F)];
+    }
+}
+
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t M, int64_t N,
                                                         float* __restrict__ out, int64_t ld_out) {
     __shared__ float tile[32][33];
@@ -333,4 +353,25 @@ extern "C" int map_scale_by_scalar_f32(const float* x, const float* scalar_dev, 
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     scale_by_scalar_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, scalar_dev, n, out);
     return check_launch("map_scale_by_scalar_f32");
+}
+
+extern "C" int map_copy2d_f32(const float* src, int64_t ld_src, int64_t M, int N, float* dst, int64_t ld_dst, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(src && dst && M > 0 && N > 0 && ld_src >= N && ld_dst >= N, "map_copy2d_f32: bad argument");
+    int64_t blocks = ceil_div(M * N, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    copy2d_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, ld_src, M, N, dst, ld_dst);
+    return check_launch("map_copy2d_f32");
+}
+
+extern "C" int map_gather_rows_i64(const int64_t* X, int64_t n_rows, int F, const int64_t* idx, int64_t n, int64_t* out,
+                                   map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(n >= 0 && F > 0 && n_rows > 0, "map_gather_rows_i64: bad shape");
+    if (n == 0) return MAP_OK;
+    MAP_REQUIRE(X && idx && out, "map_gather_rows_i64: null pointer");
+    int64_t blocks = ceil_div(n * F, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    gather_rows_i64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, F, idx, n, out);
+    return check_launch("map_gather_rows_i64");
 }

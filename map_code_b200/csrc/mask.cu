@@ -9,8 +9,17 @@ namespace mapb {
 constexpr int kMaxFields = 64;
 
 // masked_index[b, l]; element index for Philox = (row0 + b) * L + l
+// RNG offsets: offset_eff = offset + STREAMS_PER_STEP * (*step_dev) when step_dev != NULL, so a captured CUDA graph
+// draws a fresh subsequence at every replay (the device step counter is advanced by map_adamw_hyper_step).
+constexpr uint64_t kStreamsPerStep = 8;
+__device__ __forceinline__ uint64_t eff_offset(uint64_t offset, const int64_t* step_dev) {
+    return step_dev != nullptr ? offset + kStreamsPerStep * (uint64_t)(*step_dev) : offset;
+}
+
 __global__ void __launch_bounds__(256) mask_index_kernel(int64_t* __restrict__ mi, int64_t B, int L, int F, int method,
-                                                         uint64_t seed, uint64_t offset, int64_t row0) {
+                                                         uint64_t seed, uint64_t offset, int64_t row0,
+                                                         const int64_t* __restrict__ step_dev) {
+    offset = eff_offset(offset, step_dev);
     if (method == MAP_SAMPLING_RANDINT) {
         const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= B * L) return;
@@ -62,8 +71,11 @@ __global__ void __launch_bounds__(256) rfd_replace_kernel(const int64_t* __restr
                                                           const int64_t* __restrict__ idx_low,
                                                           const int64_t* __restrict__ idx_high, int64_t input_size,
                                                           uint64_t seed, uint64_t off_rep, uint64_t off_f2, int64_t row0,
+                                                          const int64_t* __restrict__ step_dev,
                                                           int64_t* __restrict__ ids_out, float* __restrict__ labels,
                                                           int64_t* __restrict__ rep_out) {
+    off_rep = eff_offset(off_rep, step_dev);
+    off_f2 = eff_offset(off_f2, step_dev);
     const int lane = threadIdx.x & 31;
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= B) return;
@@ -106,7 +118,7 @@ __global__ void __launch_bounds__(256) rfd_replace_kernel(const int64_t* __restr
 }  // namespace mapb
 
 extern "C" int map_mask_index_philox(int64_t* masked_index, int64_t B, int L, int F, int sampling_method, uint64_t seed,
-                                     uint64_t offset, int64_t row0, map_stream_t stream) {
+                                     uint64_t offset, int64_t row0, const int64_t* step_dev, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(masked_index && B >= 0 && L >= 0 && F >= 1 && F <= kMaxFields && L <= F, "map_mask_index_philox: bad shape B=%lld L=%d F=%d", (long long)B, L, F);
     if (sampling_method != MAP_SAMPLING_RANDINT && sampling_method != MAP_SAMPLING_NORMAL) {
@@ -115,7 +127,7 @@ extern "C" int map_mask_index_philox(int64_t* masked_index, int64_t B, int L, in
     }
     if (B == 0 || L == 0) return MAP_OK;
     const int64_t threads = (sampling_method == MAP_SAMPLING_RANDINT) ? B * L : B;
-    mask_index_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, as_stream(stream)>>>(masked_index, B, L, F, sampling_method, seed, offset, row0);
+    mask_index_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, as_stream(stream)>>>(masked_index, B, L, F, sampling_method, seed, offset, row0, step_dev);
     return check_launch("map_mask_index_philox");
 }
 
@@ -132,8 +144,8 @@ extern "C" int map_mfp_mask_apply(const int64_t* ids, const int64_t* masked_inde
 extern "C" int map_rfd_replace_philox(const int64_t* ids, const int64_t* masked_index, int64_t B, int F, int L, int mode,
                                       const int64_t* x_train, int64_t n_train, const int64_t* idx_low, const int64_t* idx_high,
                                       int64_t input_size, uint64_t seed, uint64_t offset_replace, uint64_t offset_field2,
-                                      int64_t row0, int64_t* ids_out, float* labels, int64_t* replace_feat_out,
-                                      map_stream_t stream) {
+                                      int64_t row0, const int64_t* step_dev, int64_t* ids_out, float* labels,
+                                      int64_t* replace_feat_out, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(ids && ids_out && labels && (L == 0 || masked_index), "map_rfd_replace_philox: null pointer");
     MAP_REQUIRE(B >= 0 && F >= 1 && F <= kMaxFields && L >= 0, "map_rfd_replace_philox: bad shape");
@@ -155,6 +167,6 @@ extern "C" int map_rfd_replace_philox(const int64_t* ids, const int64_t* masked_
     if (B == 0) return MAP_OK;
     rfd_replace_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(
         ids, masked_index, B, F, L, mode, x_train, n_train, idx_low, idx_high, input_size, seed, offset_replace, offset_field2,
-        row0, ids_out, labels, replace_feat_out);
+        row0, step_dev, ids_out, labels, replace_feat_out);
     return check_launch("map_rfd_replace_philox");
 }

@@ -1,0 +1,450 @@
+"""FusedStep — the whole pretraining / finetuning step as one static kernel schedule, captured in a CUDA graph.
+
+Replaces the inner-loop body of Trainer.MFP_pretrain / RFD_pretrain / train (reference code/trainer.py:306-331, 431-455,
+122-143): dynamic_mask -> forward -> backward -> AdamW -> LR schedule, with
+  * no host synchronisation inside the step (loss / accuracy stay on the device, the Philox offsets and the learning
+    rate are derived from a device-side step counter, so the captured graph is replayed verbatim every step);
+  * no autograd: the backward pass is scheduled explicitly, ReLU masks / residuals / CrossNet products are fused into
+    the GEMM epilogues, `torch.cat` does not exist (producers write into column slices of the `final` buffer);
+  * table gradients never materialise as [V, D]: sort-dedup -> compact [U, D] -> row-wise AdamW ("sparse", default) or
+    an exact dense sweep ("dense_exact" = the reference's dense transformers.AdamW semantics).
+It operates directly on the nn.Parameters of a map_code_b200.models model, so state_dict()/save/load keep working.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+
+STREAM_MASK_FIELD, STREAM_RFD_REPLACE, STREAM_ALIAS, STREAM_RFD_FIELD2 = 0, 1, 2, 3
+
+
+def is_no_decay(name: str) -> bool:
+    """reference trainer.py:61: no_decay = ["bias", "LayerNorm.weight"] matched as substrings."""
+    return any(nd in name for nd in ("bias", "LayerNorm.weight"))
+
+
+class _Table:
+    """One [V, D] table with AdamW state and the dedup plan of its per-step id stream."""
+
+    def __init__(self, name, param, n_ids, weight_decay, device):
+        self.name, self.p = name, param
+        self.V, self.D = param.shape
+        self.m = torch.zeros_like(param.data)
+        self.v = torch.zeros_like(param.data)
+        self.wd = weight_decay
+        self.n_ids = n_ids
+        self.plan: Optional[ops.DedupPlan] = None  # may be shared between tables fed by the same id stream
+        self.grad = torch.empty(n_ids, self.D, dtype=torch.float32, device=device)
+
+
+class FusedStep:
+    def __init__(self, model, *, batch_size: int, mask_ratio: float = 0.1, sampling_method: str = "randint",
+                 lr: float = 1e-3, weight_decay: float = 5e-2, betas=(0.9, 0.999), eps: float = 1e-8, sched: str = "cosine",
+                 warmup_steps: int = 0, total_steps: int = 1000, seed: int = 42, optimizer_mode: str = "sparse",
+                 x_train: Optional[torch.Tensor] = None, idx_low=None, idx_high=None, use_graph: bool = True,
+                 row0: int = 0, global_batch: Optional[int] = None, gemm_backend: Optional[str] = None):
+        cfg = model.config
+        self.model, self.cfg = model, cfg
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise _lib.MapB200Error("FusedStep needs the model on a CUDA device (no CPU path)")
+        if optimizer_mode not in ("sparse", "dense_exact"):
+            raise ValueError(optimizer_mode)
+        if sched.lower() not in ("cosine", "const"):
+            raise NotImplementedError(sched)  # reference trainer.py:82-83
+        self.name = model.model_name.lower()
+        if self.name not in ("dcnv2", "dnn", "deepfm"):
+            raise NotImplementedError(f"FusedStep: backbone {model.model_name}")
+        self.B, self.F, self.D = batch_size, cfg.num_fields, cfg.embed_size
+        self.V = cfg.input_size
+        self.in_dim = self.F * self.D
+        self.mode = ("MFP" if cfg.pt_type == "MFP" else "RFD") if cfg.pretrain else "CTR"
+        if cfg.pretrain and cfg.pt_type not in ("MFP", "RFD"):
+            raise NotImplementedError(cfg.pt_type)
+        self.L = int(self.F * mask_ratio) if cfg.pretrain else 0  # trainer.py:220
+        self.sampling_method = sampling_method
+        self.rfd_mode = getattr(cfg, "RFD_replace", "Unigram")
+        self.seed, self.row0 = seed, row0
+        self.global_batch = global_batch or batch_size
+        self.optimizer_mode = optimizer_mode
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.sched = _lib.SCHED_COSINE if sched.lower() == "cosine" else _lib.SCHED_CONST
+        self.warmup_steps, self.total_steps = warmup_steps, total_steps
+        self.use_graph = use_graph
+        self.gemm_backend = gemm_backend
+        self.x_train, self.idx_low, self.idx_high = x_train, idx_low, idx_high
+        if self.mode == "RFD" and self.rfd_mode in ("Unigram", "Whole-Unigram") and x_train is None:
+            raise ValueError("RFD Unigram replacement needs the training id matrix on the device (x_train)")
+        if sampling_method not in ("randint", "normal"):
+            raise NotImplementedError(sampling_method)
+        self._collect_params()
+        self._alloc()
+        self.graph = None
+        self.steps_done = 0
+        self.overrides = None
+
+    # ------------------------------------------------------------------------------------------------ setup
+    def _collect_params(self):
+        m, cfg = self.model, self.cfg
+        self.embed_w = m.embed.embedding.weight
+        self.cross: List = list(m.cross_net.cross_layers) if self.name == "dcnv2" else []
+        if self.name == "dcnv2":
+            mlp = m.parallel_dnn.dnn if cfg.num_hidden_layers > 0 else []
+        else:
+            mlp = m.dnn.dnn
+        self.mlp = [mod for i, mod in enumerate(mlp) if i % 3 == 0]
+        self.H = cfg.hidden_size if self.mlp else 0
+        self.has_fm = self.name == "deepfm"
+        # layout of `final`: DCNv2 [cross | mlp], DNN [mlp], DeepFM-pretrain [mlp | lr_fm]
+        self.cross_off, self.cross_w = 0, (self.in_dim if self.name == "dcnv2" else 0)
+        self.mlp_off = self.cross_w
+        self.final_dim = self.cross_w + self.H + (1 if (self.has_fm and cfg.pretrain) else 0)
+        self.ld_final = (self.final_dim + 3) // 4 * 4  # TMA rows must be 16-byte multiples
+        if self.has_fm:
+            raise NotImplementedError("FusedStep: DeepFM is scheduled through the module path in this revision")
+
+    def _alloc(self):
+        B, F, D, dev, cfg = self.B, self.F, self.D, self.dev, self.cfg
+        f32 = dict(dtype=torch.float32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        E = lambda *s: torch.empty(*s, **f32)
+        self.in_ids = torch.zeros(B, F, **i64)            # static graph inputs
+        self.in_labels = torch.zeros(B, **f32)            # CTR labels
+        self.step_counter = torch.zeros(1, **i64)
+        self.hyper = torch.zeros(8, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.acc_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(4, **f32)
+        self.red_ws = torch.empty(int(_lib.load().map_reduce_workspace_bytes(0)), dtype=torch.uint8, device=dev)
+        self.ids_m = torch.empty(B, F, **i64)
+        if self.mode != "CTR":
+            if self.L < 1:
+                raise ValueError(f"mask_ratio too small: int(num_fields * mask_ratio) = {self.L} masked fields")
+            self.mi = torch.empty(B, self.L, **i64)
+        # activations
+        self.X0 = E(B, self.in_dim)
+        self.final = torch.zeros(B, self.ld_final, **f32)
+        nc = len(self.cross)
+        self.Xc = [self.X0] + [E(B, self.in_dim) for _ in range(max(nc - 1, 0))]  # inputs of each cross layer
+        self.U = [E(B, self.in_dim) for _ in range(nc)]
+        nh = len(self.mlp)
+        self.Hs = [E(B, self.H) for _ in range(max(nh - 1, 0))]                   # outputs of mlp layers except the last
+        self.cross_out = self.final[:, self.cross_off:self.cross_off + self.cross_w] if nc else None
+        self.mlp_out = self.final[:, self.mlp_off:self.mlp_off + self.H] if nh else None
+        self.final_v = self.final[:, :self.final_dim]
+        # dense parameter gradients + AdamW state
+        self.dense: Dict[str, torch.nn.Parameter] = {}
+        for n, p in self.model.named_parameters():
+            if p.requires_grad and not hasattr(p, "_map_table_grad"):
+                self.dense[n] = p
+        self.grads = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
+        self.exp_avg = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
+        self.exp_avg_sq = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
+        entries = [(p.data, self.grads[n], self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None)
+                   for n, p in self.dense.items()]
+        self.adam_table, self.adam_n, self.adam_max = ops.make_adamw_tensor_list(entries, dev)
+        # backward scratch
+        md = max(self.in_dim, self.H, 1)
+        self.dA = E(B, md)   # ping-pong gradient buffers through the towers
+        self.dB = E(B, md)
+        self.dU = E(B, self.in_dim) if nc else None
+        self.dX0_acc = E(B, self.in_dim) if nc else None
+        self.dX0_mlp = E(B, self.in_dim) if nh else None
+        self.dE = E(B, self.in_dim)
+        self.colsum_ws = torch.empty(int(_lib.load().map_colsum_workspace_bytes(B, max(self.ld_final, F * cfg.proj_size if cfg.pretrain else 1, md))),
+                                     dtype=torch.uint8, device=dev)
+        # tables
+        self.tables: Dict[str, _Table] = {}
+        emb_name = "embed.embedding.weight"
+        t = _Table(emb_name, self.embed_w, B * F, 0.0 if is_no_decay(emb_name) else self.wd, dev)
+        t.plan = ops.DedupPlan(B * F, self.V, dev)
+        self.tables[emb_name] = t
+        # heads
+        if self.mode == "MFP":
+            P, K, L = cfg.proj_size, cfg.pt_neg_num, self.L
+            N = B * L
+            self.N, self.P, self.K = N, P, K
+            crit = self.model.mfp_criterion
+            self.labels = torch.empty(B, L, **i64)
+            self.enc = E(B, F * P)
+            self.d_enc = torch.zeros(B, F * P, **f32)
+            self.sel = E(max(N, 1), P)
+            self.noise = torch.empty(max(N, 1), K, **i64)
+            self.logits = E(max(N, 1), K + 1)
+            self.ids_all = torch.empty(max(N, 1), K + 1, **i64)
+            self.loss_pos = E(max(N, 1))
+            self.dz = E(max(N, 1), K + 1)
+            self.d_sel = E(max(N, 1), P)
+            n_occ = max(N, 1) * (K + 1)
+            plan = ops.DedupPlan(n_occ, self.V, dev)
+            te = _Table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.emb.weight") else self.wd, dev)
+            tb = _Table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.bias.weight") else self.wd, dev)
+            te.plan = tb.plan = plan
+            self.tables[te.name], self.tables[tb.name] = te, tb
+            self.norm_term = float(crit.norm_term)
+            self.loss_type = crit.loss_type
+            if crit.reduction != "elementwise_mean":
+                raise NotImplementedError("FusedStep supports the default reduction='elementwise_mean'")
+        elif self.mode == "RFD":
+            P = cfg.proj_size
+            self.labels = E(B, F)
+            self.rfd_h = E(B, F * P)
+            self.rfd_logits = E(B, F)
+            self.d_logits = E(B, F)
+            self.d_h = E(B, F * P)
+        else:
+            self.ctr_logits = E(B, 1)
+            self.d_logits = E(B, 1)
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _gemm(self, *a, **k):
+        return ops.gemm(*a, backend=self.gemm_backend, **k)
+
+    def _linear_bwd(self, dZ, X_in, layer_name, W, M, N, K, dX_out=None, dX_epilogue=_lib.EPI_NONE, aux0=None):
+        """Given dZ [M,N] (gradient at the pre-activation), input X_in [M,K] and weight W [N,K]:
+        dW = dZ^T X, db = colsum(dZ), optionally dX = dZ W (with a fused epilogue)."""
+        self._gemm(dZ, X_in, self.grads[layer_name + ".weight"], N, K, M, trans_a=True, trans_b=True)
+        ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
+        if dX_out is not None:
+            self._gemm(dZ, W, dX_out, M, K, N, trans_b=True, epilogue=dX_epilogue, aux0=aux0)
+
+    # ------------------------------------------------------------------------------------------------ the step
+    def _draw_and_mask(self):
+        B, F, L = self.B, self.F, self.L
+        if self.mode == "CTR":
+            return self.in_ids
+        ov = self.overrides
+        if ov is not None:  # parity tests feed the reference's index tensors instead of drawing
+            if "masked_index" in ov:
+                self.mi.copy_(ov["masked_index"])
+            if "input_ids_masked" in ov:  # the reference's own dynamic_mask output
+                self.ids_m.copy_(ov["input_ids_masked"])
+                self.labels.copy_(ov["labels"])
+                return self.ids_m
+            if self.mode == "MFP":
+                ops.mfp_mask_apply(self.in_ids, self.mi, 3, ids_out=self.ids_m, labels=self.labels)
+                return self.ids_m
+        ops.mask_index(B, L, F, self.sampling_method, self.seed, STREAM_MASK_FIELD, row0=self.row0, out=self.mi, step_dev=self.step_counter)
+        if self.mode == "MFP":
+            ops.mfp_mask_apply(self.in_ids, self.mi, 3, ids_out=self.ids_m, labels=self.labels)
+        else:
+            ops.rfd_replace(self.in_ids, self.mi, self.rfd_mode, self.seed, STREAM_RFD_REPLACE, STREAM_RFD_FIELD2, x_train=self.x_train,
+                            idx_low=self.idx_low, idx_high=self.idx_high, input_size=self.V, row0=self.row0, ids_out=self.ids_m,
+                            labels=self.labels, step_dev=self.step_counter)
+        return self.ids_m
+
+    def _forward_backbone(self, ids):
+        B, in_dim, H = self.B, self.in_dim, self.H
+        ops.emb_gather(self.embed_w.data, ids, out=self.X0)
+        nc = len(self.cross)
+        for i, layer in enumerate(self.cross):       # layers.py:197-201 with the product fused in the epilogue
+            out = self.cross_out if i == nc - 1 else self.Xc[i + 1]
+            self._gemm(self.Xc[i], layer.weight.data, out, B, in_dim, in_dim, epilogue=_lib.EPI_CROSS, bias=layer.bias.data,
+                       aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i])
+        x, k = self.X0, in_dim
+        nh = len(self.mlp)
+        for i, layer in enumerate(self.mlp):         # layers.py:187-188, ReLU fused
+            out = self.mlp_out if i == nh - 1 else self.Hs[i]
+            self._gemm(x, layer.weight.data, out, B, H, k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data)
+            x, k = out, H
+
+    def _backward_backbone(self, head_W, dHead, n_head):
+        """head_W [n_head, final_dim] is the weight of the first head layer, dHead [B, n_head] the gradient at its
+        pre-activation.  Propagates into the towers and the embedding table."""
+        B, in_dim, H = self.B, self.in_dim, self.H
+        nc, nh = len(self.cross), len(self.mlp)
+        pref_c = "cross_net.cross_layers"
+        pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
+        # ---- MLP tower: gradient through the last ReLU is fused into the dgrad GEMM's epilogue
+        if nh:
+            dZ = self.dA[:, :H]
+            self._gemm(dHead, head_W[:, self.mlp_off:self.mlp_off + H], dZ, B, H, n_head, trans_b=True,
+                       epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out)
+            for i in range(nh - 1, -1, -1):
+                layer = self.mlp[i]
+                x_in = self.X0 if i == 0 else self.Hs[i - 1]
+                k_in = in_dim if i == 0 else H
+                nxt = (self.dB if dZ.data_ptr() == self.dA.data_ptr() else self.dA)
+                if i > 0:
+                    dX = nxt[:, :H]
+                    self._linear_bwd(dZ, x_in, f"{pref_m}.{3 * i}", layer.weight.data, B, H, k_in, dX_out=dX,
+                                     dX_epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.Hs[i - 1])
+                    dZ = dX
+                else:
+                    self._linear_bwd(dZ, x_in, f"{pref_m}.{3 * i}", layer.weight.data, B, H, k_in, dX_out=self.dX0_mlp)
+        # ---- CrossNet: G = d(loss)/d(X_{i+1});  dU = G*X0, dX0 += G*U_i, dXi = G + dU W_i   (autograd of layers.py:200)
+        if nc:
+            G = self.dA[:, :in_dim]
+            self._gemm(dHead, head_W[:, self.cross_off:self.cross_off + in_dim], G, B, in_dim, n_head, trans_b=True)
+            for i in range(nc - 1, -1, -1):
+                layer = self.cross[i]
+                ops.cross_bwd_pre(G, self.X0, self.U[i], self.dU, self.dX0_acc, accumulate=(i != nc - 1))
+                Gn = (self.dB if G.data_ptr() == self.dA.data_ptr() else self.dA)[:, :in_dim]
+                self._linear_bwd(self.dU, self.Xc[i], f"{pref_c}.{i}", layer.weight.data, B, in_dim, in_dim, dX_out=Gn,
+                                 dX_epilogue=_lib.EPI_ADD, aux0=G)
+                G = Gn
+            ops.add3(G, self.dX0_acc, self.dX0_mlp if nh else None, self.dE)
+        else:
+            ops.copy2d(self.dX0_mlp, self.dE)
+        # ---- embedding table: dedup + segmented row sum (K2)
+        t = self.tables["embed.embedding.weight"]
+        t.plan.run(self.ids_cur.view(-1))
+        t.plan.reduce_rows(self.dE, self.D, out=t.grad)
+
+    def _head_mfp(self):
+        cfg, B, F, P, K, N, L = self.cfg, self.B, self.F, self.P, self.K, self.N, self.L
+        m = self.model
+        enc_W, enc_b = m.feat_encoder.weight.data, m.feat_encoder.bias.data
+        crit = m.mfp_criterion
+        self._gemm(self.final_v, enc_W, self.enc, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b)   # models.py:74
+        ops.gather_slices(self.enc, self.mi, F, P, out=self.sel)                                                   # models.py:75
+        if self.overrides is not None and "noise" in self.overrides:
+            self.noise.copy_(self.overrides["noise"].reshape(N, K))
+        else:
+            ops.alias_draw(crit.alias.prob, crit.alias.alias, self.seed, STREAM_ALIAS, N * K, elem0=self.row0 * L * K,
+                           out=self.noise.view(-1), step_dev=self.step_counter)
+        self.acc_count.zero_()
+        n_global = self.global_batch * L
+        ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
+                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
+                    loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
+        ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
+        # ---- backward of the head
+        self.d_enc.zero_()
+        ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
+        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
+        te.plan.run(self.ids_all.view(-1))
+        te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
+        self._gemm(self.d_enc, self.final_v, self.grads["feat_encoder.weight"], F * P, self.final_dim, B, trans_a=True, trans_b=True)
+        ops.colsum(self.d_enc, out=self.grads["feat_encoder.bias"], ws=self.colsum_ws)
+        self._backward_backbone(enc_W, self.d_enc, F * P)
+
+    def _head_rfd(self):
+        cfg, B, F = self.cfg, self.B, self.F
+        P = cfg.proj_size
+        l0, l2 = getattr(self.model.pred_rfd, "0"), getattr(self.model.pred_rfd, "2")
+        self._gemm(self.final_v, l0.weight.data, self.rfd_h, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS_RELU, bias=l0.bias.data)
+        self._gemm(self.rfd_h, l2.weight.data, self.rfd_logits, B, F, F * P, epilogue=_lib.EPI_BIAS, bias=l2.bias.data)
+        ops.bce_logits(self.rfd_logits.view(-1), self.labels.view(-1), stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
+        if self.global_batch != B:  # mean over the GLOBAL batch
+            ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
+        # backward
+        self._linear_bwd(self.d_logits, self.rfd_h, "pred_rfd.2", l2.weight.data, B, F, F * P, dX_out=self.d_h,
+                         dX_epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h)
+        self._gemm(self.d_h, self.final_v, self.grads["pred_rfd.0.weight"], F * P, self.final_dim, B, trans_a=True, trans_b=True)
+        ops.colsum(self.d_h, out=self.grads["pred_rfd.0.bias"], ws=self.colsum_ws)
+        self._backward_backbone(l0.weight.data, self.d_h, F * P)
+
+    def _head_ctr(self):
+        B = self.B
+        fc = self.model.fc_out
+        self._gemm(self.final_v, fc.weight.data, self.ctr_logits, B, 1, self.final_dim, epilogue=_lib.EPI_BIAS, bias=fc.bias.data)
+        ops.bce_logits(self.ctr_logits.view(-1), self.in_labels, stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
+        if self.global_batch != B:
+            ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
+        self._gemm(self.d_logits, self.final_v, self.grads["fc_out.weight"], 1, self.final_dim, B, trans_a=True, trans_b=True)
+        ops.colsum(self.d_logits, out=self.grads["fc_out.bias"], ws=self.colsum_ws)
+        self._backward_backbone(fc.weight.data, self.d_logits, 1)
+
+    def _ratio(self):
+        if not hasattr(self, "_ratio_t"):
+            self._ratio_t = torch.full((1,), self.B / self.global_batch, dtype=torch.float32, device=self.dev)
+        return self._ratio_t
+
+    def forward_backward(self):
+        """mask -> forward -> backward on the current stream; gradients land in self.grads / self.tables[*].grad."""
+        self.ids_cur = self._draw_and_mask()
+        self._forward_backbone(self.ids_cur)
+        if self.mode == "MFP":
+            self._head_mfp()
+        elif self.mode == "RFD":
+            self._head_rfd()
+        else:
+            self._head_ctr()
+
+    def reduce_gradients(self):
+        """hook for data-parallel runs (dist.py installs the all-reduce / all-to-all here)."""
+
+    def optimizer_step(self):
+        b1, b2 = self.betas
+        ops.adamw_hyper_step(self.hyper, self.step_counter, self.lr, b1, b2, self.eps, self.sched, self.warmup_steps, self.total_steps)
+        ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
+        for t in self.tables.values():
+            if self.optimizer_mode == "sparse":
+                ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.plan, t.grad, self.hyper, t.wd)
+            else:
+                ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.plan, t.grad, self.hyper, t.wd)
+
+    def _step_body(self):
+        self.forward_backward()
+        self.reduce_gradients()
+        self.optimizer_step()
+
+    # ------------------------------------------------------------------------------------------------ public API
+    def capture(self):
+        """Warm up on a side stream (lazy allocations, TMA descriptor attribute) and capture the step in a CUDA graph."""
+        if not self.use_graph or self.graph is not None:
+            return
+        snap = self._snapshot()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        self.graph = g
+        self._restore(snap)
+
+    def _state_tensors(self):
+        ts = [self.step_counter, self.hyper]
+        ts += [p.data for p in self.dense.values()] + list(self.exp_avg.values()) + list(self.exp_avg_sq.values())
+        for t in self.tables.values():
+            ts += [t.p.data, t.m, t.v]
+        return ts
+
+    def _snapshot(self):
+        """The warm-up / capture passes execute real optimizer steps; training state is put back afterwards.  Tables are
+        snapshotted too (cheap at Criteo scale; at the 100M-row sweep call capture() before loading weights instead)."""
+        return [t.clone() for t in self._state_tensors()]
+
+    def _restore(self, snap):
+        for t, s in zip(self._state_tensors(), snap):
+            t.copy_(s)
+
+    def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        """One training step on a device-resident batch [B, F] (int64).  No host synchronisation."""
+        self.in_ids.copy_(input_ids, non_blocking=True)
+        if self.mode == "CTR":
+            self.in_labels.copy_(labels.to(torch.float32), non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.steps_done += 1
+        return self.loss if self.mode == "MFP" else self.stats[0:1]
+
+    def outputs(self):
+        """Reference-style output tuple of the last step (device tensors; reading them synchronises)."""
+        if self.mode == "MFP":
+            return (self.loss.view(()), self.B * self.L, self.acc_count.view(()))
+        if self.mode == "RFD":
+            cnt = self.B * self.F
+            return (self.stats[0], cnt, self.stats[1] / cnt, self.stats[2] / cnt)
+        return (self.stats[0], self.ctr_logits)
+
+    def dense_table_grad(self, name: str) -> torch.Tensor:
+        """[V, D] view of a table's compact gradient == the `.grad` the reference materialises (parity tests)."""
+        t = self.tables[name]
+        dense = torch.zeros(t.V, t.D, dtype=torch.float32, device=self.dev)
+        t.plan.scatter_dense(t.grad, t.D, dense)
+        return dense

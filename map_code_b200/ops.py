@@ -48,6 +48,8 @@ def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tenso
         out = torch.empty(*ids.shape, D, dtype=torch.float32, device=table.device)
     if ids.numel() == 0:
         return out
+    if _lib.PROFILE is not None:
+        _lib.CURRENT_TAG = ("gather", ids.numel(), D)
     call("map_emb_gather_f32", table.data_ptr(), V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), _ptr(oob_flag), _stream())
     return out
 
@@ -77,6 +79,8 @@ class DedupPlan:
                     group: int = 1, out: Optional[torch.Tensor] = None, scalar_out: Optional[torch.Tensor] = None):
         if out is None:
             out = torch.empty(self.n, D, dtype=torch.float32, device=rows.device)
+        if _lib.PROFILE is not None:
+            _lib.CURRENT_TAG = ("segred", self.n, D)
         call("map_segment_reduce_rows", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
              self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, out.data_ptr(),
              _ptr(scalar_out), _stream())
@@ -119,6 +123,8 @@ def adamw_multi_tensor(table: torch.Tensor, n: int, max_elems: int, hyper: torch
 
 def adamw_sparse_rows(table, m, v, plan: DedupPlan, grad_compact, hyper, weight_decay: float):
     D = table.shape[1]
+    if _lib.PROFILE is not None:
+        _lib.CURRENT_TAG = ("sparse_adamw", plan.n, D)
     call("map_adamw_sparse_rows", table.data_ptr(), m.data_ptr(), v.data_ptr(), D, plan.uniq.data_ptr(), grad_compact.data_ptr(),
          plan.n_unique.data_ptr(), plan.n, hyper.data_ptr(), float(weight_decay), _stream())
 
@@ -131,7 +137,7 @@ def adamw_dense_rows_sparse_grad(table, m, v, plan: DedupPlan, grad_compact, hyp
 
 # ------------------------------------------------------------------------------------------------ K8 / K9
 def mask_index(B: int, L: int, F: int, sampling_method: str, seed: int, offset: int, row0: int = 0, device="cuda",
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     if sampling_method == "randint":
         sm = _lib.SAMPLING_RANDINT
     elif sampling_method == "normal":
@@ -140,7 +146,7 @@ def mask_index(B: int, L: int, F: int, sampling_method: str, seed: int, offset: 
         raise NotImplementedError(sampling_method)  # reference: trainer.py:226-227
     if out is None:
         out = torch.empty(B, L, dtype=torch.int64, device=device)
-    call("map_mask_index_philox", out.data_ptr(), B, L, F, sm, seed, offset, row0, _stream())
+    call("map_mask_index_philox", out.data_ptr(), B, L, F, sm, seed, offset, row0, _ptr(step_dev), _stream())
     return out
 
 
@@ -158,7 +164,8 @@ def mfp_mask_apply(ids: torch.Tensor, masked_index: torch.Tensor, mask_id: int =
 
 
 def rfd_replace(ids, masked_index, mode: str, seed: int, offset_replace: int, offset_field2: int = 0, x_train=None,
-                idx_low=None, idx_high=None, input_size: int = 0, row0: int = 0, ids_out=None, labels=None, replace_out=None):
+                idx_low=None, idx_high=None, input_size: int = 0, row0: int = 0, ids_out=None, labels=None, replace_out=None,
+                step_dev: Optional[torch.Tensor] = None):
     if mode not in _lib.RFD_MODES:
         raise NotImplementedError(mode)  # reference: trainer.py:261-262
     _check(ids, torch.int64, "ids")
@@ -171,7 +178,7 @@ def rfd_replace(ids, masked_index, mode: str, seed: int, offset_replace: int, of
         labels = torch.empty(B, F, dtype=torch.float32, device=ids.device)
     n_train = 0 if x_train is None else x_train.shape[0]
     call("map_rfd_replace_philox", ids.data_ptr(), masked_index.data_ptr(), B, F, L, _lib.RFD_MODES[mode], _ptr(x_train), n_train,
-         _ptr(idx_low), _ptr(idx_high), input_size, seed, offset_replace, offset_field2, row0, ids_out.data_ptr(),
+         _ptr(idx_low), _ptr(idx_high), input_size, seed, offset_replace, offset_field2, row0, _ptr(step_dev), ids_out.data_ptr(),
          labels.data_ptr(), _ptr(replace_out), _stream())
     return ids_out, labels
 
@@ -188,12 +195,12 @@ def alias_build(probs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def alias_draw(prob: torch.Tensor, alias: torch.Tensor, seed: int, offset: int, n: int, elem0: int = 0,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     _check(prob, torch.float32, "prob")
     _check(alias, torch.int64, "alias")
     if out is None:
         out = torch.empty(n, dtype=torch.int64, device=prob.device)
-    call("map_alias_draw_philox", prob.data_ptr(), alias.data_ptr(), prob.numel(), seed, offset, elem0, n, out.data_ptr(), _stream())
+    call("map_alias_draw_philox", prob.data_ptr(), alias.data_ptr(), prob.numel(), seed, offset, elem0, n, _ptr(step_dev), out.data_ptr(), _stream())
     return out
 
 
@@ -221,6 +228,8 @@ def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: st
         d_input = torch.empty(N, P, dtype=torch.float32, device=dev)
     if grad_scale is None:
         grad_scale = 1.0 / max(N, 1)
+    if _lib.PROFILE is not None:
+        _lib.CURRENT_TAG = ("nce", N, K, P)
     call("map_nce_fwd", inp.data_ptr(), N, P, K, target.data_ptr(), noise.data_ptr(), emb.data_ptr(), bias.data_ptr(),
          logq.data_ptr(), emb.shape[0], float(norm_term), _lib.NCE_LOSS[loss_type], float(grad_scale), logits.data_ptr(),
          _ptr(ids_out), loss_pos.data_ptr(), dz.data_ptr(), _ptr(d_input), _ptr(acc_count), _stream())
@@ -316,6 +325,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, 
     g.aux_out, g.ld_aux_out = (aux_out.data_ptr(), _ld(aux_out)) if aux_out is not None else (None, 0)
     backend = backend or gemm_backend()
     lib = _lib.load()
+    if _lib.PROFILE is not None:
+        _lib.CURRENT_TAG = ("gemm", M, N, K, int(trans_a), int(trans_b), int(epilogue))
     if backend == "tcgen05" and lib.map_gemm_tf32_supported(C.byref(g)):
         call("map_gemm_tf32_tcgen05", C.byref(g), _stream())
     else:  # skinny / unaligned shapes (N < 16, N % 4 != 0) and the exact-fp32 test mode
@@ -374,4 +385,20 @@ def scale_by_scalar(x: torch.Tensor, scalar_dev: torch.Tensor, out: Optional[tor
     if out is None:
         out = torch.empty_like(x)
     call("map_scale_by_scalar_f32", x.data_ptr(), scalar_dev.data_ptr(), x.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def copy2d(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    M, N = src.shape
+    call("map_copy2d_f32", src.data_ptr(), _ld(src), M, N, dst.data_ptr(), _ld(dst), _stream())
+    return dst
+
+
+def gather_rows_i64(X: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check(X, torch.int64, "X")
+    _check(idx, torch.int64, "idx")
+    n_rows, F = X.shape
+    if out is None:
+        out = torch.empty(idx.numel(), F, dtype=torch.int64, device=X.device)
+    call("map_gather_rows_i64", X.data_ptr(), n_rows, F, idx.data_ptr(), idx.numel(), out.data_ptr(), _stream())
     return out
