@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=5)
+    ap.add_argument("--dump-profile", default=None, help="write the per-(kernel, shape) timing table of the eager profiling pass here")
     return ap.parse_args()
 
 
@@ -304,6 +305,18 @@ def main_ours(args):
             by, fl = algorithmic(tag)
             d["bytes"] += by
             d["flops"] += fl
+        if args.dump_profile:
+            per = {}
+            for name, tag, a, b in _lib.PROFILE:
+                d = per.setdefault((name, tag), [0.0, 0])
+                d[0] += a.elapsed_time(b)
+                d[1] += 1
+            with open(args.dump_profile, "w") as f:
+                for (name, tag), (msum, n) in sorted(per.items(), key=lambda kv: -kv[1][0]):
+                    by, fl = algorithmic(tag)
+                    us = 1e3 * msum / n
+                    f.write(f"{name:34s} {str(tag):44s} n/step={n / args.profile_steps:5.1f} us={us:9.1f} "
+                            f"tflops={fl / (us * 1e-6) / 1e12 if fl else 0:7.1f} gbs={by / (us * 1e-6) / 1e9 if by else 0:8.1f}\n")
         _lib.PROFILE = None
         eng.use_graph = not args.no_graph
         tot = sum(d["ms"] for d in agg.values())

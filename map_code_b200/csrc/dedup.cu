@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) sort_prep_kernel(const int64_t* __restric
     }
 }
 
-// hist[bin * nblocks + block] = #keys of this CTA's tile whose digit == bin
+// hist[block * 256 + bin] = #keys of this CTA's tile whose digit == bin
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
                                                                  uint32_t* __restrict__ hist, int nblocks) {
     __shared__ uint32_t sh[kRadixBins];
@@ -36,7 +36,71 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t*
         if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
     }
     __syncthreads();
-    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+    hist[(int64_t)blockIdx.x * kRadixBins + threadIdx.x] = sh[threadIdx.x];
+}
+
+// Exclusive scan of the digit histogram in (bin-major, block-minor) order, computed on the block-major array:
+// out[block][bin] = #keys with a smaller digit + #keys with this digit in earlier blocks.
+// One CTA of 1024 threads = 4 groups x 256 bins; each group walks a quarter of the blocks with 8 independent loads in
+// flight per thread (the old single-CTA linear scan was a 20 us latency chain per pass).
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t tot[4][kRadixBins];
+    __shared__ uint32_t bin_excl[kRadixBins];
+    __shared__ uint32_t warp_tot[8];
+    const int bin = threadIdx.x & (kRadixBins - 1);
+    const int grp = threadIdx.x >> 8;
+    const int per = (nblocks + 3) >> 2;
+    const int b0 = grp * per;
+    const int b1 = (b0 + per < nblocks) ? b0 + per : nblocks;
+    uint32_t sum = 0;
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = hist[(int64_t)(b + k) * kRadixBins + bin];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += c[k];
+    }
+    for (; b < b1; ++b) sum += hist[(int64_t)b * kRadixBins + bin];
+    tot[grp][bin] = sum;
+    __syncthreads();
+    if (threadIdx.x < kRadixBins) {  // exclusive scan of the 256 bin totals
+        const uint32_t t = tot[0][bin] + tot[1][bin] + tot[2][bin] + tot[3][bin];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        uint32_t incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        bin_excl[bin] = incl - t;
+    }
+    __syncthreads();
+    if (threadIdx.x < kRadixBins) {
+        uint32_t off = 0;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) off += warp_tot[w];
+        bin_excl[bin] += off;
+    }
+    __syncthreads();
+    uint32_t run = bin_excl[bin];
+    for (int g = 0; g < grp; ++g) run += tot[g][bin];
+    b = b0;
+    for (; b + 8 <= b1; b += 8) {
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = hist[(int64_t)(b + k) * kRadixBins + bin];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            hist[(int64_t)(b + k) * kRadixBins + bin] = run;
+            run += c[k];
+        }
+    }
+    for (; b < b1; ++b) {
+        const uint32_t c = hist[(int64_t)b * kRadixBins + bin];
+        hist[(int64_t)b * kRadixBins + bin] = run;
+        run += c;
+    }
 }
 
 // In-place exclusive scan of `data[0..len)` by ONE CTA of 1024 threads (len <= a few million: bins*nblocks).
@@ -97,7 +161,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32
     __shared__ uint32_t warp_cnt[kSortWarps][kRadixBins];
     __shared__ uint32_t bin_base[kRadixBins];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bin_base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+    bin_base[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * kRadixBins + threadIdx.x];
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
     for (int it = 0; it < kSortItems; ++it) {
 #pragma unroll
@@ -374,7 +438,7 @@ extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_
     for (int p = 0; p < passes; ++p) {
         const int shift = p * kRadixBits;
         sort_hist_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, n, shift, hist, L.nblocks_sort);
-        scan_single_cta_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)kRadixBins * L.nblocks_sort);
+        sort_scan_kernel<<<1, 1024, 0, st>>>(hist, L.nblocks_sort);
         sort_scatter_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, vin, n, shift, hist, L.nblocks_sort, kout, vout);
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;

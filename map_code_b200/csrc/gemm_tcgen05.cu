@@ -14,6 +14,7 @@
 // lands on a multiple of the 148 SMs); 2 CTAs are co-resident per SM whenever the stage ring fits in half the shared
 // memory, so one CTA's epilogue overlaps the other's main loop.  Small wgrad grids use split-K with fp32 red.global.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -179,8 +180,8 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
         default: break;
     }
     float* dst = p.C + (int64_t)m * p.ldc + n;
-    if (p.split_k > 1) {  // partial sums of a K split: fp32 reductions into the pre-zeroed output (EPI_NONE only)
-        atomicAdd(dst + 0, out.x); atomicAdd(dst + 1, out.y); atomicAdd(dst + 2, out.z); atomicAdd(dst + 3, out.w);
+    if (p.split_k > 1) {  // partial sums of a K split: one 16-byte fp32 reduction into the pre-zeroed output (EPI_NONE only)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(out.x), "f"(out.y), "f"(out.z), "f"(out.w) : "memory");
     } else {
         *reinterpret_cast<float4*>(dst) = out;
     }
@@ -282,34 +283,53 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
             tcgen05_commit(smem_u32(&tmem_full_bar));     // accumulator complete
         }
     } else {
-        // ===================== epilogue warps: TMEM -> registers -> fused epilogue -> global =====================
+        // ===================== epilogue warps: TMEM -> registers -> smem transpose -> fused epilogue -> global =====
+        // tcgen05.ld hands every thread one accumulator ROW; writing rows straight out would make each warp store touch 32
+        // different lines.  Each warp therefore transposes 32x32 chunks through a private staging tile (the stage ring is
+        // idle once tmem_full has fired: one tile per CTA) so that 8 lanes cover 128 contiguous bytes of one output row.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int m = m0 + q * 32 + lane;       // output row owned by this thread
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         tcgen05_fence_after();
+        constexpr int kStageLd = 36;            // floats per staging row (144 B: 16-byte aligned, conflict-free 128-bit phases)
+        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + q * (32 * kStageLd);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int row_base = m0 + q * 32;
         int c = 0;
         for (; c + 32 <= p.block_n; c += 32) {
             float v[32];
             tmem_ld_x32(lane_addr + (uint32_t)c, v);
-            if (m < p.M) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + c + j;
-                    if (n < p.N) epilogue_store4(p, m, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                }
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int cg = lane & 7, rr = lane >> 3;
+            const int n = n0 + c + 4 * cg;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + rr;
+                const float4 a = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
+                const int m = row_base + r;
+                if (m < p.M && n < p.N) epilogue_store4(p, m, n, a);
             }
+            __syncwarp();
         }
         if (c < p.block_n) {  // block_n % 32 == 16
             float v[16];
             tmem_ld_x16(lane_addr + (uint32_t)c, v);
-            if (m < p.M) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const int n = n0 + c + j;
-                    if (n < p.N) epilogue_store4(p, m, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                }
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int cg = lane & 3, rr = lane >> 2;
+            const int n = n0 + c + 4 * cg;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + rr;
+                const float4 a = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
+                const int m = row_base + r;
+                if (m < p.M && n < p.N) epilogue_store4(p, m, n, a);
             }
+            __syncwarp();
         }
     }
 
@@ -424,6 +444,11 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     p.trans_a = g->trans_a ? 1 : 0;
     p.trans_b = g->trans_b ? 1 : 0;
     p.block_n = choose_block_n(g->M, g->N, p.trans_b != 0);
+    if (const char* e = getenv("MAP_B200_BLOCK_N")) {  // tuning override (scripts/tune_gemm.py)
+        int bn = atoi(e);
+        const int step = p.trans_b ? 32 : 16;
+        if (bn >= step && bn <= 256 && bn % step == 0) p.block_n = bn;
+    }
     p.epilogue = g->epilogue;
     p.C = g->C; p.ldc = g->ldc;
     p.bias = g->bias;
@@ -446,6 +471,10 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
         if (s > 16) s = 16;
         if (s > 1) p.split_k = s;
     }
+    if (const char* e = getenv("MAP_B200_SPLITK")) {
+        const int sk = atoi(e);
+        if (sk >= 1 && sk <= 64 && (sk == 1 || g->epilogue == MAP_EPI_NONE)) p.split_k = sk;
+    }
     p.num_k_blocks = (int)ceil_div(p.k_blocks_total, p.split_k);
     p.split_k = (int)ceil_div(p.k_blocks_total, p.num_k_blocks);
 
@@ -453,6 +482,10 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     const int budget2 = 110 * 1024, budget1 = 220 * 1024;
     int stages = budget2 / p.stage_bytes;
     if (stages < 3) stages = budget1 / p.stage_bytes;
+    if (const char* e = getenv("MAP_B200_STAGES")) {
+        const int st_ = atoi(e);
+        if (st_ >= 1 && st_ * p.stage_bytes <= budget1) stages = st_;
+    }
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.num_k_blocks) stages = p.num_k_blocks > 1 ? p.num_k_blocks : 1;
     if (stages < 1) stages = 1;

@@ -46,7 +46,8 @@ class FusedStep:
                  lr: float = 1e-3, weight_decay: float = 5e-2, betas=(0.9, 0.999), eps: float = 1e-8, sched: str = "cosine",
                  warmup_steps: int = 0, total_steps: int = 1000, seed: int = 42, optimizer_mode: str = "sparse",
                  x_train: Optional[torch.Tensor] = None, idx_low=None, idx_high=None, use_graph: bool = True,
-                 row0: int = 0, global_batch: Optional[int] = None, gemm_backend: Optional[str] = None):
+                 row0: int = 0, global_batch: Optional[int] = None, gemm_backend: Optional[str] = None,
+                 multi_stream: bool = True):
         cfg = model.config
         self.model, self.cfg = model, cfg
         self.dev = next(model.parameters()).device
@@ -86,6 +87,10 @@ class FusedStep:
         self.graph = None
         self.steps_done = 0
         self.overrides = None
+        # Independent branches of the step (MLP tower vs CrossNet, weight gradients vs the dgrad chain, table sorts vs
+        # GEMMs) are issued on side streams; under capture they become parallel branches of the CUDA graph.
+        self.multi_stream = multi_stream
+        self.streams = {k: torch.cuda.Stream(device=self.dev) for k in ("tab", "mlp", "dw")} if multi_stream else {}
 
     # ------------------------------------------------------------------------------------------------ setup
     def _collect_params(self):
@@ -149,9 +154,9 @@ class FusedStep:
         self.adam_table, self.adam_n, self.adam_max = ops.make_adamw_tensor_list(entries, dev)
         # backward scratch
         md = max(self.in_dim, self.H, 1)
-        self.dA = E(B, md)   # ping-pong gradient buffers through the towers
-        self.dB = E(B, md)
-        self.dU = E(B, self.in_dim) if nc else None
+        self.dZ = [E(B, self.H) for _ in range(nh)]          # gradient at each MLP pre-activation (kept: dW reads it later)
+        self.dUs = [E(B, self.in_dim) for _ in range(nc)]    # dU of each cross layer
+        self.Gc = [E(B, self.in_dim) for _ in range(nc + 1)] # d(loss)/d(X_i) through the cross chain
         self.dX0_acc = E(B, self.in_dim) if nc else None
         self.dX0_mlp = E(B, self.in_dim) if nh else None
         self.dE = E(B, self.in_dim)
@@ -204,13 +209,32 @@ class FusedStep:
     def _gemm(self, *a, **k):
         return ops.gemm(*a, backend=self.gemm_backend, **k)
 
-    def _linear_bwd(self, dZ, X_in, layer_name, W, M, N, K, dX_out=None, dX_epilogue=_lib.EPI_NONE, aux0=None):
-        """Given dZ [M,N] (gradient at the pre-activation), input X_in [M,K] and weight W [N,K]:
-        dW = dZ^T X, db = colsum(dZ), optionally dX = dZ W (with a fused epilogue)."""
-        self._gemm(dZ, X_in, self.grads[layer_name + ".weight"], N, K, M, trans_a=True, trans_b=True)
-        ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
-        if dX_out is not None:
-            self._gemm(dZ, W, dX_out, M, K, N, trans_b=True, epilogue=dX_epilogue, aux0=aux0)
+    def _on(self, name):
+        """context: issue on side stream `name` (or stay on the main stream when multi_stream is off)"""
+        import contextlib
+        return torch.cuda.stream(self.streams[name]) if self.multi_stream else contextlib.nullcontext()
+
+    def _fork(self, name):
+        """side stream `name` waits for everything issued so far on the CURRENT stream"""
+        if self.multi_stream:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.streams[name].wait_event(ev)
+
+    def _join(self, name):
+        """the CURRENT stream waits for everything issued so far on side stream `name`"""
+        if self.multi_stream:
+            ev = torch.cuda.Event()
+            ev.record(self.streams[name])
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _wgrad(self, dZ, X_in, layer_name, M, N, K):
+        """dW = dZ^T X, db = colsum(dZ) for a Linear with input X_in [M,K] and pre-activation gradient dZ [M,N].
+        Issued on the 'dw' stream: weight gradients are off the critical path (only the optimizer waits for them)."""
+        self._fork("dw")
+        with self._on("dw"):
+            self._gemm(dZ, X_in, self.grads[layer_name + ".weight"], N, K, M, trans_a=True, trans_b=True)
+            ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
 
     # ------------------------------------------------------------------------------------------------ the step
     def _draw_and_mask(self):
@@ -239,18 +263,35 @@ class FusedStep:
 
     def _forward_backbone(self, ids):
         B, in_dim, H = self.B, self.in_dim, self.H
+        # table-side work that only needs the ids starts now on the 'tab' stream: the embedding dedup sort (K2a) and, for
+        # MFP, the alias draw of the NCE noise (K5)
+        self._fork("tab")
+        with self._on("tab"):
+            self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
+            if self.mode == "MFP":
+                crit = self.model.mfp_criterion
+                if self.overrides is not None and "noise" in self.overrides:
+                    self.noise.copy_(self.overrides["noise"].reshape(self.N, self.K))
+                else:
+                    ops.alias_draw(crit.alias.prob, crit.alias.alias, self.seed, STREAM_ALIAS, self.N * self.K,
+                                   elem0=self.row0 * self.L * self.K, out=self.noise.view(-1), step_dev=self.step_counter)
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
+        nh = len(self.mlp)
+        if nh:  # MLP tower on its own stream, concurrent with CrossNet (both only read X0)
+            self._fork("mlp")
+            with self._on("mlp"):
+                x, k = self.X0, in_dim
+                for i, layer in enumerate(self.mlp):         # layers.py:187-188, ReLU fused
+                    out = self.mlp_out if i == nh - 1 else self.Hs[i]
+                    self._gemm(x, layer.weight.data, out, B, H, k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data)
+                    x, k = out, H
         nc = len(self.cross)
         for i, layer in enumerate(self.cross):       # layers.py:197-201 with the product fused in the epilogue
             out = self.cross_out if i == nc - 1 else self.Xc[i + 1]
             self._gemm(self.Xc[i], layer.weight.data, out, B, in_dim, in_dim, epilogue=_lib.EPI_CROSS, bias=layer.bias.data,
                        aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i])
-        x, k = self.X0, in_dim
-        nh = len(self.mlp)
-        for i, layer in enumerate(self.mlp):         # layers.py:187-188, ReLU fused
-            out = self.mlp_out if i == nh - 1 else self.Hs[i]
-            self._gemm(x, layer.weight.data, out, B, H, k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data)
-            x, k = out, H
+        if nh:
+            self._join("mlp")
 
     def _backward_backbone(self, head_W, dHead, n_head):
         """head_W [n_head, final_dim] is the weight of the first head layer, dHead [B, n_head] the gradient at its
@@ -259,40 +300,43 @@ class FusedStep:
         nc, nh = len(self.cross), len(self.mlp)
         pref_c = "cross_net.cross_layers"
         pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
-        # ---- MLP tower: gradient through the last ReLU is fused into the dgrad GEMM's epilogue
+        # ---- MLP tower (stream 'mlp'): the gradient through each ReLU is fused into the dgrad GEMM's epilogue
         if nh:
-            dZ = self.dA[:, :H]
-            self._gemm(dHead, head_W[:, self.mlp_off:self.mlp_off + H], dZ, B, H, n_head, trans_b=True,
-                       epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out)
-            for i in range(nh - 1, -1, -1):
-                layer = self.mlp[i]
-                x_in = self.X0 if i == 0 else self.Hs[i - 1]
-                k_in = in_dim if i == 0 else H
-                nxt = (self.dB if dZ.data_ptr() == self.dA.data_ptr() else self.dA)
-                if i > 0:
-                    dX = nxt[:, :H]
-                    self._linear_bwd(dZ, x_in, f"{pref_m}.{3 * i}", layer.weight.data, B, H, k_in, dX_out=dX,
-                                     dX_epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.Hs[i - 1])
-                    dZ = dX
-                else:
-                    self._linear_bwd(dZ, x_in, f"{pref_m}.{3 * i}", layer.weight.data, B, H, k_in, dX_out=self.dX0_mlp)
-        # ---- CrossNet: G = d(loss)/d(X_{i+1});  dU = G*X0, dX0 += G*U_i, dXi = G + dU W_i   (autograd of layers.py:200)
+            self._fork("mlp")
+            with self._on("mlp"):
+                dZ = self.dZ[nh - 1]
+                self._gemm(dHead, head_W[:, self.mlp_off:self.mlp_off + H], dZ, B, H, n_head, trans_b=True,
+                           epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out)
+                for i in range(nh - 1, -1, -1):
+                    layer = self.mlp[i]
+                    x_in = self.X0 if i == 0 else self.Hs[i - 1]
+                    k_in = in_dim if i == 0 else H
+                    self._wgrad(dZ, x_in, f"{pref_m}.{3 * i}", B, H, k_in)
+                    if i > 0:
+                        self._gemm(dZ, layer.weight.data, self.dZ[i - 1], B, k_in, H, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK,
+                                   aux0=self.Hs[i - 1])
+                        dZ = self.dZ[i - 1]
+                    else:
+                        self._gemm(dZ, layer.weight.data, self.dX0_mlp, B, k_in, H, trans_b=True)
+        # ---- CrossNet (main stream): G = d(loss)/d(X_{i+1});  dU = G*X0, dX0 += G*U_i, dXi = G + dU W_i  (autograd of layers.py:200)
         if nc:
-            G = self.dA[:, :in_dim]
+            G = self.Gc[nc]
             self._gemm(dHead, head_W[:, self.cross_off:self.cross_off + in_dim], G, B, in_dim, n_head, trans_b=True)
             for i in range(nc - 1, -1, -1):
                 layer = self.cross[i]
-                ops.cross_bwd_pre(G, self.X0, self.U[i], self.dU, self.dX0_acc, accumulate=(i != nc - 1))
-                Gn = (self.dB if G.data_ptr() == self.dA.data_ptr() else self.dA)[:, :in_dim]
-                self._linear_bwd(self.dU, self.Xc[i], f"{pref_c}.{i}", layer.weight.data, B, in_dim, in_dim, dX_out=Gn,
-                                 dX_epilogue=_lib.EPI_ADD, aux0=G)
-                G = Gn
+                ops.cross_bwd_pre(G, self.X0, self.U[i], self.dUs[i], self.dX0_acc, accumulate=(i != nc - 1))
+                self._wgrad(self.dUs[i], self.Xc[i], f"{pref_c}.{i}", B, in_dim, in_dim)
+                self._gemm(self.dUs[i], layer.weight.data, self.Gc[i], B, in_dim, in_dim, trans_b=True, epilogue=_lib.EPI_ADD, aux0=G)
+                G = self.Gc[i]
+            if nh:
+                self._join("mlp")
             ops.add3(G, self.dX0_acc, self.dX0_mlp if nh else None, self.dE)
         else:
+            self._join("mlp")
             ops.copy2d(self.dX0_mlp, self.dE)
-        # ---- embedding table: dedup + segmented row sum (K2)
+        # ---- embedding table: segmented row sum over the (already sorted) ids (K2b)
+        self._join("tab")
         t = self.tables["embed.embedding.weight"]
-        t.plan.run(self.ids_cur.view(-1))
         t.plan.reduce_rows(self.dE, self.D, out=t.grad)
 
     def _head_mfp(self):
@@ -302,25 +346,23 @@ class FusedStep:
         crit = m.mfp_criterion
         self._gemm(self.final_v, enc_W, self.enc, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b)   # models.py:74
         ops.gather_slices(self.enc, self.mi, F, P, out=self.sel)                                                   # models.py:75
-        if self.overrides is not None and "noise" in self.overrides:
-            self.noise.copy_(self.overrides["noise"].reshape(N, K))
-        else:
-            ops.alias_draw(crit.alias.prob, crit.alias.alias, self.seed, STREAM_ALIAS, N * K, elem0=self.row0 * L * K,
-                           out=self.noise.view(-1), step_dev=self.step_counter)
+        self._join("tab")  # noise drawn on the 'tab' stream
         self.acc_count.zero_()
         n_global = self.global_batch * L
         ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
                     self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
                     loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
-        ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
-        # ---- backward of the head
+        # ---- NCE table gradients on the 'tab' stream: sort the (N, K+1) ids, reduce dz * input rows per unique id
+        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
+        self._fork("tab")
+        with self._on("tab"):
+            ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
+            te.plan.run(self.ids_all.view(-1))
+            te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
+        # ---- backward of the encoder
         self.d_enc.zero_()
         ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
-        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
-        te.plan.run(self.ids_all.view(-1))
-        te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
-        self._gemm(self.d_enc, self.final_v, self.grads["feat_encoder.weight"], F * P, self.final_dim, B, trans_a=True, trans_b=True)
-        ops.colsum(self.d_enc, out=self.grads["feat_encoder.bias"], ws=self.colsum_ws)
+        self._wgrad(self.d_enc, self.final_v, "feat_encoder", B, F * P, self.final_dim)
         self._backward_backbone(enc_W, self.d_enc, F * P)
 
     def _head_rfd(self):
@@ -333,10 +375,9 @@ class FusedStep:
         if self.global_batch != B:  # mean over the GLOBAL batch
             ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
         # backward
-        self._linear_bwd(self.d_logits, self.rfd_h, "pred_rfd.2", l2.weight.data, B, F, F * P, dX_out=self.d_h,
-                         dX_epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h)
-        self._gemm(self.d_h, self.final_v, self.grads["pred_rfd.0.weight"], F * P, self.final_dim, B, trans_a=True, trans_b=True)
-        ops.colsum(self.d_h, out=self.grads["pred_rfd.0.bias"], ws=self.colsum_ws)
+        self._wgrad(self.d_logits, self.rfd_h, "pred_rfd.2", B, F, F * P)
+        self._gemm(self.d_logits, l2.weight.data, self.d_h, B, F * P, F, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h)
+        self._wgrad(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim)
         self._backward_backbone(l0.weight.data, self.d_h, F * P)
 
     def _head_ctr(self):
@@ -346,8 +387,7 @@ class FusedStep:
         ops.bce_logits(self.ctr_logits.view(-1), self.in_labels, stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
         if self.global_batch != B:
             ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
-        self._gemm(self.d_logits, self.final_v, self.grads["fc_out.weight"], 1, self.final_dim, B, trans_a=True, trans_b=True)
-        ops.colsum(self.d_logits, out=self.grads["fc_out.bias"], ws=self.colsum_ws)
+        self._wgrad(self.d_logits, self.final_v, "fc_out", B, 1, self.final_dim)
         self._backward_backbone(fc.weight.data, self.d_logits, 1)
 
     def _ratio(self):
@@ -356,7 +396,8 @@ class FusedStep:
         return self._ratio_t
 
     def forward_backward(self):
-        """mask -> forward -> backward on the current stream; gradients land in self.grads / self.tables[*].grad."""
+        """mask -> forward -> backward; gradients land in self.grads / self.tables[*].grad.  On return every side stream has
+        been joined back into the current stream."""
         self.ids_cur = self._draw_and_mask()
         self._forward_backbone(self.ids_cur)
         if self.mode == "MFP":
@@ -365,6 +406,8 @@ class FusedStep:
             self._head_rfd()
         else:
             self._head_ctr()
+        for name in self.streams:
+            self._join(name)
 
     def reduce_gradients(self):
         """hook for data-parallel runs (dist.py installs the all-reduce / all-to-all here)."""

@@ -159,6 +159,7 @@ class GatherSlicesFn(torch.autograd.Function):
         B, L = mi.shape
         ctx.save_for_backward(mi)
         ctx.dims = (B, F, P)
+        ctx.enc_shape = tuple(enc.shape)
         return ops.gather_slices(enc, mi, F, P).view(B, L, P)
 
     @staticmethod
@@ -167,7 +168,7 @@ class GatherSlicesFn(torch.autograd.Function):
         B, F, P = ctx.dims
         d_enc = torch.zeros(B, F * P, dtype=torch.float32, device=g.device)
         ops.scatter_add_slices(_c(g).view(-1, P), mi, F, P, d_enc)
-        return d_enc.view(B, F, P), None, None, None
+        return d_enc.view(ctx.enc_shape), None, None, None
 
 
 class NCEFn(torch.autograd.Function):
