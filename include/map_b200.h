@@ -216,6 +216,27 @@ int map_gemm_tf32_tcgen05(const map_gemm_args* args, map_stream_t stream);
 /* 1 if map_gemm_tf32_tcgen05 accepts these arguments (shape / alignment), else 0 */
 int map_gemm_tf32_supported(const map_gemm_args* args);
 
+/* ------------------------------------------------------------------ K13  row-sharded tables (owner-side kernels)
+ * The reference initialises NCCL (code/arguments.py:74) but never issues a collective; this is the multi-GPU path the
+ * north_star asks for: table row `id` lives on rank id % R at local row id / R.  The exchange steps between these
+ * kernels are fixed-size NCCL collectives issued by the host (map_code_b200/dist.py). */
+/* out[i,:] = (ids[i] % R == rank) ? shard[ids[i] / R, :] : 0   — summed over ranks (reduce-scatter) this is the lookup */
+int map_emb_gather_owned_f32(const float* shard, int64_t shard_rows, int D, const int64_t* ids, int64_t n_ids, int R,
+                             int rank, float* out, map_stream_t stream);
+/* keys[i] = owned ? ids[i] / R : sentinel  — local row ids for the dedup pipeline; every foreign occurrence lands in one
+ * trailing segment (sentinel = shard_rows, a dummy row) */
+int map_owned_keys(const int64_t* ids, int64_t n, int R, int rank, int64_t sentinel, int64_t* keys, map_stream_t stream);
+/* partial[n,j] = owned(idx[n,j]) ? <q[n,:], emb_shard[idx/R,:]> + bias_shard[idx/R] : 0   (K1 = K+1 columns) */
+int map_nce_scores_owned(const float* q, int64_t N, int P, int K1, const int64_t* idx, const float* emb_shard,
+                         const float* bias_shard, int R, int rank, float* partial, map_stream_t stream);
+/* the loss half of map_nce_fwd on complete scores: logits = scores - norm_term, loss_pos, dz (x grad_scale), acc_count */
+int map_nce_loss_from_scores(const float* scores, const int64_t* idx, int64_t N, int K1, const float* logprob_noise,
+                             float norm_term, int loss_type, float grad_scale, float* logits, float* loss_pos, float* dz,
+                             int32_t* acc_count, map_stream_t stream);
+/* d_q[n,:] = sum over owned j of dz[n,j] * emb_shard[idx[n,j]/R, :]   — summed over ranks this is d(loss)/d(query) */
+int map_nce_dinput_owned(const float* dz, int64_t N, int P, int K1, const int64_t* idx, const float* emb_shard, int R,
+                         int rank, float* d_q, map_stream_t stream);
+
 /* column sums: out[n] = sum_m X[m,n]  (bias gradients).  deterministic two-stage. */
 int map_colsum_f32(const float* X, int64_t ldx, int64_t M, int N, float* out, void* workspace, size_t workspace_bytes,
                    map_stream_t stream);

@@ -75,6 +75,11 @@ PROTOTYPES = {
     "map_gemm_f32_simt": (_i, [C.POINTER(GemmArgs), _p]),
     "map_gemm_tf32_tcgen05": (_i, [C.POINTER(GemmArgs), _p]),
     "map_gemm_tf32_supported": (_i, [C.POINTER(GemmArgs)]),
+    "map_emb_gather_owned_f32": (_i, [_p, _l, _i, _p, _l, _i, _i, _p, _p]),
+    "map_owned_keys": (_i, [_p, _l, _i, _i, _l, _p, _p]),
+    "map_nce_scores_owned": (_i, [_p, _l, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
+    "map_nce_loss_from_scores": (_i, [_p, _p, _l, _i, _p, _f, _i, _f, _p, _p, _p, _p, _p]),
+    "map_nce_dinput_owned": (_i, [_p, _l, _i, _i, _p, _p, _i, _i, _p, _p]),
     "map_colsum_f32": (_i, [_p, _l, _l, _i, _p, _p, _sz, _p]),
     "map_colsum_workspace_bytes": (_sz, [_l, _i]),
     "map_cross_bwd_pre": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _i, _p, _p, _p]),

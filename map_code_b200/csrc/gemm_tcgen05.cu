@@ -402,27 +402,39 @@ static int tf32_supported(const map_gemm_args* g, bool set_msg) {
     return 1;
 }
 
-// BLOCK_N so that (#m-tiles * #n-tiles) lands close to a multiple of the SM count without wasting columns
-static int choose_block_n(int M, int N, bool mn_major_b) {
+// Tile / split-K choice.  Measured on B200 (scripts/tune_gemm.py, profiles/r01b_tune_gemm.txt): at M = 4096 every GEMM of the
+// step is bound by L2->SM operand traffic, and the best configurations all put ~256-296 CTAs in flight (two co-resident
+// CTAs on each of the 148 SMs, one wave) with BLOCK_N <= 160 so that a 3-stage ring fits twice in shared memory.
+// Model: time ~ waves * (k_blocks_per_cta * (128 + bn) [operand bytes per K block] + 16 * bn [epilogue]).
+struct TileChoice {
+    int block_n, split_k;
+};
+static TileChoice choose_tiles(int M, int N, int K, bool mn_major_b, bool allow_split) {
     const int m_tiles = (int)ceil_div(M, kBlockM);
+    const int kb = (int)ceil_div(K, kBlockK);
     const int step = mn_major_b ? 32 : 16;  // MN-major B tiles are made of 32-float chunks
-    int best_bn = 128;
+    const int slots = 2 * kNumSMs;
+    TileChoice best{128, 1};
     double best_cost = 1e30;
-    for (int bn = step; bn <= 256; bn += step) {
+    for (int bn = step; bn <= 160; bn += step) {
         const int n_tiles = (int)ceil_div(N, bn);
         const int tiles = m_tiles * n_tiles;
-        const int slots = (bn <= 128) ? 2 * kNumSMs : kNumSMs;  // co-resident CTAs (see stage sizing)
-        const int waves = (int)ceil_div(tiles, slots);
-        // time ~ waves * (per-tile work) ; per-tile work ~ bn (MMA) with a floor for operand traffic (A tile is reloaded per n-tile)
-        const double per_tile = (double)bn + 48.0;
-        const double per_wave = (bn <= 128) ? 2.0 * per_tile : per_tile;   // two co-resident CTAs share one SM's tensor pipe
-        const double cost = waves * per_wave;
-        if (cost < best_cost - 1e-9) {
+        int split = 1;
+        if (allow_split && kb >= 32 && tiles < slots) {
+            split = slots / tiles;
+            if (split > kb / 8) split = kb / 8;
+            if (split > 16) split = 16;
+            if (split < 1) split = 1;
+        }
+        const int kb_cta = (int)ceil_div(kb, split);
+        const int waves = (int)ceil_div((int64_t)tiles * split, slots);
+        const double cost = (double)waves * ((double)kb_cta * (128 + bn) + 16.0 * bn) * (split > 1 ? 1.05 : 1.0);
+        if (cost < best_cost * 0.999 || (cost < best_cost * 1.001 && bn > best.block_n)) {
             best_cost = cost;
-            best_bn = bn;
+            best = TileChoice{bn, split};
         }
     }
-    return best_bn;
+    return best;
 }
 
 }  // namespace mapb
@@ -443,7 +455,8 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     p.M = g->M; p.N = g->N; p.K = g->K;
     p.trans_a = g->trans_a ? 1 : 0;
     p.trans_b = g->trans_b ? 1 : 0;
-    p.block_n = choose_block_n(g->M, g->N, p.trans_b != 0);
+    const TileChoice tc = choose_tiles(g->M, g->N, g->K, p.trans_b != 0, g->epilogue == MAP_EPI_NONE);
+    p.block_n = tc.block_n;
     if (const char* e = getenv("MAP_B200_BLOCK_N")) {  // tuning override (scripts/tune_gemm.py)
         int bn = atoi(e);
         const int step = p.trans_b ? 32 : 16;
@@ -463,14 +476,8 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
 
     const int m_tiles = (int)ceil_div(g->M, kBlockM);
     const int n_tiles = (int)ceil_div(g->N, p.block_n);
-    // split-K for small output grids with a long reduction (wgrad): partial tiles are reduced with fp32 atomics
-    p.split_k = 1;
-    if (g->epilogue == MAP_EPI_NONE && m_tiles * n_tiles < kNumSMs && p.k_blocks_total >= 32) {
-        int s = (2 * kNumSMs) / (m_tiles * n_tiles);
-        if (s > p.k_blocks_total / 8) s = p.k_blocks_total / 8;
-        if (s > 16) s = 16;
-        if (s > 1) p.split_k = s;
-    }
+    // split-K for small output grids with a long reduction (wgrad): partial tiles are reduced with 16-byte fp32 reductions
+    p.split_k = tc.split_k;
     if (const char* e = getenv("MAP_B200_SPLITK")) {
         const int sk = atoi(e);
         if (sk >= 1 && sk <= 64 && (sk == 1 || g->epilogue == MAP_EPI_NONE)) p.split_k = sk;

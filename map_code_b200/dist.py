@@ -1,0 +1,234 @@
+"""Multi-GPU step: one process per GPU, batch split over R ranks, [V, .] tables row-sharded by
+`owner(id) = id % R` (local row id // R), dense parameters replicated with one gradient all-reduce.
+
+The reference initialises NCCL (code/arguments.py:74) but never wraps the model or issues a collective; this module is
+the data-parallel path the north_star asks for.  Every exchange is a FIXED-SIZE collective (no host-side counts, no
+synchronisation, nothing data-dependent in the launch parameters):
+
+  embedding forward   all-gather(ids [B_l,F])            -> owner kernel emb_gather_owned (zeros for foreign rows)
+                      reduce-scatter(rows [R*B_l*F, D])   -> X0 of the local batch
+  embedding backward  all-gather(dE [B_l, F*D])           -> owned_keys + sort/dedup + segment sums + row-wise AdamW on the shard
+  NCE ("move the query, not the rows": 128 B of query instead of 26 x 132 B of table rows per position)
+                      all-gather(query [N_l,P], ids [N_l,K+1]) -> nce_scores_owned -> reduce-scatter(scores [R*N_l, K+1])
+                      local loss / dz                      -> all-gather(dz) -> nce_dinput_owned -> reduce-scatter(d_query)
+                      table gradients of owned rows through the same dedup pipeline
+  dense parameters    all-reduce(flat gradient buffer, SUM); the loss is scaled by 1/N_global so the sum is the global mean
+
+Philox counters are indexed by the GLOBAL row (row0 = rank * B_l), so masks, replacements and noise are identical for any R
+and the R-rank run reproduces the single-GPU run on the concatenated batch.
+
+`ShardExchange` holds the choreography and is backend-agnostic: on GPUs `kernels` is map_code_b200.ops (NCCL group); the CPU
+tests drive the same code over gloo with a torch emulation of the five owner-side kernels (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import FusedStep, _Table, is_no_decay
+
+
+# ------------------------------------------------------------------------------------------------ shard layout
+def shard_rows(V: int, R: int) -> int:
+    """rows per shard including one trailing dummy row that absorbs the 'foreign id' sentinel segment"""
+    return (V + R - 1) // R + 1
+
+
+def shard_table(full: torch.Tensor, R: int, rank: int) -> torch.Tensor:
+    """[V, D] -> this rank's [shard_rows, D]: local row i holds global row i*R + rank; the dummy row (and padding) is 0."""
+    V, D = full.shape
+    out = torch.zeros(shard_rows(V, R), D, dtype=full.dtype, device=full.device)
+    mine = full[rank::R]
+    out[:mine.shape[0]] = mine
+    return out
+
+
+def unshard_table(shards: List[torch.Tensor], V: int) -> torch.Tensor:
+    """inverse of shard_table over the list of all R shards (checkpoint export in the reference's [V, D] layout)"""
+    R = len(shards)
+    D = shards[0].shape[1]
+    full = torch.empty(V, D, dtype=shards[0].dtype, device=shards[0].device)
+    for r, s in enumerate(shards):
+        n = (V - r + R - 1) // R
+        full[r::R] = s[:n]
+    return full
+
+
+class ShardExchange:
+    """The collective choreography around the owner-side kernels.  `kernels` provides emb_gather_owned, owned_keys,
+    nce_scores_owned, nce_dinput_owned (signatures of map_code_b200.ops)."""
+
+    def __init__(self, kernels, world: int, rank: int, group=None):
+        self.k, self.R, self.rank, self.group = kernels, world, rank, group
+
+    # -- collectives (fixed sizes)
+    def all_gather(self, local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((self.R,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=self.group)
+        return out
+
+    def reduce_scatter(self, full: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        dist.reduce_scatter_tensor(out.view(-1), full.view(-1), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    # -- embedding
+    def embed_forward(self, shard: torch.Tensor, ids_local: torch.Tensor, ids_g: torch.Tensor, rows_g: torch.Tensor,
+                      out_local: torch.Tensor) -> torch.Tensor:
+        """ids_local [B_l,F] -> out_local [B_l*F, D]; fills ids_g [R,B_l,F] (kept for the backward) and scratch rows_g."""
+        self.all_gather(ids_local, ids_g)
+        self.k.emb_gather_owned(shard, ids_g.view(-1), self.R, self.rank, rows_g)
+        return self.reduce_scatter(rows_g, out_local)
+
+    def local_keys(self, ids_g: torch.Tensor, sentinel: int, keys: torch.Tensor) -> torch.Tensor:
+        return self.k.owned_keys(ids_g.view(-1), self.R, self.rank, sentinel, keys)
+
+    # -- NCE
+    def nce_scores(self, q_local, ids_local, emb_shard, bias_shard, q_g, ids_g, partial_g, scores_local):
+        self.all_gather(q_local, q_g)
+        self.all_gather(ids_local, ids_g)
+        N_g = q_g.shape[0] * q_g.shape[1]
+        self.k.nce_scores_owned(q_g.view(N_g, -1), ids_g.view(N_g, -1), emb_shard, bias_shard.view(-1), self.R, self.rank, partial_g)
+        return self.reduce_scatter(partial_g, scores_local)
+
+    def nce_dinput(self, dz_local, ids_g, emb_shard, dz_g, dq_partial_g, dq_local):
+        self.all_gather(dz_local, dz_g)
+        N_g = dz_g.shape[0] * dz_g.shape[1]
+        self.k.nce_dinput_owned(dz_g.view(N_g, -1), ids_g.view(N_g, -1), emb_shard, self.R, self.rank, dq_partial_g)
+        return self.reduce_scatter(dq_partial_g, dq_local)
+
+
+# ------------------------------------------------------------------------------------------------ the sharded fused step
+class ShardedFusedStep(FusedStep):
+    """FusedStep with row-sharded tables.  `batch_size` is the per-rank batch; the global batch is batch_size * world."""
+
+    def __init__(self, model, *, world: int, rank: int, group=None, **kw):
+        from . import ops
+        self.world, self.rank = world, rank
+        self.xch = ShardExchange(ops, world, rank, group)
+        B = kw["batch_size"]
+        kw.setdefault("use_graph", False)      # NCCL collectives are issued eagerly between the kernels
+        kw["multi_stream"] = False             # one stream: collectives order themselves with the kernels
+        kw["row0"] = rank * B
+        kw["global_batch"] = B * world
+        self._full_shapes: Dict[str, int] = {}
+        super().__init__(model, **kw)
+
+    # -- tables become shards (the model's parameters are re-pointed at the shard; export with full_state_dict())
+    def _shard_param(self, name: str, param: torch.nn.Parameter):
+        V = param.shape[0]
+        self._full_shapes[name] = V
+        param.data = shard_table(param.data, self.world, self.rank)
+
+    def _make_embed_table(self):
+        name = "embed.embedding.weight"
+        self._shard_param(name, self.embed_w)
+        R, B, F, D, dev = self.world, self.B, self.F, self.D, self.dev
+        n = R * B * F
+        t = _Table(name, self.embed_w, n, 0.0 if is_no_decay(name) else self.wd, dev)
+        from . import ops
+        t.plan = ops.DedupPlan(n, self.embed_w.shape[0], dev)
+        self.tables[name] = t
+        self.ids_g = torch.empty(R, B, F, dtype=torch.int64, device=dev)
+        self.keys_emb = torch.empty(n, dtype=torch.int64, device=dev)
+        self.rows_g = torch.empty(n, D, dtype=torch.float32, device=dev)
+        self.dE_g = torch.empty(R, B, F * D, dtype=torch.float32, device=dev)
+
+    def _make_nce_tables(self):
+        from . import ops
+        crit = self.model.mfp_criterion
+        R, N, K1, P, dev = self.world, self.N, self.K + 1, self.P, self.dev
+        self._shard_param("mfp_criterion.emb.weight", crit.emb.weight)
+        self._shard_param("mfp_criterion.bias.weight", crit.bias.weight)
+        n_occ = R * N * K1
+        plan = ops.DedupPlan(n_occ, crit.emb.weight.shape[0], dev)
+        te = _Table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.emb.weight") else self.wd, dev)
+        tb = _Table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.bias.weight") else self.wd, dev)
+        te.plan = tb.plan = plan
+        self.tables[te.name], self.tables[tb.name] = te, tb
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.q_g = torch.empty(R, N, P, **f32)
+        self.nce_ids_g = torch.empty(R, N, K1, dtype=torch.int64, device=dev)
+        self.partial_g = torch.empty(R * N, K1, **f32)
+        self.scores = torch.empty(N, K1, **f32)
+        self.dz_g = torch.empty(R, N, K1, **f32)
+        self.dq_partial_g = torch.empty(R * N, P, **f32)
+        self.keys_nce = torch.empty(n_occ, dtype=torch.int64, device=dev)
+
+    # -- hooks
+    def _embed_lookup(self, ids):
+        t = self.tables["embed.embedding.weight"]
+        self._draw_noise()
+        self.xch.embed_forward(self.embed_w.data, ids, self.ids_g, self.rows_g, self.X0.view(self.B * self.F, self.D))
+        self.xch.local_keys(self.ids_g, self.embed_w.shape[0] - 1, self.keys_emb)
+        t.plan.run(self.keys_emb)
+
+    def _embed_backward(self):
+        t = self.tables["embed.embedding.weight"]
+        self.xch.all_gather(self.dE, self.dE_g)
+        t.plan.reduce_rows(self.dE_g.view(-1, self.D), self.D, out=t.grad)
+
+    def _nce_core(self):
+        from . import ops
+        P, K, L, N = self.P, self.K, self.L, self.N
+        crit = self.model.mfp_criterion
+        torch.cat([self.labels.view(N, 1), self.noise], dim=1, out=self.ids_all)   # [target | noise], nce_loss.py:138
+        self.xch.nce_scores(self.sel, self.ids_all, crit.emb.weight.data, crit.bias.weight.data, self.q_g, self.nce_ids_g, self.partial_g,
+                            self.scores)
+        self.acc_count.zero_()
+        n_global = self.global_batch * L
+        ops.nce_loss_from_scores(self.scores, self.ids_all, crit.logprob_noise, self.norm_term, self.loss_type, 1.0 / n_global, self.logits,
+                                 self.loss_pos, self.dz, self.acc_count)
+        ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
+        self.xch.nce_dinput(self.dz, self.nce_ids_g, crit.emb.weight.data, self.dz_g, self.dq_partial_g, self.d_sel)
+        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
+        self.xch.local_keys(self.nce_ids_g, crit.emb.weight.shape[0] - 1, self.keys_nce)
+        te.plan.run(self.keys_nce)
+        te.plan.reduce_rows(self.q_g.view(-1, P), P, scale=self.dz_g.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
+
+    def reduce_gradients(self):
+        self.xch.all_reduce(self.grad_flat)
+
+    def outputs(self):
+        """global metrics: sums of the per-rank partial means / counts (tiny all-reduces, issued only when metrics are read)"""
+        if self.mode == "MFP":
+            loss = self.xch.all_reduce(self.loss.clone())
+            acc = self.xch.all_reduce(self.acc_count.clone())
+            return (loss.view(()), self.global_batch * self.L, acc.view(()))
+        st = self.xch.all_reduce(torch.stack([self.stats[0] * (self.B / self.global_batch), self.stats[1], self.stats[2]]))
+        cnt = self.global_batch * self.F
+        if self.mode == "RFD":
+            return (st[0], cnt, st[1] / cnt, st[2] / cnt)
+        return (st[0], self.ctr_logits)
+
+    def full_state_dict(self) -> Dict[str, torch.Tensor]:
+        """state_dict in the reference's layout: shards of every table are all-gathered and re-interleaved to [V, D]."""
+        sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        for name, V in self._full_shapes.items():
+            shard = sd[name]
+            parts = self.xch.all_gather(shard)
+            sd[name] = unshard_table([parts[r] for r in range(self.world)], V)
+        return sd
+
+
+def make_sharded_step(trainer, total_steps: int, warmup_steps: int, world: int, rank: int, group=None) -> ShardedFusedStep:
+    """Builds the sharded step from a Trainer's arguments and installs it as the trainer's fused step."""
+    cfg, a = trainer.model_config, trainer.args
+    beta1, beta2 = (float(b) for b in a.adam_betas.split(","))
+    need_x = cfg.pretrain and cfg.pt_type == "RFD" and a.RFD_replace in ("Unigram", "Whole-Unigram")
+    lo, hi = getattr(cfg, "idx_low", None), getattr(cfg, "idx_high", None)
+    eng = ShardedFusedStep(
+        trainer.model, world=world, rank=rank, group=group, batch_size=a.per_gpu_train_batch_size, mask_ratio=a.mask_ratio,
+        sampling_method=a.sampling_method, lr=a.learning_rate, weight_decay=a.weight_decay, betas=(beta1, beta2), eps=a.adam_epsilon,
+        sched=a.lr_sched, warmup_steps=warmup_steps, total_steps=total_steps, seed=a.seed,
+        optimizer_mode=getattr(a, "optimizer_mode", "sparse"), x_train=trainer._train_matrix() if need_x else None,
+        idx_low=None if lo is None else lo.to(trainer.device), idx_high=None if hi is None else hi.to(trainer.device))
+    trainer._fused = eng
+    return eng

@@ -146,7 +146,13 @@ class FusedStep:
         for n, p in self.model.named_parameters():
             if p.requires_grad and not hasattr(p, "_map_table_grad"):
                 self.dense[n] = p
-        self.grads = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
+        # one flat gradient buffer (a single all-reduce in data-parallel runs); per-parameter views keep 16-byte alignment
+        offs, tot = {}, 0
+        for n, p in self.dense.items():
+            offs[n] = tot
+            tot += (p.numel() + 3) // 4 * 4
+        self.grad_flat = torch.zeros(tot, **f32)
+        self.grads = {n: self.grad_flat[offs[n]:offs[n] + p.numel()].view_as(p.data) for n, p in self.dense.items()}
         self.exp_avg = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
         self.exp_avg_sq = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
         entries = [(p.data, self.grads[n], self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None)
@@ -164,10 +170,7 @@ class FusedStep:
                                      dtype=torch.uint8, device=dev)
         # tables
         self.tables: Dict[str, _Table] = {}
-        emb_name = "embed.embedding.weight"
-        t = _Table(emb_name, self.embed_w, B * F, 0.0 if is_no_decay(emb_name) else self.wd, dev)
-        t.plan = ops.DedupPlan(B * F, self.V, dev)
-        self.tables[emb_name] = t
+        self._make_embed_table()
         # heads
         if self.mode == "MFP":
             P, K, L = cfg.proj_size, cfg.pt_neg_num, self.L
@@ -184,12 +187,7 @@ class FusedStep:
             self.loss_pos = E(max(N, 1))
             self.dz = E(max(N, 1), K + 1)
             self.d_sel = E(max(N, 1), P)
-            n_occ = max(N, 1) * (K + 1)
-            plan = ops.DedupPlan(n_occ, self.V, dev)
-            te = _Table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.emb.weight") else self.wd, dev)
-            tb = _Table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.bias.weight") else self.wd, dev)
-            te.plan = tb.plan = plan
-            self.tables[te.name], self.tables[tb.name] = te, tb
+            self._make_nce_tables()
             self.norm_term = float(crit.norm_term)
             self.loss_type = crit.loss_type
             if crit.reduction != "elementwise_mean":
@@ -204,6 +202,21 @@ class FusedStep:
         else:
             self.ctr_logits = E(B, 1)
             self.d_logits = E(B, 1)
+
+    def _make_embed_table(self):
+        name = "embed.embedding.weight"
+        t = _Table(name, self.embed_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev)
+        t.plan = ops.DedupPlan(self.B * self.F, self.V, self.dev)
+        self.tables[name] = t
+
+    def _make_nce_tables(self):
+        crit = self.model.mfp_criterion
+        n_occ = max(self.N, 1) * (self.K + 1)
+        plan = ops.DedupPlan(n_occ, self.V, self.dev)
+        te = _Table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.emb.weight") else self.wd, self.dev)
+        tb = _Table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.bias.weight") else self.wd, self.dev)
+        te.plan = tb.plan = plan
+        self.tables[te.name], self.tables[tb.name] = te, tb
 
     # ------------------------------------------------------------------------------------------------ helpers
     def _gemm(self, *a, **k):
@@ -261,21 +274,34 @@ class FusedStep:
                             labels=self.labels, step_dev=self.step_counter)
         return self.ids_m
 
-    def _forward_backbone(self, ids):
-        B, in_dim, H = self.B, self.in_dim, self.H
-        # table-side work that only needs the ids starts now on the 'tab' stream: the embedding dedup sort (K2a) and, for
-        # MFP, the alias draw of the NCE noise (K5)
+    def _embed_lookup(self, ids):
+        """ids [B,F] -> X0 [B, F*D] (K1).  Table-side work that only needs the ids starts now on the 'tab' stream: the
+        embedding dedup sort (K2a) and, for MFP, the alias draw of the NCE noise (K5)."""
         self._fork("tab")
         with self._on("tab"):
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
-            if self.mode == "MFP":
-                crit = self.model.mfp_criterion
-                if self.overrides is not None and "noise" in self.overrides:
-                    self.noise.copy_(self.overrides["noise"].reshape(self.N, self.K))
-                else:
-                    ops.alias_draw(crit.alias.prob, crit.alias.alias, self.seed, STREAM_ALIAS, self.N * self.K,
-                                   elem0=self.row0 * self.L * self.K, out=self.noise.view(-1), step_dev=self.step_counter)
+            self._draw_noise()
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
+
+    def _draw_noise(self):
+        if self.mode != "MFP":
+            return
+        crit = self.model.mfp_criterion
+        if self.overrides is not None and "noise" in self.overrides:
+            self.noise.copy_(self.overrides["noise"].reshape(self.N, self.K))
+        else:
+            ops.alias_draw(crit.alias.prob, crit.alias.alias, self.seed, STREAM_ALIAS, self.N * self.K,
+                           elem0=self.row0 * self.L * self.K, out=self.noise.view(-1), step_dev=self.step_counter)
+
+    def _embed_backward(self):
+        """dE [B, F*D] -> compact table gradient: segmented row sum over the (already sorted) ids (K2b)."""
+        self._join("tab")
+        t = self.tables["embed.embedding.weight"]
+        t.plan.reduce_rows(self.dE, self.D, out=t.grad)
+
+    def _forward_backbone(self, ids):
+        B, in_dim, H = self.B, self.in_dim, self.H
+        self._embed_lookup(ids)
         nh = len(self.mlp)
         if nh:  # MLP tower on its own stream, concurrent with CrossNet (both only read X0)
             self._fork("mlp")
@@ -334,10 +360,24 @@ class FusedStep:
         else:
             self._join("mlp")
             ops.copy2d(self.dX0_mlp, self.dE)
-        # ---- embedding table: segmented row sum over the (already sorted) ids (K2b)
-        self._join("tab")
-        t = self.tables["embed.embedding.weight"]
-        t.plan.reduce_rows(self.dE, self.D, out=t.grad)
+        self._embed_backward()
+
+    def _nce_core(self):
+        """sel [N,P], labels, noise -> loss, logits, acc, d_sel and the compact gradients of the two NCE tables (K6/K7)."""
+        P, K, L = self.P, self.K, self.L
+        crit = self.model.mfp_criterion
+        self.acc_count.zero_()
+        n_global = self.global_batch * L
+        ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
+                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
+                    loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
+        # table gradients on the 'tab' stream: sort the (N, K+1) ids, reduce dz * input rows per unique id
+        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
+        self._fork("tab")
+        with self._on("tab"):
+            ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
+            te.plan.run(self.ids_all.view(-1))
+            te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
 
     def _head_mfp(self):
         cfg, B, F, P, K, N, L = self.cfg, self.B, self.F, self.P, self.K, self.N, self.L
@@ -347,18 +387,7 @@ class FusedStep:
         self._gemm(self.final_v, enc_W, self.enc, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b)   # models.py:74
         ops.gather_slices(self.enc, self.mi, F, P, out=self.sel)                                                   # models.py:75
         self._join("tab")  # noise drawn on the 'tab' stream
-        self.acc_count.zero_()
-        n_global = self.global_batch * L
-        ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
-                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
-                    loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
-        # ---- NCE table gradients on the 'tab' stream: sort the (N, K+1) ids, reduce dz * input rows per unique id
-        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
-        self._fork("tab")
-        with self._on("tab"):
-            ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
-            te.plan.run(self.ids_all.view(-1))
-            te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
+        self._nce_core()
         # ---- backward of the encoder
         self.d_enc.zero_()
         ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)

