@@ -31,8 +31,8 @@ N_TRAIN = 1 << 20
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--task", default="MFP", choices=["MFP", "RFD"])
     ap.add_argument("--optimizer-mode", default="sparse", choices=["sparse", "dense_exact"])
@@ -68,23 +68,25 @@ def config_dict(task):
 
 # --------------------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock and throttle reasons DURING the timed region through NVML (10 ms period)."""
 
     def __init__(self, index=0):
         self.samples, self.stop, self.index = [], threading.Event(), index
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.max_mhz = None
 
     def run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop.is_set():
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                self.stop.wait(0.01)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def __enter__(self):
         self.t.start()
@@ -95,16 +97,12 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for i, n in enumerate(names):
-                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                "hw_power_brake_slowdown": 0x80}
+        reasons = sorted(n for n, b in bits.items() if any(s[1] & b for s in self.samples))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
+                "power_w_max": max((s[2] for s in self.samples), default=None)}
 
 
 # --------------------------------------------------------------------------------------------------------------- CPU arm
@@ -152,7 +150,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = run_cpu(args.task, args.batch, args.steps, max(args.warmup, 1))
+    r = run_cpu(args.task, args.batch, args.steps, max(args.warmup, 1), budget_s=240.0)  # bounded: stops after ~4 min of steps
     line = {"impl": "reference", "metric": f"{args.task} pretrain samples/sec (DCNv2, Criteo shape)", "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -231,7 +229,7 @@ def main_ours(args):
         eng = mdist.make_sharded_step(trainer, total_steps, 0, world, rank)
     else:
         eng = trainer.fused_step(total_steps, 0)
-    eng.use_graph = not args.no_graph
+    eng.use_graph = not args.no_graph  # NCCL collectives of the sharded step are captured in the graph as well
 
     n_batches = N_TRAIN // Bg
     def batch(i):  # rank-local slice of global batch i (device resident)
@@ -285,17 +283,24 @@ def main_ours(args):
     # ---- per-kernel timing (eager replay of the same schedule, every C-ABI call bracketed by CUDA events on its stream)
     breakdown, roof, launches = None, None, None
     pk = peaks()
+    # (every rank executes these steps — the sharded step contains collectives — but only rank 0 keeps the records)
+    _lib.LAUNCHES = {}
+    eng.use_graph = False
+    ms_flag, eng.multi_stream = eng.multi_stream, False   # serialise the branches: clean per-kernel durations
+    eng.step(batch(0))
+    torch.cuda.synchronize()
+    launches = dict(_lib.LAUNCHES)
+    _lib.LAUNCHES = None
+    _lib.PROFILE = []
+    for i in range(args.profile_steps):
+        eng.step(batch(i + 1))
+    torch.cuda.synchronize()
+    prof_records, _lib.PROFILE = _lib.PROFILE, None
+    eng.multi_stream = ms_flag
+    if world > 1:
+        dist.barrier()
     if rank == 0:
-        _lib.LAUNCHES = {}
-        eng.use_graph = False
-        eng.step(batch(0))
-        torch.cuda.synchronize()
-        launches = dict(_lib.LAUNCHES)
-        _lib.LAUNCHES = None
-        _lib.PROFILE = []
-        for i in range(args.profile_steps):
-            eng.step(batch(i + 1))
-        torch.cuda.synchronize()
+        _lib.PROFILE = prof_records
         agg = {}
         for name, tag, a, b in _lib.PROFILE:
             key = name

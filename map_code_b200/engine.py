@@ -109,8 +109,14 @@ class FusedStep:
         self.mlp_off = self.cross_w
         self.final_dim = self.cross_w + self.H + (1 if (self.has_fm and cfg.pretrain) else 0)
         self.ld_final = (self.final_dim + 3) // 4 * 4  # TMA rows must be 16-byte multiples
+        self.fm_col = self.H  # column of `final` that holds lr_fm in DeepFM pretraining (models.py:224)
         if self.has_fm:
-            raise NotImplementedError("FusedStep: DeepFM is scheduled through the module path in this revision")
+            self.lr_w = m.lr_layer.embed_w.weight
+            self.lr_b = m.lr_layer.bias
+        if cfg.pretrain:
+            self.head0_name = "feat_encoder" if cfg.pt_type == "MFP" else "pred_rfd.0"
+        else:
+            self.head0_name = "dnn_fc_out" if self.has_fm else "fc_out"
 
     def _alloc(self):
         B, F, D, dev, cfg = self.B, self.F, self.D, self.dev, self.cfg
@@ -125,6 +131,7 @@ class FusedStep:
         self.acc_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(4, **f32)
         self.red_ws = torch.empty(int(_lib.load().map_reduce_workspace_bytes(0)), dtype=torch.uint8, device=dev)
+        self.red_ws2 = torch.empty_like(self.red_ws)
         self.ids_m = torch.empty(B, F, **i64)
         if self.mode != "CTR":
             if self.L < 1:
@@ -141,22 +148,66 @@ class FusedStep:
         self.cross_out = self.final[:, self.cross_off:self.cross_off + self.cross_w] if nc else None
         self.mlp_out = self.final[:, self.mlp_off:self.mlp_off + self.H] if nh else None
         self.final_v = self.final[:, :self.final_dim]
+        # RFD head: pred_rfd.2 is Linear(F*P -> F) with F = 39: not a multiple of 4 floats, so its rows of logits / gradients
+        # would be unaligned for TMA.  Its weight and bias are re-pointed at the first F rows of zero-padded storage
+        # ([Fp, F*P], Fp = roundup4(F)); the padded rows stay zero for ever (their gradients are exactly zero), the
+        # nn.Parameter keeps its reference shape, and every GEMM of the head runs on tensor cores at N = K = Fp.
+        self._pad_rows: Dict[str, int] = {}
+        if self.mode == "RFD":
+            l2 = getattr(self.model.pred_rfd, "2")
+            self.Fp = (F + 3) // 4 * 4
+            self.W2p = torch.zeros(self.Fp, l2.weight.shape[1], **f32)
+            self.W2p[:F].copy_(l2.weight.data)
+            l2.weight.data = self.W2p[:F]
+            self.b2p = torch.zeros(self.Fp, **f32)
+            self.b2p[:F].copy_(l2.bias.data)
+            l2.bias.data = self.b2p[:F]
+            self._pad_rows = {"pred_rfd.2.weight": self.Fp, "pred_rfd.2.bias": self.Fp}
+        # DeepFM pretraining: final_dim = hidden + 1 = 1001 (models.py:211) is not a multiple of 4 floats.  The first head
+        # layer's weight [n_out, 1001] is re-pointed at a strided view of zero-padded storage [n_out, 1004] (the padding
+        # columns meet zero activations and receive zero gradients, so they stay zero under AdamW); GEMMs and the optimizer
+        # work on the padded, TMA-aligned storage, the nn.Parameter keeps its reference shape.
+        self._pad_cols: Dict[str, torch.Tensor] = {}
+        if cfg.pretrain and self.ld_final != self.final_dim:
+            wname = self.head0_name + ".weight"
+            mod = self.model.feat_encoder if cfg.pt_type == "MFP" else getattr(self.model.pred_rfd, "0")
+            Wp = torch.zeros(mod.weight.shape[0], self.ld_final, **f32)
+            Wp[:, :self.final_dim].copy_(mod.weight.data)
+            mod.weight.data = Wp[:, :self.final_dim]
+            self._pad_cols[wname] = Wp
         # dense parameter gradients + AdamW state
         self.dense: Dict[str, torch.nn.Parameter] = {}
         for n, p in self.model.named_parameters():
             if p.requires_grad and not hasattr(p, "_map_table_grad"):
                 self.dense[n] = p
         # one flat gradient buffer (a single all-reduce in data-parallel runs); per-parameter views keep 16-byte alignment
-        offs, tot = {}, 0
+        offs, tot, padded = {}, 0, {}
         for n, p in self.dense.items():
             offs[n] = tot
-            tot += (p.numel() + 3) // 4 * 4
+            if n in self._pad_rows:
+                padded[n] = self._pad_rows[n] * (p.numel() // p.shape[0])
+            elif n in self._pad_cols:
+                padded[n] = self._pad_cols[n].numel()
+            else:
+                padded[n] = p.numel()
+            tot += (padded[n] + 3) // 4 * 4
         self.grad_flat = torch.zeros(tot, **f32)
-        self.grads = {n: self.grad_flat[offs[n]:offs[n] + p.numel()].view_as(p.data) for n, p in self.dense.items()}
-        self.exp_avg = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
-        self.exp_avg_sq = {n: torch.zeros_like(p.data) for n, p in self.dense.items()}
-        entries = [(p.data, self.grads[n], self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None)
-                   for n, p in self.dense.items()]
+        self.grads, self.grads_padded, self.opt_param = {}, {}, {}
+        for n, p in self.dense.items():
+            flat = self.grad_flat[offs[n]:offs[n] + padded[n]]
+            if n in self._pad_cols:  # optimizer sees the padded contiguous storage; .grads[n] is the reference-shaped view
+                self.grads_padded[n] = flat.view(p.shape[0], self.ld_final)
+                self.grads[n] = self.grads_padded[n][:, :p.shape[1]]
+                self.opt_param[n] = self._pad_cols[n]
+            else:
+                if n in self._pad_rows:
+                    self.grads_padded[n] = flat.view(self._pad_rows[n], -1)
+                self.grads[n] = flat[:p.numel()].view_as(p.data)
+                self.opt_param[n] = p.data
+        self.exp_avg = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense}
+        self.exp_avg_sq = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense}
+        entries = [(self.opt_param[n], self.grad_flat[offs[n]:offs[n] + self.opt_param[n].numel()].view_as(self.opt_param[n]),
+                    self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None) for n in self.dense]
         self.adam_table, self.adam_n, self.adam_max = ops.make_adamw_tensor_list(entries, dev)
         # backward scratch
         md = max(self.in_dim, self.H, 1)
@@ -171,6 +222,11 @@ class FusedStep:
         # tables
         self.tables: Dict[str, _Table] = {}
         self._make_embed_table()
+        if self.has_fm:
+            self._make_lr_table()
+            self.d_lrfm = E(B, 1)
+            self.d_w_occ = E(B * F)
+            self.lr_fm = E(B, 1)
         # heads
         if self.mode == "MFP":
             P, K, L = cfg.proj_size, cfg.pt_neg_num, self.L
@@ -197,7 +253,9 @@ class FusedStep:
             self.labels = E(B, F)
             self.rfd_h = E(B, F * P)
             self.rfd_logits = E(B, F)
+            self.rfd_logits_p = E(B, self.Fp)
             self.d_logits = E(B, F)
+            self.d_logits_p = torch.zeros(B, self.Fp, **f32)
             self.d_h = E(B, F * P)
         else:
             self.ctr_logits = E(B, 1)
@@ -207,6 +265,13 @@ class FusedStep:
         name = "embed.embedding.weight"
         t = _Table(name, self.embed_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev)
         t.plan = ops.DedupPlan(self.B * self.F, self.V, self.dev)
+        self.tables[name] = t
+
+    def _make_lr_table(self):
+        """DeepFM's first-order table lr_layer.embed_w [V,1] is fed by the same id stream as the embedding: it shares its plan."""
+        name = "lr_layer.embed_w.weight"
+        t = _Table(name, self.lr_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev)
+        t.plan = self.tables["embed.embedding.weight"].plan
         self.tables[name] = t
 
     def _make_nce_tables(self):
@@ -246,7 +311,11 @@ class FusedStep:
         Issued on the 'dw' stream: weight gradients are off the critical path (only the optimizer waits for them)."""
         self._fork("dw")
         with self._on("dw"):
-            self._gemm(dZ, X_in, self.grads[layer_name + ".weight"], N, K, M, trans_a=True, trans_b=True)
+            wname = layer_name + ".weight"
+            if wname in self._pad_cols:  # column-padded head weight: compute on the aligned [N, ld_final] storage
+                self._gemm(dZ, self.final, self.grads_padded[wname], N, self.ld_final, M, trans_a=True, trans_b=True)
+            else:
+                self._gemm(dZ, X_in, self.grads[wname], N, K, M, trans_a=True, trans_b=True)
             ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
 
     # ------------------------------------------------------------------------------------------------ the step
@@ -298,10 +367,19 @@ class FusedStep:
         self._join("tab")
         t = self.tables["embed.embedding.weight"]
         t.plan.reduce_rows(self.dE, self.D, out=t.grad)
+        if self.has_fm:
+            tl = self.tables["lr_layer.embed_w.weight"]
+            tl.plan.reduce_rows(self.d_w_occ, 1, out=tl.grad)
 
     def _forward_backbone(self, ids):
         B, in_dim, H = self.B, self.in_dim, self.H
         self._embed_lookup(ids)
+        if self.has_fm:  # lr_fm = LR(ids) + FM2(E): written straight into its column of `final` (pretrain) or kept apart (CTR)
+            if self.cfg.pretrain:
+                ops.fm_lr_fwd(self.X0.view(B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=self.final[:, self.fm_col:],
+                              ld_out=self.ld_final)
+            else:
+                ops.fm_lr_fwd(self.X0.view(B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=self.lr_fm, ld_out=1)
         nh = len(self.mlp)
         if nh:  # MLP tower on its own stream, concurrent with CrossNet (both only read X0)
             self._fork("mlp")
@@ -360,6 +438,11 @@ class FusedStep:
         else:
             self._join("mlp")
             ops.copy2d(self.dX0_mlp, self.dE)
+        if self.has_fm:  # d(lr_fm) flows into the embeddings (FM term) and into the first-order table + its bias
+            if self.cfg.pretrain:
+                self._gemm(dHead, head_W[:, self.fm_col:self.fm_col + 1], self.d_lrfm, B, 1, n_head, trans_b=True)
+            ops.fm_lr_bwd(self.X0.view(B, self.F, self.D), self.d_lrfm, 1, self.dE.view(B, self.F, self.D), self.d_w_occ, accumulate=True)
+            ops.reduce_sum(self.d_lrfm.view(-1), 1.0, out=self.grads["lr_layer.bias"], ws=self.red_ws2)
         self._embed_backward()
 
     def _nce_core(self):
@@ -395,28 +478,38 @@ class FusedStep:
         self._backward_backbone(enc_W, self.d_enc, F * P)
 
     def _head_rfd(self):
-        cfg, B, F = self.cfg, self.B, self.F
+        cfg, B, F, Fp = self.cfg, self.B, self.F, self.Fp
         P = cfg.proj_size
-        l0, l2 = getattr(self.model.pred_rfd, "0"), getattr(self.model.pred_rfd, "2")
+        l0 = getattr(self.model.pred_rfd, "0")
         self._gemm(self.final_v, l0.weight.data, self.rfd_h, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS_RELU, bias=l0.bias.data)
-        self._gemm(self.rfd_h, l2.weight.data, self.rfd_logits, B, F, F * P, epilogue=_lib.EPI_BIAS, bias=l2.bias.data)
+        self._gemm(self.rfd_h, self.W2p, self.rfd_logits_p, B, Fp, F * P, epilogue=_lib.EPI_BIAS, bias=self.b2p)   # models.py:80
+        ops.copy2d(self.rfd_logits_p[:, :F], self.rfd_logits)
         ops.bce_logits(self.rfd_logits.view(-1), self.labels.view(-1), stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
         if self.global_batch != B:  # mean over the GLOBAL batch
             ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
+        ops.copy2d(self.d_logits, self.d_logits_p[:, :F])      # padded columns stay 0
         # backward
-        self._wgrad(self.d_logits, self.rfd_h, "pred_rfd.2", B, F, F * P)
-        self._gemm(self.d_logits, l2.weight.data, self.d_h, B, F * P, F, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h)
+        self._fork("dw")
+        with self._on("dw"):
+            self._gemm(self.d_logits_p, self.rfd_h, self.grads_padded["pred_rfd.2.weight"], Fp, F * P, B, trans_a=True, trans_b=True)
+            ops.colsum(self.d_logits_p, out=self.grads_padded["pred_rfd.2.bias"].view(-1), ws=self.colsum_ws)
+        self._gemm(self.d_logits_p, self.W2p, self.d_h, B, F * P, Fp, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h)
         self._wgrad(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim)
         self._backward_backbone(l0.weight.data, self.d_h, F * P)
 
     def _head_ctr(self):
         B = self.B
-        fc = self.model.fc_out
+        fc = self.model.dnn_fc_out if self.has_fm else self.model.fc_out
+        name = self.head0_name
         self._gemm(self.final_v, fc.weight.data, self.ctr_logits, B, 1, self.final_dim, epilogue=_lib.EPI_BIAS, bias=fc.bias.data)
+        if self.has_fm:
+            ops.add3(self.ctr_logits, self.lr_fm, None, self.ctr_logits)
         ops.bce_logits(self.ctr_logits.view(-1), self.in_labels, stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
         if self.global_batch != B:
             ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
-        self._wgrad(self.d_logits, self.final_v, "fc_out", B, 1, self.final_dim)
+        if self.has_fm:
+            ops.copy2d(self.d_logits, self.d_lrfm)
+        self._wgrad(self.d_logits, self.final_v, name, B, 1, self.final_dim)
         self._backward_backbone(fc.weight.data, self.d_logits, 1)
 
     def _ratio(self):
@@ -477,7 +570,7 @@ class FusedStep:
 
     def _state_tensors(self):
         ts = [self.step_counter, self.hyper]
-        ts += [p.data for p in self.dense.values()] + list(self.exp_avg.values()) + list(self.exp_avg_sq.values())
+        ts += list(self.opt_param.values()) + list(self.exp_avg.values()) + list(self.exp_avg_sq.values())
         for t in self.tables.values():
             ts += [t.p.data, t.m, t.v]
         return ts

@@ -1,8 +1,8 @@
 """Mirror of the reference's `code/trainer.py` (Trainer): same constructor, `dynamic_mask`, `get_optimizer`,
 `MFP_pretrain`, `RFD_pretrain`, `train`, `eval`, `MFP_pretrain_eval`, `RFD_pretrain_eval`, `save_model`, `load_model`,
 `test`.  Differences, all on purpose:
-  * the inner-loop body runs as one captured CUDA graph (`engine.FusedStep`) for the DCNv2 / DNN backbones; DeepFM goes
-    through the module path (autograd over the same kernels);
+  * the inner-loop body runs as one captured CUDA graph (`engine.FusedStep`) for the DCNv2 / DNN / DeepFM backbones (the module
+    path — autograd over the same kernels — serves eval and ragged last batches);
   * `dynamic_mask` runs on the device with a counter-based Philox stream (seed, step) instead of torch's host generator;
   * batches come from a device-resident shuffled-index batcher instead of DataLoader + per-row __getitem__
     (reference: 12 ms per 4096-row batch on the host);
@@ -185,7 +185,7 @@ class Trainer:
         return self._fused
 
     def supports_fused(self) -> bool:
-        return self.model.model_name.lower() in ("dcnv2", "dnn")
+        return self.model.model_name.lower() in ("dcnv2", "dnn", "deepfm")
 
     def train_step(self, X, Y=None):
         """Public single-step API: X [B, F] int64 on the host (ideally pinned) or on the device; returns the reference's

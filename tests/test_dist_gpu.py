@@ -1,0 +1,90 @@
+"""Multi-GPU parity (needs >= 2 GPUs): the R-rank row-sharded step equals the single-GPU step on the concatenated batch
+(SURVEY.md §8e parity oracle).  Philox streams are indexed by global row, so both runs draw identical masks and noise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _setup(pt_type, B, seed=0):
+    from map_code_b200 import synthetic as S
+    from map_code_b200.arguments import Config
+    from map_code_b200.models import BaseModel
+    F, D, H, P, K = 39, 16, 64, 32, 25
+    sizes = [max(2, s // 200) for s in S.field_sizes("criteo")]
+    V = S.vocab_size(sizes)
+    X = S.make_ids(sizes, 4096, seed=seed)
+    cfg = dict(model_name="DCNv2", embed_size=D, hidden_size=H, num_hidden_layers=3, num_cross_layers=3, hidden_act="relu",
+               hidden_dropout_rate=0.0, embed_dropout_rate=0.0, embed_norm=False, layer_norm_eps=1e-12, pt_neg_num=K, proj_size=P,
+               input_size=V, num_fields=F, pretrain=True, pt_type=pt_type, RFD_replace="Unigram", feat_count=S.feat_count(X, V),
+               data_dir=None, seed=42)
+    torch.manual_seed(1)
+    return BaseModel.from_config(Config.from_dict(cfg)), X, V
+
+
+def _rank_main(rank, world, port, pt_type, Bl, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from map_code_b200.dist import ShardedFusedStep
+        model, X, V = _setup(pt_type, Bl * world)
+        model.cuda()
+        eng = ShardedFusedStep(model, world=world, rank=rank, batch_size=Bl, mask_ratio=0.1, lr=1e-3, weight_decay=5e-2, sched="cosine",
+                               warmup_steps=1, total_steps=10, seed=42, optimizer_mode="dense_exact", x_train=X.cuda())
+        losses = []
+        for s in range(3):
+            gb = X[s * Bl * world:(s + 1) * Bl * world]
+            eng.step(gb[rank * Bl:(rank + 1) * Bl].contiguous().cuda())
+            losses.append(float(eng.outputs()[0]))
+        sd = eng.full_state_dict()
+        if rank == 0:
+            torch.save(dict(losses=losses, sd={k: v.cpu() for k, v in sd.items()}), out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pt_type", ["MFP", "RFD"])
+def test_sharded_step_equals_single_gpu(pt_type, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from map_code_b200.engine import FusedStep
+    world, Bl = 2, 256
+    out = str(tmp_path / "sharded.pt")
+    mp.spawn(_rank_main, args=(world, _free_port(), pt_type, Bl, out), nprocs=world, join=True)
+    got = torch.load(out)
+    model, X, V = _setup(pt_type, Bl * world)
+    model.cuda()
+    eng = FusedStep(model, batch_size=Bl * world, mask_ratio=0.1, lr=1e-3, weight_decay=5e-2, sched="cosine", warmup_steps=1,
+                    total_steps=10, seed=42, optimizer_mode="dense_exact", use_graph=False, x_train=X.cuda())
+    sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    for s in range(3):
+        eng.step(X[s * Bl * world:(s + 1) * Bl * world].contiguous().cuda())
+        ref = float(eng.outputs()[0])
+        assert abs(got["losses"][s] - ref) < 2e-4 * max(1.0, abs(ref)), (s, got["losses"][s], ref)
+    sd = model.state_dict()
+    for k, v in got["sd"].items():
+        if not v.dtype.is_floating_point:
+            assert torch.equal(v, sd[k].cpu())
+            continue
+        upd_ref = (sd[k].cpu() - sd0[k]).double()
+        upd_got = (v - sd0[k]).double()
+        denom = upd_ref.norm()
+        if denom == 0:
+            assert upd_got.norm() == 0, k
+        else:
+            # same kernels, same inputs; only the summation order of partial sums (reduce-scatter, all-reduce, TF32 tiles) differs
+            assert float((upd_got - upd_ref).norm() / denom) < 2e-2, f"{k}: {float((upd_got - upd_ref).norm() / denom):.3e}"

@@ -110,7 +110,7 @@ def test_modules_vs_reference_golden(golden, case, backend, monkeypatch):
 
 
 @pytest.mark.parametrize("backend", ["simt", "tcgen05"])
-@pytest.mark.parametrize("case", ["dcnv2_mfp", "dcnv2_rfd", "dcnv2_ctr"])
+@pytest.mark.parametrize("case", ["dcnv2_mfp", "dcnv2_rfd", "dcnv2_ctr", "deepfm_mfp", "deepfm_ctr"])
 def test_fused_step_vs_reference_golden(golden, case, backend):
     """The graph-capturable FusedStep (explicit backward, dedup'd table gradients, dense_exact optimizer) fed the reference's
     index tensors reproduces the reference's losses, gradients and three optimizer steps."""

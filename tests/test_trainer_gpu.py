@@ -1,0 +1,94 @@
+"""The reference-shaped public API end to end on the GPU: Trainer.MFP_pretrain / RFD_pretrain / train / eval / save / finetune
+on a small synthetic dataset (the flow of code/run.py:66-84)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class DS:
+    def __init__(self, X, Y):
+        self.X, self.Y = X, Y
+
+    def __len__(self):
+        return len(self.Y)
+
+
+def make(pt_type="MFP", pretrain=True, model_name="DCNv2", tmp="."):
+    from map_code_b200 import synthetic as S
+    from map_code_b200.arguments import Config, TrainingArguments
+    from map_code_b200.models import BaseModel
+    F = 39 if model_name != "DeepFM" else 24
+    sizes = [max(2, s // 300) for s in (S.field_sizes("criteo") if F == 39 else S.field_sizes("avazu"))]
+    V = S.vocab_size(sizes)
+    X = S.make_ids(sizes, 1280, seed=0)
+    Y = (torch.rand(1280, generator=torch.Generator().manual_seed(1)) < 0.2).long()
+    cfg = Config.from_dict(dict(model_name=model_name, embed_size=16, hidden_size=64, num_hidden_layers=3, num_cross_layers=3,
+                                hidden_act="relu", hidden_dropout_rate=0.0, embed_dropout_rate=0.0, embed_norm=False, layer_norm_eps=1e-12,
+                                pt_neg_num=25, proj_size=32, input_size=V, num_fields=F, pretrain=pretrain, pt_type=pt_type,
+                                RFD_replace="Unigram", feat_count=S.feat_count(X, V), data_dir=None, seed=42, table_grad_mode="sparse"))
+    args = TrainingArguments(output_dir=str(tmp), per_gpu_train_batch_size=256, per_gpu_eval_batch_size=512, learning_rate=1e-3,
+                             weight_decay=5e-2, num_train_epochs=2, lr_sched="cosine", logging_steps=2, sampling_method="randint",
+                             mask_ratio=0.1, pretrain=pretrain, pt_type=pt_type, seed=42)
+    torch.manual_seed(0)
+    model = BaseModel.from_config(cfg)
+    train, valid = DS(X[:1024].numpy(), Y[:1024].numpy()), DS(X[1024:].numpy(), Y[1024:].numpy())
+    return model, cfg, args, train, valid
+
+
+@pytest.mark.parametrize("model_name", ["DCNv2", "DeepFM"])
+@pytest.mark.parametrize("pt_type", ["MFP", "RFD"])
+def test_pretrain_loop_runs_and_learns(pt_type, model_name, tmp_path):
+    from map_code_b200.trainer import Trainer
+    model, cfg, args, train, valid = make(pt_type, True, model_name, tmp_path)
+    tr = Trainer(model, cfg, args, train, valid)
+    getattr(tr, f"{pt_type}_pretrain")()
+    assert tr.global_step == 8 and len(tr.eval_metrics) == 2
+    losses = [m[0] for m in tr.eval_metrics]
+    assert all(np.isfinite(losses)) and losses[1] < losses[0], losses     # the eval loss goes down between epochs
+    path = os.path.join(str(tmp_path), "8.model")
+    assert os.path.exists(path)
+    sd = torch.load(path)
+    assert "embed.embedding.weight" in sd and sd["embed.embedding.weight"].shape == (cfg.input_size, 16)
+    # finetune from the checkpoint: tensors that match by name+shape are loaded (models.py:97-112)
+    m2, cfg2, args2, train2, valid2 = make(pt_type, False, model_name, tmp_path)
+    m2.load_for_finetune(path)
+    assert torch.equal(m2.embed.embedding.weight.detach().cpu(), sd["embed.embedding.weight"])
+
+
+@pytest.mark.parametrize("model_name", ["DCNv2", "DeepFM"])
+def test_ctr_train_eval_test(model_name, tmp_path):
+    from map_code_b200.trainer import Trainer
+    model, cfg, args, train, valid = make("MFP", False, model_name, tmp_path)
+    tr = Trainer(model, cfg, args, train, valid)
+    tr.train()
+    assert len(tr.eval_metrics) >= 1 and 0.0 <= tr.eval_metrics[0][0] <= 1.0 and np.isfinite(tr.eval_metrics[0][1])
+    auc, ll = tr.test(valid)
+    assert 0.0 <= auc <= 1.0
+
+
+def test_dynamic_mask_api_and_errors(tmp_path):
+    from map_code_b200.trainer import Trainer
+    model, cfg, args, train, valid = make("MFP", True, "DCNv2", tmp_path)
+    model.cuda()
+    tr = Trainer(model, cfg, args, train, valid)
+    X = torch.from_numpy(train.X[:32])
+    out = tr.dynamic_mask({"input_ids": X.clone(), "labels": torch.zeros(32)}, "randint")
+    assert set(out.keys()) == {"input_ids", "labels", "masked_index"} and out["masked_index"].shape == (32, 3)
+    assert (out["input_ids"].gather(1, out["masked_index"]) == 3).all()
+    assert torch.equal(out["labels"].cpu(), X.gather(1, out["masked_index"].cpu()))
+    with pytest.raises(NotImplementedError):
+        tr.dynamic_mask({"input_ids": X.clone()}, "bogus")
+    args.pt_type = "XYZ"
+    with pytest.raises(NotImplementedError):
+        tr.dynamic_mask({"input_ids": X.clone()}, "randint")
+    args.pt_type, args.RFD_replace = "RFD", "Nope"
+    with pytest.raises(NotImplementedError):
+        tr.dynamic_mask({"input_ids": X.clone()}, "randint")
+    from map_code_b200.models import BaseModel
+    cfg.model_name = "xdeepfm"
+    with pytest.raises(NotImplementedError):
+        BaseModel.from_config(cfg)
