@@ -36,7 +36,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--task", default="MFP", choices=["MFP", "RFD"])
     ap.add_argument("--optimizer-mode", default="sparse", choices=["sparse", "dense_exact"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 4096; 65536 for --workload c5)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2: DCNv2 Criteo shape (BASELINE configs[1]/[2], the headline); c4: DeepFM on the Avazu shape (configs[3]); "
+                         "c5: DCNv2, ~1e8-row vocabulary x dim 64, batch 65536 (configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=5)
@@ -52,18 +55,32 @@ def peaks():
     return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
 
 
+WORKLOAD = "c2"
+
+
 def workload_name(task, batch, n):
+    if WORKLOAD == "c4":
+        return (f"DeepFM {task} pretraining, synthetic Avazu shape (24 fields, V=1334055), embed 16, hidden 1000x3, proj 32, K=25, "
+                f"mask_ratio 0.1 (L=2), batch {batch}/GPU x {n} GPU")
+    if WORKLOAD == "c5":
+        return (f"DCNv2 {task} pretraining, scaled Criteo shape (39 fields, V=99999992), embed 64, hidden 1000x3, cross 3, proj 32, K=25, "
+                f"mask_ratio 0.1 (L=3), batch {batch}/GPU x {n} GPU")
     return (f"DCNv2 {task} pretraining, synthetic Criteo shape (39 fields, V=1085271), embed 16, hidden 1000x3, cross 3, proj 32, "
             f"K=25, mask_ratio 0.1 (L=3), batch {batch}/GPU x {n} GPU")
 
 
 def config_dict(task):
     from map_code_b200 import synthetic as S
-    sizes = S.field_sizes("criteo")
+    if WORKLOAD == "c4":
+        sizes, name, d = S.field_sizes("avazu"), "DeepFM", D
+    elif WORKLOAD == "c5":
+        sizes, name, d = S.field_sizes("criteo", 100_000_000), "DCNv2", 64
+    else:
+        sizes, name, d = S.field_sizes("criteo"), "DCNv2", D
     V = S.vocab_size(sizes)
-    return sizes, V, dict(model_name="DCNv2", embed_size=D, hidden_size=H, num_hidden_layers=NH, num_cross_layers=NC, hidden_act="relu",
+    return sizes, V, dict(model_name=name, embed_size=d, hidden_size=H, num_hidden_layers=NH, num_cross_layers=NC, hidden_act="relu",
                           hidden_dropout_rate=0.0, embed_dropout_rate=0.0, embed_norm=False, layer_norm_eps=1e-12, pt_neg_num=K,
-                          proj_size=P, input_size=V, num_fields=F_CRITEO, pretrain=True, pt_type=task, RFD_replace="Unigram")
+                          proj_size=P, input_size=V, num_fields=len(sizes), pretrain=True, pt_type=task, RFD_replace="Unigram")
 
 
 # --------------------------------------------------------------------------------------------------------------- clocks
@@ -107,10 +124,15 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------------------------- CPU arm
 def build_oracle(task, batch, n_train=1 << 16):
-    """The reference's CPU path restated (oracle/map_oracle.py): dense gradients + dense AdamW over every table."""
+    """The reference's CPU path restated (oracle/map_oracle.py): dense gradients + dense AdamW over every table.
+    The dense reference algorithm cannot hold the C5 tables (3 x 25.6 GB + dense gradients): the CPU arm of c5 is timed at
+    the largest configuration the reference handles, the c2 vocabulary and width (stated in `sample`)."""
+    global WORKLOAD
     from map_code_b200 import synthetic as S
     from oracle import map_oracle as O
+    saved, WORKLOAD = WORKLOAD, ("c2" if WORKLOAD == "c5" else WORKLOAD)
     sizes, V, cfgd = config_dict(task)
+    WORKLOAD = saved
     X = S.make_ids(sizes, n_train, seed=0)
     fc = S.feat_count(X, V)
     cfg = O.OracleConfig(**cfgd)
@@ -205,11 +227,15 @@ def main_ours(args):
 
     sizes, V, cfgd = config_dict(args.task)
     Bg = args.batch * world
-    X_train = S.make_ids(sizes, N_TRAIN, seed=0)
+    n_train = N_TRAIN if WORKLOAD != "c5" else max(1 << 18, 4 * Bg)
+    X_train = S.make_ids(sizes, n_train, seed=0)
     fc = S.feat_count(X_train, V)
     cfgd.update(feat_count=fc, data_dir=None, seed=42, table_grad_mode="sparse")
     torch.manual_seed(1)
-    model = BaseModel.from_config(Config.from_dict(cfgd)).to(dev)
+    with torch.device(dev):  # parameters are created on the GPU (the C5 tables do not fit comfortably in host memory)
+        model = BaseModel.from_config(Config.from_dict(cfgd))
+    model.to(dev)
+    n_fields = len(sizes)
 
     class DS:
         def __init__(self, X):
@@ -224,6 +250,8 @@ def main_ours(args):
     X_dev = X_train.to(dev)
     trainer = Trainer(model, model.config, targs, DS(X_dev), DS(X_dev))
     total_steps = 100000
+    if world > 1 and WORKLOAD == "c4":
+        raise SystemExit("c4 (DeepFM) runs on one GPU in this revision: the first-order table is not row-sharded yet")
     if world > 1:
         from map_code_b200 import dist as mdist
         eng = mdist.make_sharded_step(trainer, total_steps, 0, world, rank)
@@ -231,7 +259,7 @@ def main_ours(args):
         eng = trainer.fused_step(total_steps, 0)
     eng.use_graph = not args.no_graph  # NCCL collectives of the sharded step are captured in the graph as well
 
-    n_batches = N_TRAIN // Bg
+    n_batches = n_train // Bg
     def batch(i):  # rank-local slice of global batch i (device resident)
         r0 = (i % n_batches) * Bg + rank * args.batch
         return X_dev[r0:r0 + args.batch]
@@ -359,13 +387,14 @@ def main_ours(args):
 
     n_launch = sum(launches.values()) if launches else None
     line = {
-        "metric": f"{args.task} pretrain samples/sec (DCNv2, Criteo shape)", "value": value, "unit": "samples/s", "n_gpus": world,
+        "metric": f"{args.task} pretrain samples/sec ({'DeepFM, Avazu shape' if WORKLOAD == 'c4' else 'DCNv2, Criteo shape'})", "value": value,
+        "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core multiplies, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": workload_name(args.task, args.batch, world), "global_batch": Bg, "optimizer_mode": args.optimizer_mode,
-                   "cuda_graph": not args.no_graph, "l2": "inputs larger than L2: tables+optimizer state ~0.9 GB touched at random, a new batch every step; no explicit flush",
+                   "cuda_graph": not args.no_graph, "l2": "inputs larger than L2: tables + optimizer state (0.9 GB at c2/c4, >100 GB at c5) touched at random, a new batch every step; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else f"row-sharded tables (id mod {world}) + NCCL all-to-all; dense params replicated + allreduce"},
-        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": args.batch * F_CRITEO * 8, "d2h_bytes_per_step": 4,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": args.batch * n_fields * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": (n_launch * args.steps) if n_launch else None, "launches_per_step": n_launch,
         "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown, "loss_after": loss_after,
@@ -377,6 +406,9 @@ def main_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    WORKLOAD = a.workload
+    if a.batch is None:
+        a.batch = 65536 if WORKLOAD == "c5" else B_PER_GPU
     if a.impl == "reference":
         main_reference(a)
     else:

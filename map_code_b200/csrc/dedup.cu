@@ -149,54 +149,91 @@ __global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint32_t* data, i
     }
 }
 
-// Stable scatter of one digit.  Order inside a tile is (item round, thread) == ascending index, ranks are computed per
-// warp with match.any and combined across warps/rounds through shared-memory counters.
+// Stable scatter of one digit.  Order inside a tile is (item round, thread) == ascending index.  Ranks are computed per warp
+// with match.any and combined across warps / rounds through shared-memory counters; the tile is then REORDERED IN SHARED
+// MEMORY by digit so that the global writes of one digit are contiguous (coalesced runs instead of 32 scattered 4-byte
+// stores per warp instruction).
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                     const uint32_t* __restrict__ vals_in, int64_t n,
                                                                     int shift, const uint32_t* __restrict__ hist_scanned,
                                                                     int nblocks, uint32_t* __restrict__ keys_out,
                                                                     uint32_t* __restrict__ vals_out) {
-    // counts[round][warp][bin] would be 8*8*256*4 = 64 KB; instead process rounds sequentially with a running
-    // per-bin base (bin_base) and per-round per-warp counts (8*256*4 = 8 KB).
-    __shared__ uint32_t warp_cnt[kSortWarps][kRadixBins];
-    __shared__ uint32_t bin_base[kRadixBins];
+    __shared__ uint32_t warp_cnt[kSortWarps][kRadixBins];  // per-round per-warp digit counts -> exclusive prefixes
+    __shared__ uint32_t tile_run[kRadixBins];              // running count of each digit over the rounds done so far
+    __shared__ uint32_t tile_excl[kRadixBins];             // exclusive scan over digits of the tile histogram
+    __shared__ uint32_t gbase[kRadixBins];                 // global start of (digit, this tile)
+    __shared__ uint32_t warp_tot[kSortWarps];
+    __shared__ uint32_t keys_s[kSortTile];
+    __shared__ uint32_t vals_s[kSortTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bin_base[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * kRadixBins + threadIdx.x];
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    const int tile_n = (int)((n - base < kSortTile) ? (n - base) : kSortTile);
+    gbase[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * kRadixBins + threadIdx.x];
+    tile_run[threadIdx.x] = 0;
+    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+    // ---- pass A: load, and rank every key among the keys of the same digit that precede it in the tile
     for (int it = 0; it < kSortItems; ++it) {
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) warp_cnt[w][threadIdx.x] = 0;
         __syncthreads();
-        const int64_t i = base + it * kSortThreads + threadIdx.x;
-        const bool valid = i < n;
-        uint32_t key = 0, val = 0;
-        if (valid) {
-            key = keys_in[i];
-            val = vals_in[i];
-        }
-        const uint32_t digit = valid ? ((key >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
+        const int li = it * kSortThreads + threadIdx.x;
+        const bool valid = li < tile_n;
+        key[it] = valid ? keys_in[base + li] : 0u;
+        val[it] = valid ? vals_in[base + li] : 0u;
+        const uint32_t digit = valid ? ((key[it] >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
         const uint32_t peers = __match_any_sync(0xffffffffu, digit);
         const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank_in_warp == 0) warp_cnt[warp][digit] = __popc(peers);
         __syncthreads();
-        // thread d: exclusive prefix of bin d over the warps of this round, then advance the running base
-        {
-            uint32_t run = bin_base[threadIdx.x];
+        {   // thread d: exclusive prefix of digit d over the warps of this round, on top of the rounds before
+            uint32_t run = tile_run[threadIdx.x];
 #pragma unroll
             for (int w = 0; w < kSortWarps; ++w) {
                 const uint32_t c = warp_cnt[w][threadIdx.x];
                 warp_cnt[w][threadIdx.x] = run;
                 run += c;
             }
-            bin_base[threadIdx.x] = run;
+            tile_run[threadIdx.x] = run;
         }
         __syncthreads();
-        if (valid) {
-            const uint32_t pos = warp_cnt[warp][digit] + rank_in_warp;
-            keys_out[pos] = key;
-            vals_out[pos] = val;
-        }
+        rank[it] = valid ? warp_cnt[warp][digit] + rank_in_warp : 0u;
         __syncthreads();
+    }
+    // ---- exclusive scan of the tile histogram (tile_run now holds the per-digit totals)
+    {
+        const uint32_t t = tile_run[threadIdx.x];
+        uint32_t incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        tile_excl[threadIdx.x] = off + incl - t;
+    }
+    __syncthreads();
+    // ---- pass B: reorder the tile by digit in shared memory (stable)
+#pragma unroll
+    for (int it = 0; it < kSortItems; ++it) {
+        const int li = it * kSortThreads + threadIdx.x;
+        if (li < tile_n) {
+            const uint32_t digit = (key[it] >> shift) & (kRadixBins - 1);
+            const uint32_t lp = tile_excl[digit] + rank[it];
+            keys_s[lp] = key[it];
+            vals_s[lp] = val[it];
+        }
+    }
+    __syncthreads();
+    // ---- pass C: position i of the reordered tile goes to gbase[digit] + (i - tile_excl[digit])
+    for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
+        const uint32_t k = keys_s[i];
+        const uint32_t digit = (k >> shift) & (kRadixBins - 1);
+        const uint32_t pos = gbase[digit] + ((uint32_t)i - tile_excl[digit]);
+        keys_out[pos] = k;
+        vals_out[pos] = vals_s[i];
     }
 }
 
@@ -277,7 +314,7 @@ template <>
 struct RowVec<4> {
     float4 v;
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+    __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
     __device__ __forceinline__ void fma(const RowVec& a, float s) {
         v.x = fmaf(a.v.x, s, v.x); v.y = fmaf(a.v.y, s, v.y); v.z = fmaf(a.v.z, s, v.z); v.w = fmaf(a.v.w, s, v.w);
     }
@@ -290,15 +327,17 @@ template <>
 struct RowVec<1> {
     float v;
     __device__ __forceinline__ void zero() { v = 0.f; }
-    __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+    __device__ __forceinline__ void load(const float* p) { v = *p; }
     __device__ __forceinline__ void fma(const RowVec& a, float s) { v = fmaf(a.v, s, v); }
     __device__ __forceinline__ void store(float* p) const { *p = v; }
     __device__ __forceinline__ void atomic_add(float* p) const { atomicAdd(p, v); }
 };
 
-// One group of `lanes` threads (lanes = D / VEC) walks kSegTile consecutive sorted positions.  A segment that lies
-// entirely inside the tile is written with a plain store; segments that straddle tiles (hot ids such as <mask>=3) are
-// combined with atomics into the pre-zeroed compact gradient: at most 2 atomics per tile per lane.
+// One group of `lanes` threads (lanes = D / VEC) walks kSegTile consecutive sorted positions.  A segment that lies entirely
+// inside the tile is written with a plain store.  Segments that straddle tile borders (hot ids: <mask> = 3 collects B*L
+// occurrences) are first merged ACROSS THE GROUPS OF THE CTA through shared memory — every group deposits at most a
+// "head" and a "tail" partial — and only the per-CTA result goes to global memory: a plain store when the segment lies
+// inside the CTA's range, otherwise one atomic per CTA (instead of one per 8 occurrences).
 template <int VEC>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __restrict__ rows, int64_t ld_rows, int lanes,
                                                              const float* __restrict__ scale, int group,
@@ -307,59 +346,107 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
                                                              const int32_t* __restrict__ n_unique, int64_t n,
                                                              float* __restrict__ grad, float* __restrict__ scalar_out,
                                                              int D) {
-    const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t tile = gthread / lanes;
-    const int lane = (int)(gthread - tile * lanes);
-    const int64_t t0 = tile * kSegTile;
-    if (t0 >= n) return;
+    __shared__ int slot_seg[2 * 256];                  // segment id of every head (2g) / tail (2g+1) slot, -1 = empty
+    __shared__ float slot_sc[2 * 256];
+    __shared__ __align__(16) float slot_vec[2 * 256 * VEC];  // [slot][lanes * VEC] with 2 * G * lanes * VEC <= 512 * VEC
+    const int G = 256 / lanes;                         // groups per CTA
+    const int g = threadIdx.x / lanes;
+    const int lane = threadIdx.x - g * lanes;
+    const bool in_group = g < G;
+    const int64_t blk_t0 = (int64_t)blockIdx.x * G * kSegTile;
+    const int64_t blk_t1 = (blk_t0 + (int64_t)G * kSegTile < n) ? blk_t0 + (int64_t)G * kSegTile : n;
+    const int64_t t0 = blk_t0 + (int64_t)g * kSegTile;
+    const bool active = in_group && t0 < n;
     const int64_t t1 = (t0 + kSegTile < n) ? t0 + kSegTile : n;
     const int U = *n_unique;
-    // segment containing t0: largest s with seg_start[s] <= t0
-    int lo = 0, hi = U - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int64_t)seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+    const int rowlen = lanes * VEC;
+    if (in_group && lane == 0) {
+        slot_seg[2 * g] = -1;
+        slot_seg[2 * g + 1] = -1;
     }
-    int s = lo;
-    int64_t s_end = seg_start[s + 1];
-
-    RowVec<VEC> r[kSegTile];
-    float sc[kSegTile];
-#pragma unroll
-    for (int k = 0; k < kSegTile; ++k) {
-        sc[k] = 0.f;
-        r[k].zero();
-        if (t0 + k < t1) {
-            const int64_t occ = occ_sorted[t0 + k];
-            sc[k] = (scale != nullptr) ? __ldg(scale + occ) : 1.f;
-            r[k].load(rows + (occ / group) * ld_rows + lane * VEC);
+    if (active) {
+        // segment containing t0: largest s with seg_start[s] <= t0
+        int lo = 0, hi = U - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int64_t)seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
         }
-    }
-    RowVec<VEC> acc;
-    acc.zero();
-    float sacc = 0.f;
-    int64_t seg_first_pos = (int64_t)seg_start[s];
+        int s = lo;
+        int64_t s_end = seg_start[s + 1];
+        RowVec<VEC> r[kSegTile];
+        float sc[kSegTile];
 #pragma unroll
-    for (int k = 0; k < kSegTile; ++k) {
-        const int64_t pos = t0 + k;
-        if (pos < t1) {
-            acc.fma(r[k], sc[k]);
-            sacc += sc[k];
-            if (pos + 1 == s_end || pos + 1 == t1) {  // flush
-                const bool whole = (seg_first_pos >= t0) && (s_end <= t1);
-                float* dst = grad + (int64_t)s * D + lane * VEC;
-                if (whole) acc.store(dst); else acc.atomic_add(dst);
-                if (scalar_out != nullptr && lane == 0) {
-                    if (whole) scalar_out[s] = sacc; else atomicAdd(scalar_out + s, sacc);
-                }
-                acc.zero();
-                sacc = 0.f;
-                if (pos + 1 == s_end && pos + 1 < t1) {
-                    ++s;
-                    seg_first_pos = s_end;
-                    s_end = seg_start[s + 1];
+        for (int k = 0; k < kSegTile; ++k) {
+            sc[k] = 0.f;
+            r[k].zero();
+            if (t0 + k < t1) {
+                const int64_t occ = occ_sorted[t0 + k];
+                sc[k] = (scale != nullptr) ? __ldg(scale + occ) : 1.f;
+                r[k].load(rows + (occ / group) * ld_rows + lane * VEC);
+            }
+        }
+        RowVec<VEC> acc;
+        acc.zero();
+        float sacc = 0.f;
+        int64_t seg_first_pos = (int64_t)seg_start[s];
+#pragma unroll
+        for (int k = 0; k < kSegTile; ++k) {
+            const int64_t pos = t0 + k;
+            if (pos < t1) {
+                acc.fma(r[k], sc[k]);
+                sacc += sc[k];
+                if (pos + 1 == s_end || pos + 1 == t1) {  // flush
+                    const bool starts_here = seg_first_pos >= t0;
+                    const bool ends_here = s_end <= t1;
+                    if (starts_here && ends_here) {       // interior segment of this tile
+                        acc.store(grad + (int64_t)s * D + lane * VEC);
+                        if (scalar_out != nullptr && lane == 0) scalar_out[s] = sacc;
+                    } else {                              // straddles: head slot if it began before the tile, else tail slot
+                        const int slot = starts_here ? 2 * g + 1 : 2 * g;
+                        acc.store(slot_vec + slot * rowlen + lane * VEC);
+                        if (lane == 0) {
+                            slot_seg[slot] = s;
+                            slot_sc[slot] = sacc;
+                        }
+                    }
+                    acc.zero();
+                    sacc = 0.f;
+                    if (pos + 1 == s_end && pos + 1 < t1) {
+                        ++s;
+                        seg_first_pos = s_end;
+                        s_end = seg_start[s + 1];
+                    }
                 }
             }
+        }
+    }
+    __syncthreads();
+    if (!in_group) return;
+    // merge equal-segment runs of slots (in position order; empty slots are skipped); the first slot of a run is its leader
+    for (int h = 0; h < 2; ++h) {
+        const int i = 2 * g + h;
+        const int s = slot_seg[i];
+        if (s < 0) continue;
+        int j = i - 1;
+        while (j >= 0 && slot_seg[j] < 0) --j;
+        if (j >= 0 && slot_seg[j] == s) continue;  // not the leader
+        RowVec<VEC> acc;
+        acc.load(slot_vec + i * rowlen + lane * VEC);
+        float sacc = slot_sc[i];
+        for (int k = i + 1; k < 2 * G; ++k) {
+            const int sk = slot_seg[k];
+            if (sk < 0) continue;
+            if (sk != s) break;
+            RowVec<VEC> o;
+            o.load(slot_vec + k * rowlen + lane * VEC);
+            acc.fma(o, 1.f);
+            sacc += slot_sc[k];
+        }
+        const bool whole = ((int64_t)seg_start[s] >= blk_t0) && ((int64_t)seg_start[s + 1] <= blk_t1);
+        float* dst = grad + (int64_t)s * D + lane * VEC;
+        if (whole) acc.store(dst); else acc.atomic_add(dst);
+        if (scalar_out != nullptr && lane == 0) {
+            if (whole) scalar_out[s] = sacc; else atomicAdd(scalar_out + s, sacc);
         }
     }
 }
@@ -465,9 +552,9 @@ extern "C" int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
         zero_unique_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad_compact, scalar_out, D, n_unique, max_elems);
     }
+    MAP_REQUIRE(lanes <= 256, "map_segment_reduce_rows: D=%d too wide for one CTA", D);
     const int64_t tiles = ceil_div(n_ids, kSegTile);
-    const int64_t threads = tiles * lanes;
-    const unsigned blocks = (unsigned)ceil_div(threads, 256);
+    const unsigned blocks = (unsigned)ceil_div(tiles, 256 / lanes);
     if (vec)
         segment_reduce_kernel<4><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique,
                                                          n_ids, grad_compact, scalar_out, D);

@@ -575,13 +575,19 @@ class FusedStep:
             ts += [t.p.data, t.m, t.v]
         return ts
 
+    SNAPSHOT_LIMIT_BYTES = 8 << 30
+
     def _snapshot(self):
-        """The warm-up / capture passes execute real optimizer steps; training state is put back afterwards.  Tables are
-        snapshotted too (cheap at Criteo scale; at the 100M-row sweep call capture() before loading weights instead)."""
-        return [t.clone() for t in self._state_tensors()]
+        """The warm-up / capture passes execute real optimizer steps; training state is put back afterwards.  When the state
+        is too large to clone (the 100M-row tables of config C5) only the step counter is restored: the two warm-up passes
+        then count as two real optimizer steps on their batch — capture before loading weights if that matters."""
+        ts = self._state_tensors()
+        if sum(t.numel() * t.element_size() for t in ts) > self.SNAPSHOT_LIMIT_BYTES:
+            ts = ts[:2]
+        return [(t, t.clone()) for t in ts]
 
     def _restore(self, snap):
-        for t, s in zip(self._state_tensors(), snap):
+        for t, s in snap:
             t.copy_(s)
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None):

