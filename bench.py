@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=5)
+    ap.add_argument("--timeline", default=None, help="re-capture the step with a timestamp marker after every call and write the "
+                                                     "per-stream timeline of one graph replay here (single GPU)")
     ap.add_argument("--dump-profile", default=None, help="write the per-(kernel, shape) timing table of the eager profiling pass here")
     return ap.parse_args()
 
@@ -207,8 +209,68 @@ def algorithmic(tag):
     return 0.0, 0.0
 
 
+def _stage(msg):
+    if os.environ.get("MAP_B200_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+def write_timeline(eng, batch, path):
+    """Timeline of the captured multi-stream step: the step is re-captured with a one-thread %globaltimer marker after every
+    C-ABI call on that call's stream; one replay then yields the end time of every call inside the real graph schedule
+    (markers add ~1-2 us per call, so the step is a little slower than the timed one)."""
+    from map_code_b200 import _lib
+    buf = torch.zeros(4096, dtype=torch.int64, device=eng.dev)
+    t_begin = torch.zeros(1, dtype=torch.int64, device=eng.dev)
+    _lib.TIMELINE = dict(buf=buf, ops=[])
+    eng.graph = None
+    eng.use_graph = True
+    orig_body = eng._step_body
+
+    def body():
+        _lib.load().map_timestamp_ns(t_begin.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.TIMELINE["ops"].clear()
+        orig_body()
+
+    eng._step_body = body
+    for i in range(4):
+        eng.step(batch(i))
+    torch.cuda.synchronize()
+    ops_, _lib.TIMELINE = list(_lib.TIMELINE["ops"]), None
+    eng._step_body = orig_body
+    eng.graph = None
+    t0 = int(t_begin.item())
+    ends = buf[:len(ops_)].cpu().tolist()
+    streams = {}
+    last_end = {}
+    rows = []
+    for (name, tag, st), e in zip(ops_, ends):
+        sid = streams.setdefault(st, len(streams))
+        rows.append((e - t0, sid, name, tag, last_end.get(sid)))
+        last_end[sid] = e - t0
+    with open(path, "w") as f:
+        f.write(f"# step span {max(r[0] for r in rows) / 1e3:.1f} us; columns: end_us stream since_prev_on_stream_us call tag\n")
+        for end, sid, name, tag, prev in sorted(rows):
+            d = "" if prev is None else f"{(end - prev) / 1e3:8.1f}"
+            f.write(f"{end / 1e3:9.1f} s{sid} {d:>8s} {name:30s} {tag if tag else ''}\n")
+
+
+def _shutdown(world):
+    """Multi-rank exit: ranks leave together and skip the NCCL communicator teardown (destroy_process_group after CUDA-graph
+    captured collectives was seen to hang at N=2); the result line is already flushed."""
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main_ours(args):
+    import faulthandler
     import torch.distributed as dist
+    faulthandler.enable()  # a SIGSEGV in native code prints the Python stack of every thread
     from map_code_b200 import _lib, synthetic as S
     from map_code_b200.arguments import Config, TrainingArguments
     from map_code_b200.models import BaseModel
@@ -222,7 +284,11 @@ def main_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a lost rank must not hang the box: collectives time out after 3 minutes, and every thread's stack is dumped if the
+        # whole run is still alive after 12 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        faulthandler.dump_traceback_later(720, exit=True)
     _lib.load()  # fail loudly if the sm_100a library is missing
 
     sizes, V, cfgd = config_dict(args.task)
@@ -264,6 +330,7 @@ def main_ours(args):
         r0 = (i % n_batches) * Bg + rank * args.batch
         return X_dev[r0:r0 + args.batch]
 
+    _stage('engine built')
     # ---- warm-up (also captures the CUDA graph)
     for i in range(max(args.warmup, 3)):
         eng.step(batch(i))
@@ -271,6 +338,7 @@ def main_ours(args):
     if world > 1:
         dist.barrier()
 
+    _stage('warm-up done')
     # ---- timed region: device-resident inputs, CUDA events, no host sync inside
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -289,6 +357,7 @@ def main_ours(args):
     loss_after = float(eng.outputs()[0])
     value = Bg * args.steps / (ms / 1e3)
 
+    _stage('timed region done')
     # ---- e2e: public API with HOST (pinned) inputs; H2D copy of the ids and D2H read of the loss every step
     host_batches = [X_train[(i % n_batches) * Bg + rank * args.batch:][:args.batch].contiguous().pin_memory() for i in range(8)]
     for i in range(3):
@@ -308,6 +377,7 @@ def main_ours(args):
         e2e_s = float(t.item())
     e2e = Bg * args.steps / e2e_s
 
+    _stage('e2e done')
     # ---- per-kernel timing (eager replay of the same schedule, every C-ABI call bracketed by CUDA events on its stream)
     breakdown, roof, launches = None, None, None
     pk = peaks()
@@ -374,9 +444,11 @@ def main_ours(args):
             roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                     "traffic": None, "note": f"peak = {pk['src']} copy bandwidth"}
 
+    _stage('profiling pass done')
+    if args.timeline and world == 1 and not args.no_graph:
+        write_timeline(eng, batch, args.timeline)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(world)
         return
 
     cpu = None
@@ -400,8 +472,7 @@ def main_ours(args):
         "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown, "loss_after": loss_after,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown(world)
 
 
 if __name__ == "__main__":

@@ -41,6 +41,9 @@ int map_abi_version(void);
 const char* map_last_error(void);
 /* number of SMs of the current device (grid sizing on the host side) */
 int map_sm_count(int* out);
+/* *slot = %globaltimer (ns) when the stream reaches this point: a one-thread marker kernel.  Used by bench.py --timeline to
+ * reconstruct the timeline of the captured multi-stream step (there is no nsys in the image). */
+int map_timestamp_ns(unsigned long long* slot, map_stream_t stream);
 
 /* ------------------------------------------------------------------ K1  embedding gather
  * replaces nn.Embedding forward: code/layers.py:98 (Embeddings.forward), code/models.py:139 (LR.embed_w),
@@ -197,6 +200,12 @@ int map_fm_lr_bwd(const float* feat_embed, const float* g, int64_t ld_g, int64_t
 #define MAP_EPI_MUL_RELUMASK 4  /* C = acc * (aux0 > 0)                          (dX through a ReLU, aux0 = fwd output) */
 #define MAP_EPI_ADD 5           /* C = acc + aux0                                 (residual gradient) */
 #define MAP_EPI_ADD_MUL 6       /* C = (acc + aux0) * aux1 ; aux_out = (acc + aux0)  (next cross layer's dU from G) */
+/* One whole CrossNetV2 backward stage in the dgrad GEMM's epilogue (autograd of code/layers.py:200, replaces the separate
+ * elementwise pass):  G = acc + aux0 (aux0 = G of the layer above, NULL for the first stage) ; aux_out = G ;
+ * C = G * aux1 (dU of the layer below, aux1 = X0) ; acc_out (+)= G * aux2 (dX0 accumulator, aux2 = U of the layer below;
+ * acc_accumulate = 0 stores, 1 adds with fp32 reductions). */
+#define MAP_EPI_CROSS_BWD 7
+#define MAP_EPI_ADD3 8          /* C = acc + aux0 + aux1 (+ aux2 if not NULL)     (dE = G0 + dX0_cross + dX0_mlp) */
 typedef struct {
     int32_t M, N, K;
     int32_t trans_a, trans_b;
@@ -208,13 +217,24 @@ typedef struct {
     const float* aux0; int64_t ld_aux0;
     const float* aux1; int64_t ld_aux1;
     float* aux_out; int64_t ld_aux_out;
+    const float* aux2; int64_t ld_aux2;
+    float* acc_out; int64_t ld_acc_out;   /* MAP_EPI_CROSS_BWD only */
+    int32_t acc_accumulate;
+    int32_t reserved_;
+    /* optional, any epilogue: colsum_out[n] += sum_m C[m,n] with fp32 reductions (bias gradient of the layer whose
+     * pre-activation gradient this GEMM writes); the caller zeroes it beforehand.  Not with split-K. */
+    float* colsum_out;
 } map_gemm_args;
+/* bias / aux0 / aux1 are read through the read-only (non-coherent) path: they must not alias C or aux_out. */
 /* exact fp32 on CUDA cores: skinny shapes (N < 64: pred_rfd.2, fc_out) and the fp32 cross-check of the TF32 path */
 int map_gemm_f32_simt(const map_gemm_args* args, map_stream_t stream);
 /* tcgen05 (kind::tf32) + TMA + TMEM, fp32 accumulate.  Requires 16-byte aligned base pointers and lda/ldb % 4 == 0. */
 int map_gemm_tf32_tcgen05(const map_gemm_args* args, map_stream_t stream);
 /* 1 if map_gemm_tf32_tcgen05 accepts these arguments (shape / alignment), else 0 */
 int map_gemm_tf32_supported(const map_gemm_args* args);
+/* Tuning aid (scripts/trace_gemm.py): while dev_buf != NULL every CTA of the following tcgen05 GEMM launches (grids of at
+ * most capacity_records CTAs) writes 8 uint64 phase timestamps to dev_buf[8 * linear_cta_id ...].  NULL switches it off. */
+int map_gemm_set_trace(unsigned long long* dev_buf, int64_t capacity_records);
 
 /* ------------------------------------------------------------------ K13  row-sharded tables (owner-side kernels)
  * The reference initialises NCCL (code/arguments.py:74) but never issues a collective; this is the multi-GPU path the

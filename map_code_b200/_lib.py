@@ -18,7 +18,7 @@ SCHED_CONST, SCHED_COSINE = 0, 1
 SAMPLING_RANDINT, SAMPLING_NORMAL = 0, 1
 RFD_MODES = {"Unigram": 0, "Uniform": 1, "Whole-Uniform": 2, "Whole-Unigram": 3}
 NCE_LOSS = {"nce": 0, "sampled": 1}
-EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_CROSS, EPI_MUL_RELUMASK, EPI_ADD, EPI_ADD_MUL = range(7)
+EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_CROSS, EPI_MUL_RELUMASK, EPI_ADD, EPI_ADD_MUL, EPI_CROSS_BWD, EPI_ADD3 = range(9)
 
 
 class GemmArgs(C.Structure):
@@ -32,6 +32,10 @@ class GemmArgs(C.Structure):
         ("aux0", C.c_void_p), ("ld_aux0", C.c_int64),
         ("aux1", C.c_void_p), ("ld_aux1", C.c_int64),
         ("aux_out", C.c_void_p), ("ld_aux_out", C.c_int64),
+        ("aux2", C.c_void_p), ("ld_aux2", C.c_int64),
+        ("acc_out", C.c_void_p), ("ld_acc_out", C.c_int64),
+        ("acc_accumulate", C.c_int32), ("reserved_", C.c_int32),
+        ("colsum_out", C.c_void_p),
     ]
 
 
@@ -49,6 +53,7 @@ PROTOTYPES = {
     "map_abi_version": (_i, []),
     "map_last_error": (C.c_char_p, []),
     "map_sm_count": (_i, [C.POINTER(C.c_int)]),
+    "map_timestamp_ns": (_i, [_p, _p]),
     "map_emb_gather_f32": (_i, [_p, _l, _i, _p, _l, _p, _p, _p]),
     "map_dedup_workspace_bytes": (_sz, [_l]),
     "map_dedup_ids": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _sz, _p]),
@@ -75,6 +80,7 @@ PROTOTYPES = {
     "map_gemm_f32_simt": (_i, [C.POINTER(GemmArgs), _p]),
     "map_gemm_tf32_tcgen05": (_i, [C.POINTER(GemmArgs), _p]),
     "map_gemm_tf32_supported": (_i, [C.POINTER(GemmArgs)]),
+    "map_gemm_set_trace": (_i, [_p, _l]),
     "map_emb_gather_owned_f32": (_i, [_p, _l, _i, _p, _l, _i, _i, _p, _p]),
     "map_owned_keys": (_i, [_p, _l, _i, _i, _l, _p, _p]),
     "map_nce_scores_owned": (_i, [_p, _l, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
@@ -131,6 +137,8 @@ KERNELS_PER_CALL = {
 PROFILE = None        # set to a list: every call is bracketed by CUDA events -> (name, tag, start_event, end_event)
 CURRENT_TAG = None    # free-form shape tag set by ops.* just before a call (e.g. "4096x1000x624 tn")
 LAUNCHES = None       # set to a dict: name -> number of kernels launched
+TIMELINE = None       # set to dict(buf=<device int64 tensor>, ops=[]): a timestamp marker follows every call on its stream
+HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace"}
 
 
 def call(name: str, *args):
@@ -150,6 +158,12 @@ def call(name: str, *args):
         CURRENT_TAG = None
     else:
         rc = getattr(load(), name)(*args)
+    if TIMELINE is not None and name not in HOST_FUNCS and rc == MAP_OK:
+        i = len(TIMELINE["ops"])
+        if 8 * (i + 1) <= TIMELINE["buf"].numel() * 8:
+            TIMELINE["ops"].append((name, CURRENT_TAG if PROFILE is None else None, int(args[-1] or 0)))
+            load().map_timestamp_ns(TIMELINE["buf"].data_ptr() + 8 * i, args[-1])
+        CURRENT_TAG = None
     if rc != MAP_OK:
         msg = f"{name} failed ({rc}): {last_error()}"
         if rc == MAP_EUNSUPPORTED:

@@ -22,7 +22,18 @@ int check_launch(const char* what) {
     }
     return MAP_OK;
 }
+__global__ void timestamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    *slot = t;
+}
 }  // namespace mapb
+
+extern "C" int map_timestamp_ns(unsigned long long* slot, map_stream_t stream) {
+    MAP_REQUIRE(slot != nullptr, "map_timestamp_ns: null pointer");
+    mapb::timestamp_kernel<<<1, 1, 0, mapb::as_stream(stream)>>>(slot);
+    return mapb::check_launch("map_timestamp_ns");
+}
 
 extern "C" int map_abi_version(void) { return MAP_B200_ABI_VERSION; }
 extern "C" const char* map_last_error(void) { return mapb::g_err; }

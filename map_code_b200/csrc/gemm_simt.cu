@@ -24,6 +24,17 @@ __device__ __forceinline__ float apply_epilogue(const map_gemm_args& a, float ac
             a.aux_out[(int64_t)m * a.ld_aux_out + n] = s;
             return s * a.aux1[(int64_t)m * a.ld_aux1 + n];
         }
+        case MAP_EPI_CROSS_BWD: {  // every (m, n) belongs to exactly one thread: the accumulation is a plain read-modify-write
+            const float g = acc + (a.aux0 ? a.aux0[(int64_t)m * a.ld_aux0 + n] : 0.f);
+            if (a.aux_out) a.aux_out[(int64_t)m * a.ld_aux_out + n] = g;
+            float* d = a.acc_out + (int64_t)m * a.ld_acc_out + n;
+            const float t = g * a.aux2[(int64_t)m * a.ld_aux2 + n];
+            *d = a.acc_accumulate ? *d + t : t;
+            return g * a.aux1[(int64_t)m * a.ld_aux1 + n];
+        }
+        case MAP_EPI_ADD3:
+            return acc + a.aux0[(int64_t)m * a.ld_aux0 + n] + a.aux1[(int64_t)m * a.ld_aux1 + n] +
+                   (a.aux2 ? a.aux2[(int64_t)m * a.ld_aux2 + n] : 0.f);
         default: return acc;
     }
 }
@@ -71,6 +82,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const map_gemm_args a) {
         }
         __syncthreads();
     }
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -78,10 +90,23 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const map_gemm_args a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < a.N) a.C[(int64_t)m * a.ldc + n] = apply_epilogue(a, acc[i][j], m, n);
+            if (n < a.N) {
+                const float out = apply_epilogue(a, acc[i][j], m, n);
+                a.C[(int64_t)m * a.ldc + n] = out;
+                csum[j] += out;
+            }
+        }
+    }
+    if (a.colsum_out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < a.N) atomicAdd(a.colsum_out + n, csum[j]);
         }
     }
 }
+
+static_assert(sizeof(map_gemm_args) == 176, "map_gemm_args layout is part of the C ABI (mirrored by ctypes in _lib.py)");
 
 int validate_gemm_args(const map_gemm_args* g, const char* who) {
     MAP_REQUIRE(g != nullptr, "%s: null args", who);
@@ -97,6 +122,8 @@ int validate_gemm_args(const map_gemm_args* g, const char* who) {
         case MAP_EPI_MUL_RELUMASK:
         case MAP_EPI_ADD: MAP_REQUIRE(g->aux0, "%s: epilogue needs aux0", who); break;
         case MAP_EPI_ADD_MUL: MAP_REQUIRE(g->aux0 && g->aux1 && g->aux_out, "%s: EPI_ADD_MUL needs aux0, aux1, aux_out", who); break;
+        case MAP_EPI_CROSS_BWD: MAP_REQUIRE(g->aux1 && g->aux2 && g->acc_out, "%s: EPI_CROSS_BWD needs aux1 (X0), aux2 (U), acc_out", who); break;
+        case MAP_EPI_ADD3: MAP_REQUIRE(g->aux0 && g->aux1, "%s: EPI_ADD3 needs aux0 and aux1", who); break;
         default: set_error("%s: unknown epilogue %d", who, g->epilogue); return MAP_EUNSUPPORTED;
     }
     return MAP_OK;

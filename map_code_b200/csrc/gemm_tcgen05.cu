@@ -44,7 +44,22 @@ struct GemmParams {
     const float* aux0; int64_t ld_aux0;
     const float* aux1; int64_t ld_aux1;
     float* aux_out; int64_t ld_aux_out;
+    const float* aux2; int64_t ld_aux2;
+    float* acc_out; int64_t ld_acc_out;
+    int acc_accumulate;
+    float* colsum_out;
+    unsigned long long* trace;  // optional per-CTA phase timestamps (map_gemm_set_trace), nullptr in production
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// trace record of one CTA: 8 x u64 = {globaltimer at entry, clock at entry, clock after setup, clock when the first stage
+// landed (MMA warp), clock when the last MMA was issued, clock when the accumulator was complete (epilogue warp 2), clock at
+// the end of warp 2's epilogue, globaltimer at exit | smid << 48}
+constexpr int kTraceWords = 8;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,54 +155,177 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// ------------------------------------------------------------------------------------------------ epilogue on 4 columns
+// ------------------------------------------------------------------------------------------------ epilogue
+// Per warp and per chunk of W (32 or 16) accumulator columns: lane = (row-in-group rr, 4-column group cg); the warp walks its
+// 32 rows in ITERS steps of RPI rows, so that W/4 lanes cover W*4 contiguous bytes of one output row (full 128-byte lines at
+// W = 32).  Everything the fused epilogue READS from global memory (bias, aux0, aux1) is fetched into registers by
+// epi_prefetch BEFORE the accumulator chunk is pulled out of TMEM: the loads of all rows are in flight together (one L2
+// round trip per chunk instead of one per row), and chunk 0 is prefetched while the main loop is still running.
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_nc(const float* p) {  // read-only for the lifetime of the kernel, streamed once
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
-__device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int n, float4 acc) {
-    float4 out = acc;
-    switch (p.epilogue) {
-        case MAP_EPI_BIAS: {
-            const float4 b = ld4(p.bias + n);
-            out = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
-        } break;
-        case MAP_EPI_BIAS_RELU: {
-            const float4 b = ld4(p.bias + n);
-            out = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f));
-        } break;
-        case MAP_EPI_CROSS: {
-            const float4 b = ld4(p.bias + n);
-            const float4 xi = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
-            const float4 x0 = ld4(p.aux1 + (int64_t)m * p.ld_aux1 + n);
-            const float4 u = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
-            *reinterpret_cast<float4*>(p.aux_out + (int64_t)m * p.ld_aux_out + n) = u;
-            out = make_float4(fmaf(x0.x, u.x, xi.x), fmaf(x0.y, u.y, xi.y), fmaf(x0.z, u.z, xi.z), fmaf(x0.w, u.w, xi.w));
-        } break;
-        case MAP_EPI_MUL_RELUMASK: {
-            const float4 y = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
-            out = make_float4(y.x > 0.f ? acc.x : 0.f, y.y > 0.f ? acc.y : 0.f, y.z > 0.f ? acc.z : 0.f, y.w > 0.f ? acc.w : 0.f);
-        } break;
-        case MAP_EPI_ADD: {
-            const float4 r = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
-            out = make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
-        } break;
-        case MAP_EPI_ADD_MUL: {
-            const float4 r = ld4(p.aux0 + (int64_t)m * p.ld_aux0 + n);
-            const float4 x = ld4(p.aux1 + (int64_t)m * p.ld_aux1 + n);
-            const float4 s = make_float4(acc.x + r.x, acc.y + r.y, acc.z + r.z, acc.w + r.w);
-            *reinterpret_cast<float4*>(p.aux_out + (int64_t)m * p.ld_aux_out + n) = s;
-            out = make_float4(s.x * x.x, s.y * x.y, s.z * x.z, s.w * x.w);
-        } break;
-        default: break;
+struct EpiRegs {
+    float4 bias;
+    float4 a0[8];
+    float4 a1[8];
+    float4 a2[8];
+};
+
+// The epilogue kind is a template parameter of the kernel: a run-time switch in the innermost loop compiled to an indirect
+// branch through a constant-memory jump table per 16 output bytes and dominated the epilogue (r01d trace: ~9000 cycles).
+__host__ __device__ constexpr bool epi_has_bias(int e) { return e == MAP_EPI_BIAS || e == MAP_EPI_BIAS_RELU || e == MAP_EPI_CROSS; }
+__host__ __device__ constexpr bool epi_has_aux0(int e) { return e >= MAP_EPI_CROSS; }   // CROSS_BWD: optional (checked at run time)
+__host__ __device__ constexpr bool epi_has_aux1(int e) {
+    return e == MAP_EPI_CROSS || e == MAP_EPI_ADD_MUL || e == MAP_EPI_CROSS_BWD || e == MAP_EPI_ADD3;
+}
+__host__ __device__ constexpr bool epi_has_aux2(int e) { return e == MAP_EPI_CROSS_BWD || e == MAP_EPI_ADD3; }  // ADD3: optional
+__host__ __device__ constexpr bool epi_has_aux_out(int e) { return e == MAP_EPI_CROSS || e == MAP_EPI_ADD_MUL || e == MAP_EPI_CROSS_BWD; }
+// accumulator columns per epilogue chunk: three streamed operands per output only fit in registers at half width
+__host__ __device__ constexpr int epi_chunk_w(int e) { return (e == MAP_EPI_CROSS_BWD || e == MAP_EPI_ADD3) ? 16 : 32; }
+
+template <int EPI, int W>
+__device__ __forceinline__ void epi_prefetch(const GemmParams& p, int lane, int row_base, int ncol0, bool full_tile, EpiRegs& e) {
+    constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+    const int cg = lane % LPR, rr = lane / LPR;
+    const int n = ncol0 + 4 * cg;
+    const bool n_ok = full_tile || n < p.N;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (epi_has_bias(EPI)) e.bias = n_ok ? ld4_nc(p.bias + n) : z;
+    if (epi_has_aux0(EPI)) {
+        const bool have = (EPI != MAP_EPI_CROSS_BWD) || p.aux0 != nullptr;
+        const float* src = p.aux0 + (int64_t)(row_base + rr) * p.ld_aux0 + n;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+            e.a0[i] = (have && n_ok && (full_tile || row_base + i * RPI + rr < p.M)) ? ld4_nc(src) : z;
+            src += (int64_t)RPI * p.ld_aux0;
+        }
     }
-    float* dst = p.C + (int64_t)m * p.ldc + n;
-    if (p.split_k > 1) {  // partial sums of a K split: one 16-byte fp32 reduction into the pre-zeroed output (EPI_NONE only)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(out.x), "f"(out.y), "f"(out.z), "f"(out.w) : "memory");
-    } else {
-        *reinterpret_cast<float4*>(dst) = out;
+    if (epi_has_aux1(EPI)) {
+        const float* src = p.aux1 + (int64_t)(row_base + rr) * p.ld_aux1 + n;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+            e.a1[i] = (n_ok && (full_tile || row_base + i * RPI + rr < p.M)) ? ld4_nc(src) : z;
+            src += (int64_t)RPI * p.ld_aux1;
+        }
+    }
+    if (epi_has_aux2(EPI)) {
+        const bool have = (EPI != MAP_EPI_ADD3) || p.aux2 != nullptr;
+        const float* src = p.aux2 + (int64_t)(row_base + rr) * p.ld_aux2 + n;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+            e.a2[i] = (have && n_ok && (full_tile || row_base + i * RPI + rr < p.M)) ? ld4_nc(src) : z;
+            src += (int64_t)RPI * p.ld_aux2;
+        }
     }
 }
 
+__device__ __forceinline__ void red_add4(float* dst, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// returns the value written to C (for the fused column sums)
+template <int EPI, bool SPLIT>
+__device__ __forceinline__ float4 epilogue_store4(float* dst, float* aux_dst, float* acc_dst, bool acc_accumulate, float4 acc,
+                                                  const float4& b, const float4& x0_, const float4& x1_, const float4& x2_) {
+    float4 out = acc;
+    if (EPI == MAP_EPI_BIAS) {
+        out = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
+    } else if (EPI == MAP_EPI_BIAS_RELU) {
+        out = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f));
+    } else if (EPI == MAP_EPI_CROSS) {  // aux0 = Xi, aux1 = X0
+        const float4 u = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
+        *reinterpret_cast<float4*>(aux_dst) = u;
+        out = make_float4(fmaf(x1_.x, u.x, x0_.x), fmaf(x1_.y, u.y, x0_.y), fmaf(x1_.z, u.z, x0_.z), fmaf(x1_.w, u.w, x0_.w));
+    } else if (EPI == MAP_EPI_MUL_RELUMASK) {
+        out = make_float4(x0_.x > 0.f ? acc.x : 0.f, x0_.y > 0.f ? acc.y : 0.f, x0_.z > 0.f ? acc.z : 0.f, x0_.w > 0.f ? acc.w : 0.f);
+    } else if (EPI == MAP_EPI_ADD) {
+        out = make_float4(acc.x + x0_.x, acc.y + x0_.y, acc.z + x0_.z, acc.w + x0_.w);
+    } else if (EPI == MAP_EPI_ADD_MUL) {
+        const float4 sm = make_float4(acc.x + x0_.x, acc.y + x0_.y, acc.z + x0_.z, acc.w + x0_.w);
+        *reinterpret_cast<float4*>(aux_dst) = sm;
+        out = make_float4(sm.x * x1_.x, sm.y * x1_.y, sm.z * x1_.z, sm.w * x1_.w);
+    } else if (EPI == MAP_EPI_CROSS_BWD) {  // aux0 = G above (or 0), aux1 = X0, aux2 = U below
+        const float4 g = make_float4(acc.x + x0_.x, acc.y + x0_.y, acc.z + x0_.z, acc.w + x0_.w);
+        if (aux_dst != nullptr) *reinterpret_cast<float4*>(aux_dst) = g;
+        const float4 t = make_float4(g.x * x2_.x, g.y * x2_.y, g.z * x2_.z, g.w * x2_.w);
+        if (acc_accumulate) red_add4(acc_dst, t); else *reinterpret_cast<float4*>(acc_dst) = t;
+        out = make_float4(g.x * x1_.x, g.y * x1_.y, g.z * x1_.z, g.w * x1_.w);
+    } else if (EPI == MAP_EPI_ADD3) {
+        out = make_float4(acc.x + x0_.x + x1_.x + x2_.x, acc.y + x0_.y + x1_.y + x2_.y, acc.z + x0_.z + x1_.z + x2_.z,
+                          acc.w + x0_.w + x1_.w + x2_.w);
+    }
+    if (SPLIT) {  // partial sums of a K split: one 16-byte fp32 reduction into the pre-zeroed output (EPI_NONE only)
+        red_add4(dst, out);
+    } else {
+        *reinterpret_cast<float4*>(dst) = out;
+    }
+    return out;
+}
+
+constexpr int kStageLd = 36;  // floats per staging row (144 B: 16-byte aligned, conflict-free 128-bit phases)
+
+// one chunk: TMEM -> registers -> per-warp smem transpose -> fused epilogue on the prefetched operands -> global
+template <int EPI, bool SPLIT, int W>
+__device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, int lane, uint32_t taddr, int row_base, int ncol0,
+                                          bool full_tile, const EpiRegs& e) {
+    constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+    float v[W];
+    if (W == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
+#pragma unroll
+    for (int j = 0; j < W / 4; ++j)
+        *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int cg = lane % LPR, rr = lane / LPR;
+    const int n = ncol0 + 4 * cg;
+    float* dst = p.C + (int64_t)(row_base + rr) * p.ldc + n;
+    float* aux_dst = (epi_has_aux_out(EPI) && p.aux_out != nullptr) ? p.aux_out + (int64_t)(row_base + rr) * p.ld_aux_out + n : nullptr;
+    float* acc_dst = (EPI == MAP_EPI_CROSS_BWD) ? p.acc_out + (int64_t)(row_base + rr) * p.ld_acc_out + n : nullptr;
+    const bool acc_accumulate = p.acc_accumulate != 0;
+    const float* src = stg + rr * kStageLd + 4 * cg;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (full_tile) {  // interior tile (the common case): straight-line code, no per-row guards
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(src + i * RPI * kStageLd);
+            const float4 o = epilogue_store4<EPI, SPLIT>(dst, aux_dst, acc_dst, acc_accumulate, a, e.bias, e.a0[i], e.a1[i], e.a2[i]);
+            cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+            dst += (int64_t)RPI * p.ldc;
+            if (epi_has_aux_out(EPI) && aux_dst != nullptr) aux_dst += (int64_t)RPI * p.ld_aux_out;
+            if (EPI == MAP_EPI_CROSS_BWD) acc_dst += (int64_t)RPI * p.ld_acc_out;
+        }
+    } else {
+        const bool n_ok = n < p.N;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(src + i * RPI * kStageLd);
+            if (n_ok && row_base + i * RPI + rr < p.M) {
+                const float4 o = epilogue_store4<EPI, SPLIT>(dst, aux_dst, acc_dst, acc_accumulate, a, e.bias, e.a0[i], e.a1[i], e.a2[i]);
+                cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+            }
+            dst += (int64_t)RPI * p.ldc;
+            if (epi_has_aux_out(EPI) && aux_dst != nullptr) aux_dst += (int64_t)RPI * p.ld_aux_out;
+            if (EPI == MAP_EPI_CROSS_BWD) acc_dst += (int64_t)RPI * p.ld_acc_out;
+        }
+    }
+    if (!SPLIT && p.colsum_out != nullptr) {  // column sums of C over this warp's 32 rows -> one 16-byte reduction per column group
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+            cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+            cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+        }
+        if (lane < LPR && (full_tile || n < p.N)) red_add4(p.colsum_out + n, cs);
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
+template <int EPI, bool SPLIT>
 __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                          const __grid_constant__ CUtensorMap tmap_b,
                                                                          const GemmParams p) {
@@ -206,6 +344,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
     const int kb0 = blockIdx.z * p.num_k_blocks;
     int nkb = p.k_blocks_total - kb0;
     if (nkb > p.num_k_blocks) nkb = p.num_k_blocks;
+    unsigned long long* trace = nullptr;
+    if (p.trace != nullptr)
+        trace = p.trace + (size_t)kTraceWords * (blockIdx.x + gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z));
+    if (trace != nullptr && threadIdx.x == 0) {
+        trace[0] = globaltimer_ns();
+        trace[1] = (unsigned long long)clock64();
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -225,6 +370,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (trace != nullptr && threadIdx.x == 0) trace[2] = (unsigned long long)clock64();
 
     if (warp == 0) {
         // ===================== TMA producer (one elected lane) =====================
@@ -270,6 +416,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
                 const uint32_t round = (uint32_t)(i / p.stages);
                 mbar_wait(smem_u32(&full_bar[s]), round & 1u);
                 tcgen05_fence_after();
+                if (trace != nullptr && i == 0) trace[3] = (unsigned long long)clock64();
                 const uint32_t a_src = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
                 const uint32_t b_src = a_src + kATileBytes;
 #pragma unroll
@@ -281,6 +428,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
                 tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs have read it
             }
             tcgen05_commit(smem_u32(&tmem_full_bar));     // accumulator complete
+            if (trace != nullptr) trace[4] = (unsigned long long)clock64();
         }
     } else {
         // ===================== epilogue warps: TMEM -> registers -> smem transpose -> fused epilogue -> global =====
@@ -288,53 +436,35 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
         // different lines.  Each warp therefore transposes 32x32 chunks through a private staging tile (the stage ring is
         // idle once tmem_full has fired: one tile per CTA) so that 8 lanes cover 128 contiguous bytes of one output row.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        mbar_wait(smem_u32(&tmem_full_bar), 0);
-        tcgen05_fence_after();
-        constexpr int kStageLd = 36;            // floats per staging row (144 B: 16-byte aligned, conflict-free 128-bit phases)
         float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + q * (32 * kStageLd);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int row_base = m0 + q * 32;
+        EpiRegs e;
+        const bool full_tile = (m0 + kBlockM <= p.M) && (n0 + p.block_n <= p.N);
+        constexpr int CW = epi_chunk_w(EPI);
+        if (p.block_n >= CW) epi_prefetch<EPI, CW>(p, lane, row_base, n0, full_tile, e);
+        else epi_prefetch<EPI, 16>(p, lane, row_base, n0, full_tile, e);
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tcgen05_fence_after();
+        if (trace != nullptr && threadIdx.x == 64) trace[5] = (unsigned long long)clock64();
         int c = 0;
-        for (; c + 32 <= p.block_n; c += 32) {
-            float v[32];
-            tmem_ld_x32(lane_addr + (uint32_t)c, v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            __syncwarp();
-            const int cg = lane & 7, rr = lane >> 3;
-            const int n = n0 + c + 4 * cg;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 4 + rr;
-                const float4 a = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
-                const int m = row_base + r;
-                if (m < p.M && n < p.N) epilogue_store4(p, m, n, a);
-            }
-            __syncwarp();
+        for (; c + CW <= p.block_n; c += CW) {
+            epi_chunk<EPI, SPLIT, CW>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
+            if (c + 2 * CW <= p.block_n) epi_prefetch<EPI, CW>(p, lane, row_base, n0 + c + CW, full_tile, e);
+            else if (CW == 32 && c + CW < p.block_n) epi_prefetch<EPI, 16>(p, lane, row_base, n0 + c + CW, full_tile, e);
         }
-        if (c < p.block_n) {  // block_n % 32 == 16
-            float v[16];
-            tmem_ld_x16(lane_addr + (uint32_t)c, v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            __syncwarp();
-            const int cg = lane & 3, rr = lane >> 2;
-            const int n = n0 + c + 4 * cg;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + rr;
-                const float4 a = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
-                const int m = row_base + r;
-                if (m < p.M && n < p.N) epilogue_store4(p, m, n, a);
-            }
-            __syncwarp();
-        }
+        if (CW == 32 && c < p.block_n)  // block_n % 32 == 16
+            epi_chunk<EPI, SPLIT, 16>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
+        if (trace != nullptr && threadIdx.x == 64) trace[6] = (unsigned long long)clock64();
     }
 
     tcgen05_fence_before();
     __syncthreads();
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        trace[7] = (globaltimer_ns() & 0xFFFFFFFFFFFFull) | ((unsigned long long)smid << 48);
+    }
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -398,6 +528,9 @@ static int tf32_supported(const map_gemm_args* g, bool set_msg) {
     if (g->aux0 && (!aligned16(g->aux0) || g->ld_aux0 % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux0 alignment");
     if (g->aux1 && (!aligned16(g->aux1) || g->ld_aux1 % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux1 alignment");
     if (g->aux_out && (!aligned16(g->aux_out) || g->ld_aux_out % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux_out alignment");
+    if (g->aux2 && (!aligned16(g->aux2) || g->ld_aux2 % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: aux2 alignment");
+    if (g->acc_out && (!aligned16(g->acc_out) || g->ld_acc_out % 4 != 0)) UNSUP("map_gemm_tf32_tcgen05: acc_out alignment");
+    if (g->colsum_out && !aligned16(g->colsum_out)) UNSUP("map_gemm_tf32_tcgen05: colsum_out must be 16-byte aligned");
 #undef UNSUP
     return 1;
 }
@@ -437,7 +570,16 @@ static TileChoice choose_tiles(int M, int N, int K, bool mn_major_b, bool allow_
     return best;
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+static int64_t g_trace_records = 0;
+
 }  // namespace mapb
+
+extern "C" int map_gemm_set_trace(unsigned long long* dev_buf, int64_t capacity_records) {
+    mapb::g_trace_buf = dev_buf;
+    mapb::g_trace_records = dev_buf ? capacity_records : 0;
+    return MAP_OK;
+}
 
 extern "C" int map_gemm_tf32_supported(const map_gemm_args* args) {
     if (args == nullptr || args->M <= 0 || args->N <= 0 || args->K <= 0) return 0;
@@ -455,7 +597,7 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     p.M = g->M; p.N = g->N; p.K = g->K;
     p.trans_a = g->trans_a ? 1 : 0;
     p.trans_b = g->trans_b ? 1 : 0;
-    const TileChoice tc = choose_tiles(g->M, g->N, g->K, p.trans_b != 0, g->epilogue == MAP_EPI_NONE);
+    const TileChoice tc = choose_tiles(g->M, g->N, g->K, p.trans_b != 0, g->epilogue == MAP_EPI_NONE && g->colsum_out == nullptr);
     p.block_n = tc.block_n;
     if (const char* e = getenv("MAP_B200_BLOCK_N")) {  // tuning override (scripts/tune_gemm.py)
         int bn = atoi(e);
@@ -468,6 +610,10 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     p.aux0 = g->aux0; p.ld_aux0 = g->ld_aux0;
     p.aux1 = g->aux1; p.ld_aux1 = g->ld_aux1;
     p.aux_out = g->aux_out; p.ld_aux_out = g->ld_aux_out;
+    p.aux2 = g->aux2; p.ld_aux2 = g->ld_aux2;
+    p.acc_out = g->acc_out; p.ld_acc_out = g->ld_acc_out;
+    p.acc_accumulate = g->acc_accumulate;
+    p.colsum_out = g->colsum_out;
     p.b_tile_bytes = p.trans_b ? ((p.block_n + 31) / 32) * 4096 : p.block_n * 128;
     p.stage_bytes = (kATileBytes + p.b_tile_bytes + 1023) & ~1023;
     p.tmem_cols = 32;
@@ -507,14 +653,28 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     else rc = make_tmap(&tmap_b, g->B, g->N, g->K, g->ldb, kBlockK, true);                // [K rows][N contiguous]
     if (rc != MAP_OK) return rc;
 
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
+    constexpr int kNumKernels = 10;
+    static const KernelFn kernels[kNumKernels] = {
+        gemm_tf32_tcgen05_kernel<MAP_EPI_NONE, false>,     gemm_tf32_tcgen05_kernel<MAP_EPI_BIAS, false>,
+        gemm_tf32_tcgen05_kernel<MAP_EPI_BIAS_RELU, false>, gemm_tf32_tcgen05_kernel<MAP_EPI_CROSS, false>,
+        gemm_tf32_tcgen05_kernel<MAP_EPI_MUL_RELUMASK, false>, gemm_tf32_tcgen05_kernel<MAP_EPI_ADD, false>,
+        gemm_tf32_tcgen05_kernel<MAP_EPI_ADD_MUL, false>,  gemm_tf32_tcgen05_kernel<MAP_EPI_CROSS_BWD, false>,
+        gemm_tf32_tcgen05_kernel<MAP_EPI_ADD3, false>,     gemm_tf32_tcgen05_kernel<MAP_EPI_NONE, true>};
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048) != cudaSuccess) {
-            set_error("map_gemm_tf32_tcgen05: cannot raise dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
-            return MAP_ECUDA;
+        for (int i = 0; i < kNumKernels; ++i) {
+            if (cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048) != cudaSuccess) {
+                set_error("map_gemm_tf32_tcgen05: cannot raise dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+                return MAP_ECUDA;
+            }
         }
         attr_set = true;
     }
+    MAP_REQUIRE(g->epilogue >= MAP_EPI_NONE && g->epilogue <= MAP_EPI_ADD3, "map_gemm_tf32_tcgen05: unknown epilogue %d", g->epilogue);
+    MAP_REQUIRE(p.split_k == 1 || (g->epilogue == MAP_EPI_NONE && g->colsum_out == nullptr),
+                "map_gemm_tf32_tcgen05: split-K needs MAP_EPI_NONE without column sums");
+    const KernelFn kernel = p.split_k > 1 ? kernels[kNumKernels - 1] : kernels[g->epilogue];
     if (p.split_k > 1) {
         if (cudaMemset2DAsync(g->C, (size_t)g->ldc * sizeof(float), 0, (size_t)g->N * sizeof(float), (size_t)g->M, st) != cudaSuccess) {
             set_error("map_gemm_tf32_tcgen05: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -522,6 +682,7 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
         }
     }
     dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)p.split_k);
-    gemm_tf32_tcgen05_kernel<<<grid, kGemmThreads, smem_bytes, st>>>(tmap_a, tmap_b, p);
+    p.trace = ((int64_t)n_tiles * m_tiles * p.split_k <= g_trace_records) ? g_trace_buf : nullptr;
+    kernel<<<grid, kGemmThreads, smem_bytes, st>>>(tmap_a, tmap_b, p);
     return check_launch("map_gemm_tf32_tcgen05");
 }

@@ -181,7 +181,10 @@ class FusedStep:
             if p.requires_grad and not hasattr(p, "_map_table_grad"):
                 self.dense[n] = p
         # one flat gradient buffer (a single all-reduce in data-parallel runs); per-parameter views keep 16-byte alignment
-        offs, tot, padded = {}, 0, {}
+        # 1-D parameters (biases) come first: their gradients are accumulated by fused column sums in GEMM epilogues
+        # (fp32 reductions), so that prefix is zeroed with one small memset at the start of every step.
+        self.dense = dict(sorted(self.dense.items(), key=lambda kv: 0 if kv[1].dim() == 1 else 1))
+        offs, tot, padded, n_bias_floats = {}, 0, {}, 0
         for n, p in self.dense.items():
             offs[n] = tot
             if n in self._pad_rows:
@@ -191,7 +194,10 @@ class FusedStep:
             else:
                 padded[n] = p.numel()
             tot += (padded[n] + 3) // 4 * 4
+            if p.dim() == 1:
+                n_bias_floats = tot
         self.grad_flat = torch.zeros(tot, **f32)
+        self.bias_grad_flat = self.grad_flat[:n_bias_floats]
         self.grads, self.grads_padded, self.opt_param = {}, {}, {}
         for n, p in self.dense.items():
             flat = self.grad_flat[offs[n]:offs[n] + padded[n]]
@@ -306,9 +312,10 @@ class FusedStep:
             ev.record(self.streams[name])
             torch.cuda.current_stream().wait_event(ev)
 
-    def _wgrad(self, dZ, X_in, layer_name, M, N, K):
+    def _wgrad(self, dZ, X_in, layer_name, M, N, K, bias_done=False):
         """dW = dZ^T X, db = colsum(dZ) for a Linear with input X_in [M,K] and pre-activation gradient dZ [M,N].
-        Issued on the 'dw' stream: weight gradients are off the critical path (only the optimizer waits for them)."""
+        Issued on the 'dw' stream: weight gradients are off the critical path (only the optimizer waits for them).
+        bias_done: the GEMM that produced dZ already accumulated its column sums into the bias gradient (colsum_out)."""
         self._fork("dw")
         with self._on("dw"):
             wname = layer_name + ".weight"
@@ -316,7 +323,8 @@ class FusedStep:
                 self._gemm(dZ, self.final, self.grads_padded[wname], N, self.ld_final, M, trans_a=True, trans_b=True)
             else:
                 self._gemm(dZ, X_in, self.grads[wname], N, K, M, trans_a=True, trans_b=True)
-            ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
+            if not bias_done:
+                ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
 
     # ------------------------------------------------------------------------------------------------ the step
     def _draw_and_mask(self):
@@ -348,8 +356,8 @@ class FusedStep:
         embedding dedup sort (K2a) and, for MFP, the alias draw of the NCE noise (K5)."""
         self._fork("tab")
         with self._on("tab"):
+            self._draw_noise()   # first: the NCE head waits for the noise, nothing waits for the sort until the backward
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
-            self._draw_noise()
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
 
     def _draw_noise(self):
@@ -404,37 +412,45 @@ class FusedStep:
         nc, nh = len(self.cross), len(self.mlp)
         pref_c = "cross_net.cross_layers"
         pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
-        # ---- MLP tower (stream 'mlp'): the gradient through each ReLU is fused into the dgrad GEMM's epilogue
+        # ---- MLP tower (stream 'mlp'): the gradient through each ReLU and the bias gradient (column sums of dZ) are fused into
+        # the dgrad GEMM's epilogue
         if nh:
             self._fork("mlp")
             with self._on("mlp"):
                 dZ = self.dZ[nh - 1]
                 self._gemm(dHead, head_W[:, self.mlp_off:self.mlp_off + H], dZ, B, H, n_head, trans_b=True,
-                           epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out)
+                           epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out, colsum_out=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"])
                 for i in range(nh - 1, -1, -1):
                     layer = self.mlp[i]
                     x_in = self.X0 if i == 0 else self.Hs[i - 1]
                     k_in = in_dim if i == 0 else H
-                    self._wgrad(dZ, x_in, f"{pref_m}.{3 * i}", B, H, k_in)
+                    self._wgrad(dZ, x_in, f"{pref_m}.{3 * i}", B, H, k_in, bias_done=True)
                     if i > 0:
                         self._gemm(dZ, layer.weight.data, self.dZ[i - 1], B, k_in, H, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK,
-                                   aux0=self.Hs[i - 1])
+                                   aux0=self.Hs[i - 1], colsum_out=self.grads[f"{pref_m}.{3 * (i - 1)}.bias"])
                         dZ = self.dZ[i - 1]
                     else:
                         self._gemm(dZ, layer.weight.data, self.dX0_mlp, B, k_in, H, trans_b=True)
-        # ---- CrossNet (main stream): G = d(loss)/d(X_{i+1});  dU = G*X0, dX0 += G*U_i, dXi = G + dU W_i  (autograd of layers.py:200)
+        # ---- CrossNet (main stream), autograd of layers.py:200 with every elementwise stage inside a GEMM epilogue:
+        #   G_{i} = d(loss)/d(X_i);  dU_i = G_{i+1} * X0;  dX0 += G_{i+1} * U_i;  G_i = G_{i+1} + dU_i W_i;  db_i = colsum(dU_i)
+        # The GEMM that produces G_{i+1} (the head dgrad for i = nc-1, the dgrad of layer i+1 otherwise) also writes dU_i,
+        # accumulates dX0 and db_i (MAP_EPI_CROSS_BWD); the last one adds everything into dE (MAP_EPI_ADD3).
         if nc:
-            G = self.Gc[nc]
-            self._gemm(dHead, head_W[:, self.cross_off:self.cross_off + in_dim], G, B, in_dim, n_head, trans_b=True)
+            self._gemm(dHead, head_W[:, self.cross_off:self.cross_off + in_dim], self.dUs[nc - 1], B, in_dim, n_head, trans_b=True,
+                       epilogue=_lib.EPI_CROSS_BWD, aux0=None, aux1=self.X0, aux2=self.U[nc - 1], aux_out=self.Gc[nc],
+                       acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"])
             for i in range(nc - 1, -1, -1):
                 layer = self.cross[i]
-                ops.cross_bwd_pre(G, self.X0, self.U[i], self.dUs[i], self.dX0_acc, accumulate=(i != nc - 1))
-                self._wgrad(self.dUs[i], self.Xc[i], f"{pref_c}.{i}", B, in_dim, in_dim)
-                self._gemm(self.dUs[i], layer.weight.data, self.Gc[i], B, in_dim, in_dim, trans_b=True, epilogue=_lib.EPI_ADD, aux0=G)
-                G = self.Gc[i]
-            if nh:
-                self._join("mlp")
-            ops.add3(G, self.dX0_acc, self.dX0_mlp if nh else None, self.dE)
+                self._wgrad(self.dUs[i], self.Xc[i], f"{pref_c}.{i}", B, in_dim, in_dim, bias_done=True)
+                if i > 0:
+                    self._gemm(self.dUs[i], layer.weight.data, self.dUs[i - 1], B, in_dim, in_dim, trans_b=True,
+                               epilogue=_lib.EPI_CROSS_BWD, aux0=self.Gc[i + 1], aux1=self.X0, aux2=self.U[i - 1], aux_out=self.Gc[i],
+                               acc_out=self.dX0_acc, acc_accumulate=True, colsum_out=self.grads[f"{pref_c}.{i - 1}.bias"])
+                else:
+                    if nh:
+                        self._join("mlp")
+                    self._gemm(self.dUs[0], layer.weight.data, self.dE, B, in_dim, in_dim, trans_b=True, epilogue=_lib.EPI_ADD3,
+                               aux0=self.Gc[1], aux1=self.dX0_acc, aux2=self.dX0_mlp if nh else None)
         else:
             self._join("mlp")
             ops.copy2d(self.dX0_mlp, self.dE)
@@ -493,8 +509,9 @@ class FusedStep:
         with self._on("dw"):
             self._gemm(self.d_logits_p, self.rfd_h, self.grads_padded["pred_rfd.2.weight"], Fp, F * P, B, trans_a=True, trans_b=True)
             ops.colsum(self.d_logits_p, out=self.grads_padded["pred_rfd.2.bias"].view(-1), ws=self.colsum_ws)
-        self._gemm(self.d_logits_p, self.W2p, self.d_h, B, F * P, Fp, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h)
-        self._wgrad(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim)
+        self._gemm(self.d_logits_p, self.W2p, self.d_h, B, F * P, Fp, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h,
+                   colsum_out=self.grads["pred_rfd.0.bias"])
+        self._wgrad(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim, bias_done=True)
         self._backward_backbone(l0.weight.data, self.d_h, F * P)
 
     def _head_ctr(self):
@@ -520,6 +537,8 @@ class FusedStep:
     def forward_backward(self):
         """mask -> forward -> backward; gradients land in self.grads / self.tables[*].grad.  On return every side stream has
         been joined back into the current stream."""
+        if self.bias_grad_flat.numel():
+            self.bias_grad_flat.zero_()
         self.ids_cur = self._draw_and_mask()
         self._forward_backbone(self.ids_cur)
         if self.mode == "MFP":

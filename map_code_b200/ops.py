@@ -48,7 +48,7 @@ def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tenso
         out = torch.empty(*ids.shape, D, dtype=torch.float32, device=table.device)
     if ids.numel() == 0:
         return out
-    if _lib.PROFILE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
         _lib.CURRENT_TAG = ("gather", ids.numel(), D)
     call("map_emb_gather_f32", table.data_ptr(), V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), _ptr(oob_flag), _stream())
     return out
@@ -79,7 +79,7 @@ class DedupPlan:
                     group: int = 1, out: Optional[torch.Tensor] = None, scalar_out: Optional[torch.Tensor] = None):
         if out is None:
             out = torch.empty(self.n, D, dtype=torch.float32, device=rows.device)
-        if _lib.PROFILE is not None:
+        if _lib.PROFILE is not None or _lib.TIMELINE is not None:
             _lib.CURRENT_TAG = ("segred", self.n, D)
         call("map_segment_reduce_rows", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
              self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, out.data_ptr(),
@@ -123,7 +123,7 @@ def adamw_multi_tensor(table: torch.Tensor, n: int, max_elems: int, hyper: torch
 
 def adamw_sparse_rows(table, m, v, plan: DedupPlan, grad_compact, hyper, weight_decay: float):
     D = table.shape[1]
-    if _lib.PROFILE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
         _lib.CURRENT_TAG = ("sparse_adamw", plan.n, D)
     call("map_adamw_sparse_rows", table.data_ptr(), m.data_ptr(), v.data_ptr(), D, plan.uniq.data_ptr(), grad_compact.data_ptr(),
          plan.n_unique.data_ptr(), plan.n, hyper.data_ptr(), float(weight_decay), _stream())
@@ -188,8 +188,8 @@ def alias_build(probs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """HOST function of the library (native Vose builder, bit-identical to the reference's Python loop)."""
     p = probs.detach().to("cpu", torch.float32).contiguous()
     V = p.numel()
-    prob = torch.empty(V, dtype=torch.float32)
-    alias = torch.empty(V, dtype=torch.int64)
+    prob = torch.empty(V, dtype=torch.float32, device="cpu")    # explicit: a torch.device(...) context may be active
+    alias = torch.empty(V, dtype=torch.int64, device="cpu")
     call("map_alias_build", p.data_ptr(), V, prob.data_ptr(), alias.data_ptr())
     return prob, alias
 
@@ -228,7 +228,7 @@ def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: st
         d_input = torch.empty(N, P, dtype=torch.float32, device=dev)
     if grad_scale is None:
         grad_scale = 1.0 / max(N, 1)
-    if _lib.PROFILE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
         _lib.CURRENT_TAG = ("nce", N, K, P)
     call("map_nce_fwd", inp.data_ptr(), N, P, K, target.data_ptr(), noise.data_ptr(), emb.data_ptr(), bias.data_ptr(),
          logq.data_ptr(), emb.shape[0], float(norm_term), _lib.NCE_LOSS[loss_type], float(grad_scale), logits.data_ptr(),
@@ -310,7 +310,8 @@ def _ld(t: torch.Tensor) -> int:
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
-         epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, backend: Optional[str] = None):
+         epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, aux2=None, acc_out=None,
+         acc_accumulate: bool = False, colsum_out=None, backend: Optional[str] = None):
     """acc[m,n] = sum_k A[m,k]*B[n,k] with storage transposes; see include/map_b200.h.  Operands are 2-D row-major views
     (row stride = leading dimension, so column slices of wider buffers work)."""
     g = GemmArgs()
@@ -323,9 +324,13 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, 
     g.aux0, g.ld_aux0 = (aux0.data_ptr(), _ld(aux0)) if aux0 is not None else (None, 0)
     g.aux1, g.ld_aux1 = (aux1.data_ptr(), _ld(aux1)) if aux1 is not None else (None, 0)
     g.aux_out, g.ld_aux_out = (aux_out.data_ptr(), _ld(aux_out)) if aux_out is not None else (None, 0)
+    g.aux2, g.ld_aux2 = (aux2.data_ptr(), _ld(aux2)) if aux2 is not None else (None, 0)
+    g.acc_out, g.ld_acc_out = (acc_out.data_ptr(), _ld(acc_out)) if acc_out is not None else (None, 0)
+    g.acc_accumulate = int(bool(acc_accumulate))
+    g.colsum_out = _ptr(colsum_out)
     backend = backend or gemm_backend()
     lib = _lib.load()
-    if _lib.PROFILE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
         _lib.CURRENT_TAG = ("gemm", M, N, K, int(trans_a), int(trans_b), int(epilogue))
     if backend == "tcgen05" and lib.map_gemm_tf32_supported(C.byref(g)):
         call("map_gemm_tf32_tcgen05", C.byref(g), _stream())

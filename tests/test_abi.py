@@ -36,7 +36,7 @@ def test_header_declares_and_library_exports_every_symbol(lib):
 
 def test_struct_layouts_match_header(lib):
     import ctypes as C
-    assert C.sizeof(lib.GemmArgs) == 24 + 8 * 13  # 6 int32 + 13 pointer/int64 fields
+    assert C.sizeof(lib.GemmArgs) == 24 + 8 * 13 + 8 * 4 + 8 + 8  # + aux2/acc_out (+ld), acc_accumulate/reserved, colsum_out
     assert C.sizeof(lib.AdamwTensor) == 64
 
 
@@ -75,3 +75,15 @@ def test_alias_build_large_matches_oracle_c():
     recon.index_add_(0, a1, 1.0 - p1.double())
     err = (recon / probs.numel() - probs.double()).abs()
     assert err.max() < 1e-7 and err.sum() < 1e-3  # float32 Vose round-off, inherited bit-for-bit from the reference's loop
+
+
+def test_alias_build_ignores_default_device_context():
+    """bench.py builds the model under `with torch.device(cuda)`; the HOST table builder must still allocate on the CPU
+    (a device allocation there handed a device pointer to host code: SIGSEGV at 2 GPUs, round 1)."""
+    import torch
+    from map_code_b200 import ops
+    probs = torch.arange(1, 17, dtype=torch.float32) / 136.0
+    with torch.device("meta"):
+        prob, alias = ops.alias_build(probs)
+    assert prob.device.type == "cpu" and alias.device.type == "cpu"
+    assert alias.tolist() == [11, 13, 14, 14, 15, 15, 15, 15, 0, 8, 9, 10, 11, 12, 13, 14]  # SURVEY.md §8c KAT

@@ -442,48 +442,69 @@ def _gemm_case(gen, M, N, K, ta, tb):
     return A, B, As, Bs
 
 
-def _epilogue_ref(epi, acc, bias, aux0, aux1):
+def _epilogue_ref(epi, acc, bias, aux0, aux1, aux2=None, acc_prev=None):
+    """returns (C, aux_out, acc_out) in float64"""
     from map_code_b200 import _lib as L
     if epi == L.EPI_NONE:
-        return acc, None
+        return acc, None, None
     if epi == L.EPI_BIAS:
-        return acc + bias, None
+        return acc + bias, None, None
     if epi == L.EPI_BIAS_RELU:
-        return torch.relu(acc + bias), None
+        return torch.relu(acc + bias), None, None
     if epi == L.EPI_CROSS:
         u = acc + bias
-        return aux0 + aux1 * u, u
+        return aux0 + aux1 * u, u, None
     if epi == L.EPI_MUL_RELUMASK:
-        return acc * (aux0 > 0), None
+        return acc * (aux0 > 0), None, None
     if epi == L.EPI_ADD:
-        return acc + aux0, None
+        return acc + aux0, None, None
     if epi == L.EPI_ADD_MUL:
         s = acc + aux0
-        return s * aux1, s
+        return s * aux1, s, None
+    if epi == L.EPI_CROSS_BWD:   # G = acc + aux0 ; C = G * aux1 ; acc_out (+)= G * aux2
+        g = acc + aux0
+        return g * aux1, g, (acc_prev if acc_prev is not None else 0) + g * aux2
+    if epi == L.EPI_ADD3:
+        return acc + aux0 + aux1 + aux2, None, None
     raise AssertionError
 
 
-def _run_gemm(ops, backend, M, N, K, ta, tb, epi, seed=0):
+def _run_gemm(ops, backend, M, N, K, ta, tb, epi, seed=0, accumulate=False, colsum=True):
+    from map_code_b200 import _lib as L
     gen = torch.Generator().manual_seed(seed)
     A, B, As, Bs = _gemm_case(gen, M, N, K, ta, tb)
     bias = torch.randn(N, generator=gen)
     aux0 = torch.randn(M, N, generator=gen)
     aux1 = torch.randn(M, N, generator=gen)
+    aux2 = torch.randn(M, N, generator=gen)
+    acc_prev = torch.randn(M, N, generator=gen) if accumulate else None
     acc = (A.double() @ B.double().t())
-    want, want_aux = _epilogue_ref(epi, acc, bias.double(), aux0.double(), aux1.double())
+    want, want_aux, want_acc = _epilogue_ref(epi, acc, bias.double(), aux0.double(), aux1.double(), aux2.double(),
+                                             acc_prev.double() if accumulate else None)
     Cd = torch.full((M, N), float("nan"), device="cuda")
     auxo = torch.full((M, N), float("nan"), device="cuda")
+    acco = dev(acc_prev) if accumulate else torch.full((M, N), float("nan"), device="cuda")
+    use_colsum = colsum and N % 4 == 0
+    cs = torch.full((N,), 0.5, device="cuda") if use_colsum else None   # accumulates ON TOP of the caller's content
     ops.gemm(dev(As), dev(Bs), Cd, M, N, K, trans_a=ta, trans_b=tb, epilogue=epi, bias=dev(bias), aux0=dev(aux0), aux1=dev(aux1),
-             aux_out=auxo, backend=backend)
+             aux_out=auxo, aux2=dev(aux2), acc_out=acco if epi == L.EPI_CROSS_BWD else None, acc_accumulate=accumulate,
+             colsum_out=cs, backend=backend)
     torch.cuda.synchronize()
+    if use_colsum:  # fused bias gradient: column sums of what was written to C
+        got_cs = cs.cpu().double() - 0.5
+        want_cs = Cd.cpu().double().sum(0)
+        assert (got_cs - want_cs).abs().max() < 1e-3 * max(1.0, float(want_cs.abs().max())), "fused column sums"
+    if want_acc is not None:
+        ga = acco.cpu().double()
+        assert ((ga - want_acc).norm() / want_acc.norm()) < 2e-3, "acc_out"
     return Cd.cpu().double(), want, (auxo.cpu().double() if want_aux is not None else None), want_aux, acc
 
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(64, 64, 16), (130, 39, 1248), (257, 1, 77), (100, 100, 100)])
 def test_gemm_simt_exact_fp32(ops, M, N, K, ta, tb):
-    for epi in range(7):
-        got, want, ga, wa, _ = _run_gemm(ops, "simt", M, N, K, ta, tb, epi, seed=epi)
+    for epi in range(9):
+        got, want, ga, wa, _ = _run_gemm(ops, "simt", M, N, K, ta, tb, epi, seed=epi, accumulate=(epi == 7 and M % 2 == 0))
         torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * math.sqrt(K))
         if wa is not None:
             torch.testing.assert_close(ga, wa, rtol=1e-4, atol=1e-4 * math.sqrt(K))
@@ -503,13 +524,16 @@ def _check_tf32(got, want, K, scale=1.0):
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 128), (256, 256, 96), (4096, 624, 624), (300, 1000, 1000),
                                    (1000, 624, 4096), (4096, 1248, 1624), (129, 16, 40), (4096, 1624, 1248)])
 def test_gemm_tcgen05_tf32(ops, M, N, K, ta, tb):
-    got, want, _, _, _ = _run_gemm(ops, "tcgen05", M, N, K, ta, tb, 0)
+    got, want, _, _, _ = _run_gemm(ops, "tcgen05", M, N, K, ta, tb, 0, colsum=False)   # EPI_NONE may pick split-K
     _check_tf32(got, want, K)
 
 
-@pytest.mark.parametrize("epi", [1, 2, 3, 4, 5, 6])
-def test_gemm_tcgen05_epilogues(ops, epi):
-    got, want, ga, wa, acc = _run_gemm(ops, "tcgen05", 515, 624, 624, False, epi in (4, 5, 6), epi, seed=epi)
+@pytest.mark.parametrize("accumulate", [False, True])
+@pytest.mark.parametrize("epi", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_gemm_tcgen05_epilogues(ops, epi, accumulate):
+    if accumulate and epi != 7:
+        pytest.skip("acc_accumulate only exists for MAP_EPI_CROSS_BWD")
+    got, want, ga, wa, acc = _run_gemm(ops, "tcgen05", 515, 624, 624, False, epi in (4, 5, 6, 7, 8), epi, seed=epi, accumulate=accumulate)
     # compare through the accumulator error only: the epilogue itself is exact fp32
     assert torch.isfinite(got).all()
     err = (got - want).abs().max()
