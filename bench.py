@@ -445,8 +445,8 @@ def main_ours(args):
                     "traffic": None, "note": f"peak = {pk['src']} copy bandwidth"}
 
     _stage('profiling pass done')
-    if args.timeline and world == 1 and not args.no_graph:
-        write_timeline(eng, batch, args.timeline)
+    if args.timeline and not args.no_graph:   # every rank re-captures and replays (collectives), rank 0 writes the file
+        write_timeline(eng, batch, args.timeline if rank == 0 else os.devnull)
     if rank != 0:
         _shutdown(world)
         return
@@ -465,7 +465,7 @@ def main_ours(args):
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core multiplies, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": workload_name(args.task, args.batch, world), "global_batch": Bg, "optimizer_mode": args.optimizer_mode,
                    "cuda_graph": not args.no_graph, "l2": "inputs larger than L2: tables + optimizer state (0.9 GB at c2/c4, >100 GB at c5) touched at random, a new batch every step; no explicit flush",
-                   "parallelism": "single GPU" if world == 1 else f"row-sharded tables (id mod {world}) + NCCL all-to-all; dense params replicated + allreduce"},
+                   "parallelism": "single GPU" if world == 1 else f"tables row-sharded by id mod {world} in NVLink peer memory (remote rows read directly by the gather / NCE kernels, owners pull gradients); dense params replicated + NCCL all-reduce"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": args.batch * n_fields * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": (n_launch * args.steps) if n_launch else None, "launches_per_step": n_launch,

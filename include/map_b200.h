@@ -69,6 +69,20 @@ int map_dedup_ids(const int64_t* ids, int64_t n_ids, int key_bits, int64_t* uniq
 int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
                             const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
                             int64_t n_ids, float* grad_compact, float* scalar_out, map_stream_t stream);
+/* Extended forms used by the owner-side merge of the row-sharded tables (map_owned_compact below):
+ *   n_dev      (may be NULL) device int32: only the first min(n_ids, *n_dev) keys exist (grids are sized for n_ids);
+ *   seg_shift  keys that agree above bit `seg_shift` form ONE segment and uniq_ids = key >> seg_shift (the low bits only
+ *              fix the order of the occurrences, e.g. by source rank);
+ *   occ_map    (may be NULL) occurrence o of the sorted list refers to row code occ_map[o] instead of o;
+ *   row_ptrs   (may be NULL) host array of n_peers device pointers: row code c lives at row_ptrs[c / rows_per_peer] + (c % rows_per_peer) * ld_rows
+ *              (peer memory mapped with map_p2p_open; the loads travel over NVLink). */
+int map_dedup_ids_ex(const int64_t* ids, int64_t n_ids, const int32_t* n_dev, int key_bits, int seg_shift, int64_t* uniq_ids,
+                     int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,
+                     map_stream_t stream);
+int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
+                               const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique, int64_t n_ids,
+                               const int32_t* n_dev, const int32_t* occ_map, const float* const* row_ptrs, int n_peers,
+                               int64_t rows_per_peer, float* grad_compact, float* scalar_out, map_stream_t stream);
 /* dense[uniq_ids[u], :] = grad_compact[u, :]  (dense must be zero-filled by the caller): the `.grad` the reference sees */
 int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const int32_t* n_unique, int64_t max_unique,
                      int D, float* dense, map_stream_t stream);
@@ -256,6 +270,30 @@ int map_nce_loss_from_scores(const float* scores, const int64_t* idx, int64_t N,
 /* d_q[n,:] = sum over owned j of dz[n,j] * emb_shard[idx[n,j]/R, :]   — summed over ranks this is d(loss)/d(query) */
 int map_nce_dinput_owned(const float* dz, int64_t N, int P, int K1, const int64_t* idx, const float* emb_shard, int R,
                          int rank, float* d_q, map_stream_t stream);
+
+/* ------------------------------------------------------------------ K13b row-sharded tables over NVLink peer memory
+ * (the default multi-GPU path; the collective-based owner kernels above remain as the portable variant).
+ * Every rank allocates its shards / compact gradients with map_p2p_alloc and maps the other ranks' buffers with
+ * map_p2p_open (CUDA IPC, lazy peer access); kernels then take a HOST array of R device base pointers (R <= 8). */
+int map_p2p_alloc(size_t bytes, void** ptr, unsigned char* handle64);  /* cudaMalloc (zero-filled) + 64-byte IPC handle */
+int map_p2p_open(const unsigned char* handle64, void** ptr);           /* another process' allocation -> local address */
+int map_p2p_close(void* ptr);
+int map_p2p_free(void* ptr);
+/* out[i,:] = shard[ids[i] % R][ids[i] / R, :] — replaces nn.Embedding forward (code/layers.py:98) on a sharded table: the
+ * lookup itself is the exchange (remote rows are read over NVLink), there is no id / row all-to-all. */
+int map_emb_gather_sharded_f32(const void* const* shard_ptrs, int R, int64_t V, int D, const int64_t* ids, int64_t n_ids,
+                               float* out, int32_t* oob_flag, map_stream_t stream);
+/* map_nce_fwd on row-sharded output tables (emb [V,P], bias [V,1] split by id % R); logprob_noise is replicated. */
+int map_nce_fwd_sharded(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
+                        const void* const* emb_shards, const void* const* bias_shards, int R, const float* logprob_noise,
+                        float norm_term, int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos,
+                        float* dz, float* d_input, int32_t* acc_count, map_stream_t stream);
+/* Owner-side merge, step 1: scan the R per-rank unique-id lists (uniq_ptrs[s] = int64 ids ascending, n_unique_ptrs[s] =
+ * device int32 count) and append the entries this rank owns: keys[k] = ((id / R) << ceil_log2(R)) | s, src[k] = s * cap + u,
+ * *n_out = number of entries.  Then map_dedup_ids_ex(keys, R * cap, n_out, key_bits, ceil_log2(R), ...) and
+ * map_segment_reduce_rows_ex(..., occ_map = src, row_ptrs = the ranks' compact gradients, rows_per_peer = cap). */
+int map_owned_compact(const void* const* uniq_ptrs, const void* const* n_unique_ptrs, int R, int rank, int64_t cap, int64_t* keys,
+                      int32_t* src, int32_t* n_out, map_stream_t stream);
 
 /* column sums: out[n] = sum_m X[m,n]  (bias gradients).  deterministic two-stage. */
 int map_colsum_f32(const float* X, int64_t ldx, int64_t M, int N, float* out, void* workspace, size_t workspace_bytes,

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "map_dedup_workspace_bytes": (_sz, [_l]),
     "map_dedup_ids": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "map_segment_reduce_rows": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _l, _p, _p, _p]),
+    "map_dedup_ids_ex": (_i, [_p, _l, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "map_segment_reduce_rows_ex": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _l, _p, _p, _p, _i, _l, _p, _p, _p]),
     "map_scatter_rows": (_i, [_p, _p, _p, _l, _i, _p, _p]),
     "map_adamw_hyper_step": (_i, [_p, _p, _d, _d, _d, _d, _i, _l, _l, _p]),
     "map_adamw_hyper_set": (_i, [_p, _d, _d, _d, _d, _l, _p]),
@@ -86,6 +88,13 @@ PROTOTYPES = {
     "map_nce_scores_owned": (_i, [_p, _l, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
     "map_nce_loss_from_scores": (_i, [_p, _p, _l, _i, _p, _f, _i, _f, _p, _p, _p, _p, _p]),
     "map_nce_dinput_owned": (_i, [_p, _l, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "map_p2p_alloc": (_i, [_sz, C.POINTER(C.c_void_p), _p]),
+    "map_p2p_open": (_i, [_p, C.POINTER(C.c_void_p)]),
+    "map_p2p_close": (_i, [_p]),
+    "map_p2p_free": (_i, [_p]),
+    "map_emb_gather_sharded_f32": (_i, [_p, _i, _l, _i, _p, _l, _p, _p, _p]),
+    "map_nce_fwd_sharded": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _i, _p, _f, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "map_owned_compact": (_i, [_p, _p, _i, _i, _l, _p, _p, _p, _p]),
     "map_colsum_f32": (_i, [_p, _l, _l, _i, _p, _p, _sz, _p]),
     "map_colsum_workspace_bytes": (_sz, [_l, _i]),
     "map_cross_bwd_pre": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _i, _p, _p, _p]),
@@ -131,6 +140,8 @@ def last_error() -> str:
 # number of kernels one entry point launches (for the `gpu_launches` figure of bench.py)
 KERNELS_PER_CALL = {
     "map_dedup_ids": lambda args: 1 + 3 * ((int(args[2]) + 7) // 8) + 3,   # prep + (hist, scan, scatter) per pass + heads (3)
+    "map_dedup_ids_ex": lambda args: 1 + 3 * ((int(args[3]) + 7) // 8) + 3,
+    "map_segment_reduce_rows_ex": 2, "map_p2p_alloc": 0, "map_p2p_open": 0, "map_p2p_close": 0, "map_p2p_free": 0,
     "map_segment_reduce_rows": 2, "map_reduce_sum_f32": 2, "map_bce_logits_fwd": 2, "map_colsum_f32": 2,
     "map_alias_build": 0,
 }
@@ -138,7 +149,19 @@ PROFILE = None        # set to a list: every call is bracketed by CUDA events ->
 CURRENT_TAG = None    # free-form shape tag set by ops.* just before a call (e.g. "4096x1000x624 tn")
 LAUNCHES = None       # set to a dict: name -> number of kernels launched
 TIMELINE = None       # set to dict(buf=<device int64 tensor>, ops=[]): a timestamp marker follows every call on its stream
-HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace"}
+HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace", "map_p2p_alloc", "map_p2p_open", "map_p2p_close", "map_p2p_free"}
+
+
+def mark(name: str, tag=None, stream: int = None):
+    """Timeline marker after a non-library operation (e.g. an NCCL collective issued through torch.distributed)."""
+    if TIMELINE is None:
+        return
+    import torch
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    i = len(TIMELINE["ops"])
+    if i < TIMELINE["buf"].numel():
+        TIMELINE["ops"].append((name, tag, int(st or 0)))
+        load().map_timestamp_ns(TIMELINE["buf"].data_ptr() + 8 * i, st)
 
 
 def call(name: str, *args):
@@ -160,7 +183,7 @@ def call(name: str, *args):
         rc = getattr(load(), name)(*args)
     if TIMELINE is not None and name not in HOST_FUNCS and rc == MAP_OK:
         i = len(TIMELINE["ops"])
-        if 8 * (i + 1) <= TIMELINE["buf"].numel() * 8:
+        if i < TIMELINE["buf"].numel():
             TIMELINE["ops"].append((name, CURRENT_TAG if PROFILE is None else None, int(args[-1] or 0)))
             load().map_timestamp_ns(TIMELINE["buf"].data_ptr() + 8 * i, args[-1])
         CURRENT_TAG = None

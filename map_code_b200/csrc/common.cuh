@@ -23,6 +23,22 @@ inline cudaStream_t as_stream(map_stream_t s) { return reinterpret_cast<cudaStre
 
 constexpr int kNumSMs = 148;  // B200: grids are sized in multiples of this
 
+// Row-sharded tables over NVLink peer memory (p2p.cu): base pointer of every rank's shard, passed to kernels by value.
+constexpr int kMaxPeers = 8;  // one 8-GPU NVSwitch node
+struct PeerTable {
+    const void* p[kMaxPeers];
+};
+static inline int fill_peer_table(PeerTable* t, const void* const* ptrs, int R, const char* who) {
+    MAP_REQUIRE(R >= 1 && R <= kMaxPeers, "%s: R=%d must be in [1, %d]", who, R, kMaxPeers);
+    MAP_REQUIRE(ptrs != nullptr, "%s: null peer pointer table", who);
+    for (int r = 0; r < kMaxPeers; ++r) t->p[r] = nullptr;
+    for (int r = 0; r < R; ++r) {
+        MAP_REQUIRE(ptrs[r] != nullptr, "%s: peer pointer %d is null", who, r);
+        t->p[r] = ptrs[r];
+    }
+    return MAP_OK;
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- Philox4x32-10 (repo-wide stream convention)

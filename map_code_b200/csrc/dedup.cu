@@ -13,9 +13,18 @@ constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per CTA
 constexpr int kSortWarps = kSortThreads / 32;
 
+// The number of keys may live on the device (n_dev != nullptr: the owner-side merge of the row-sharded tables compacts a
+// data-dependent number of entries): grids are sized for the capacity n, every kernel clamps to min(n, *n_dev).
+__device__ __forceinline__ int64_t eff_n(int64_t n, const int32_t* n_dev) {
+    if (n_dev == nullptr) return n;
+    const int64_t d = (int64_t)__ldg(n_dev);
+    return d < n ? d : n;
+}
+
 // ---------------------------------------------------------------------------------------------- sort
-__global__ void __launch_bounds__(256) sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, uint32_t* keys,
-                                                        uint32_t* vals) {
+__global__ void __launch_bounds__(256) sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, const int32_t* n_dev,
+                                                        uint32_t* keys, uint32_t* vals) {
+    n = eff_n(n, n_dev);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         keys[i] = (uint32_t)ids[i];
@@ -24,9 +33,10 @@ __global__ void __launch_bounds__(256) sort_prep_kernel(const int64_t* __restric
 }
 
 // hist[block * 256 + bin] = #keys of this CTA's tile whose digit == bin
-__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
-                                                                 uint32_t* __restrict__ hist, int nblocks) {
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, const int32_t* n_dev,
+                                                                 int shift, uint32_t* __restrict__ hist, int nblocks) {
     __shared__ uint32_t sh[kRadixBins];
+    n = eff_n(n, n_dev);
     sh[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
@@ -155,7 +165,8 @@ __global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint32_t* data, i
 // stores per warp instruction).
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                     const uint32_t* __restrict__ vals_in, int64_t n,
-                                                                    int shift, const uint32_t* __restrict__ hist_scanned,
+                                                                    const int32_t* n_dev, int shift,
+                                                                    const uint32_t* __restrict__ hist_scanned,
                                                                     int nblocks, uint32_t* __restrict__ keys_out,
                                                                     uint32_t* __restrict__ vals_out) {
     __shared__ uint32_t warp_cnt[kSortWarps][kRadixBins];  // per-round per-warp digit counts -> exclusive prefixes
@@ -166,7 +177,9 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32
     __shared__ uint32_t keys_s[kSortTile];
     __shared__ uint32_t vals_s[kSortTile];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    n = eff_n(n, n_dev);
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    if (base >= n) return;  // (uniform) tile beyond a device-side count
     const int tile_n = (int)((n - base < kSortTile) ? (n - base) : kSortTile);
     gbase[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * kRadixBins + threadIdx.x];
     tile_run[threadIdx.x] = 0;
@@ -242,18 +255,22 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-__device__ __forceinline__ uint32_t head_flag(const uint32_t* keys, int64_t i) {
-    return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+// keys that agree above `seg_shift` belong to one segment (the low bits order the occurrences of a row deterministically,
+// e.g. by source rank in the sharded merge)
+__device__ __forceinline__ uint32_t head_flag(const uint32_t* keys, int64_t i, int seg_shift) {
+    return (i == 0 || (keys[i] >> seg_shift) != (keys[i - 1] >> seg_shift)) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(kScanThreads) heads_count_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                   const int32_t* n_dev, int seg_shift,
                                                                    uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t sh[kScanThreads / 32];
+    n = eff_n(n, n_dev);
     const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
     uint32_t c = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k)
-        if (base + k < n) c += head_flag(keys, base + k);
+        if (base + k < n) c += head_flag(keys, base + k, seg_shift);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
@@ -266,18 +283,27 @@ __global__ void __launch_bounds__(kScanThreads) heads_count_kernel(const uint32_
 }
 
 __global__ void __launch_bounds__(kScanThreads) heads_emit_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                  const int32_t* n_dev, int seg_shift,
                                                                   const uint32_t* __restrict__ tile_offsets,
                                                                   int64_t* __restrict__ uniq_ids,
                                                                   int32_t* __restrict__ seg_start,
                                                                   int32_t* __restrict__ n_unique) {
     __shared__ uint32_t warp_tot[kScanThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    n = eff_n(n, n_dev);
+    if (n == 0) {  // empty list (possible with a device-side count)
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            seg_start[0] = 0;
+            *n_unique = 0;
+        }
+        return;
+    }
     const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
     uint32_t f[kScanItems];
     uint32_t tsum = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        f[k] = (base + k < n) ? head_flag(keys, base + k) : 0u;
+        f[k] = (base + k < n) ? head_flag(keys, base + k, seg_shift) : 0u;
         tsum += f[k];
     }
     uint32_t incl = tsum;
@@ -294,7 +320,7 @@ __global__ void __launch_bounds__(kScanThreads) heads_emit_kernel(const uint32_t
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         if (f[k]) {
-            uniq_ids[u] = (int64_t)keys[base + k];
+            uniq_ids[u] = (int64_t)(keys[base + k] >> seg_shift);
             seg_start[u] = (int32_t)(base + k);
             ++u;
         }
@@ -345,10 +371,13 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
                                                              const int32_t* __restrict__ seg_start,
                                                              const int32_t* __restrict__ n_unique, int64_t n,
                                                              float* __restrict__ grad, float* __restrict__ scalar_out,
-                                                             int D) {
+                                                             int D, const int32_t* __restrict__ n_dev,
+                                                             const int32_t* __restrict__ occ_map,
+                                                             const PeerTable row_tab, int64_t rows_per_peer) {
     __shared__ int slot_seg[2 * 256];                  // segment id of every head (2g) / tail (2g+1) slot, -1 = empty
     __shared__ float slot_sc[2 * 256];
     __shared__ __align__(16) float slot_vec[2 * 256 * VEC];  // [slot][lanes * VEC] with 2 * G * lanes * VEC <= 512 * VEC
+    n = eff_n(n, n_dev);
     const int G = 256 / lanes;                         // groups per CTA
     const int g = threadIdx.x / lanes;
     const int lane = threadIdx.x - g * lanes;
@@ -380,9 +409,15 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
             sc[k] = 0.f;
             r[k].zero();
             if (t0 + k < t1) {
-                const int64_t occ = occ_sorted[t0 + k];
+                int64_t occ = occ_sorted[t0 + k];
+                if (occ_map != nullptr) occ = __ldg(occ_map + occ);   // compacted entry -> (peer, row) code
                 sc[k] = (scale != nullptr) ? __ldg(scale + occ) : 1.f;
-                r[k].load(rows + (occ / group) * ld_rows + lane * VEC);
+                if (rows_per_peer > 0) {  // rows live in R peer buffers (NVLink loads): code = peer * rows_per_peer + row
+                    const int64_t peer = occ / rows_per_peer;
+                    r[k].load(static_cast<const float*>(row_tab.p[peer]) + (occ - peer * rows_per_peer) * ld_rows + lane * VEC);
+                } else {
+                    r[k].load(rows + (occ / group) * ld_rows + lane * VEC);
+                }
             }
         }
         RowVec<VEC> acc;
@@ -495,13 +530,14 @@ static DedupLayout dedup_layout(int64_t n) {
 
 extern "C" size_t map_dedup_workspace_bytes(int64_t n_ids) { return mapb::dedup_layout(n_ids).total; }
 
-extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_t* uniq_ids, int32_t* seg_start,
-                             int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,
-                             map_stream_t stream) {
+extern "C" int map_dedup_ids_ex(const int64_t* ids, int64_t n, const int32_t* n_dev, int key_bits, int seg_shift, int64_t* uniq_ids,
+                                int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, void* workspace,
+                                size_t workspace_bytes, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(ids && uniq_ids && seg_start && occ_sorted && n_unique && workspace, "map_dedup_ids: null pointer");
     MAP_REQUIRE(n > 0 && n < (int64_t)1 << 31, "map_dedup_ids: n=%lld out of range", (long long)n);
     MAP_REQUIRE(key_bits >= 1 && key_bits <= 32, "map_dedup_ids: key_bits=%d", key_bits);
+    MAP_REQUIRE(seg_shift >= 0 && seg_shift < key_bits, "map_dedup_ids: seg_shift=%d", seg_shift);
     const DedupLayout L = dedup_layout(n);
     if (workspace_bytes < L.total) {
         set_error("map_dedup_ids: workspace %zu < %zu", workspace_bytes, L.total);
@@ -521,29 +557,46 @@ extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_
     uint32_t* vout = (passes % 2 == 0) ? vals_a : occ;
     uint32_t* kin = keys_a;
     uint32_t* kout = keys_b;
-    sort_prep_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ids, n, kin, vin);
+    sort_prep_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ids, n, n_dev, kin, vin);
     for (int p = 0; p < passes; ++p) {
         const int shift = p * kRadixBits;
-        sort_hist_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, n, shift, hist, L.nblocks_sort);
+        sort_hist_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, n, n_dev, shift, hist, L.nblocks_sort);
         sort_scan_kernel<<<1, 1024, 0, st>>>(hist, L.nblocks_sort);
-        sort_scatter_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, vin, n, shift, hist, L.nblocks_sort, kout, vout);
+        sort_scatter_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, vin, n, n_dev, shift, hist, L.nblocks_sort, kout, vout);
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
     // kin now holds the sorted keys, vin == occ_sorted
-    heads_count_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, tiles);
+    heads_count_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles);
     scan_single_cta_kernel<<<1, 1024, 0, st>>>(tiles, L.nblocks_scan);
-    heads_emit_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, tiles, uniq_ids, seg_start, n_unique);
+    heads_emit_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles, uniq_ids, seg_start, n_unique);
     return check_launch("map_dedup_ids");
 }
 
-extern "C" int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
-                                       const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
-                                       int64_t n_ids, float* grad_compact, float* scalar_out, map_stream_t stream) {
+extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_t* uniq_ids, int32_t* seg_start,
+                             int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,
+                             map_stream_t stream) {
+    return map_dedup_ids_ex(ids, n, nullptr, key_bits, 0, uniq_ids, seg_start, occ_sorted, n_unique, workspace, workspace_bytes, stream);
+}
+
+extern "C" int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
+                                          const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
+                                          int64_t n_ids, const int32_t* n_dev, const int32_t* occ_map,
+                                          const float* const* row_ptrs, int n_peers, int64_t rows_per_peer, float* grad_compact,
+                                          float* scalar_out, map_stream_t stream) {
     using namespace mapb;
-    MAP_REQUIRE(rows && occ_sorted && seg_start && n_unique && grad_compact, "map_segment_reduce_rows: null pointer");
+    PeerTable row_tab{};
+    if (row_ptrs != nullptr) {  // host array of device pointers -> by-value kernel parameter
+        const int rc = fill_peer_table(&row_tab, reinterpret_cast<const void* const*>(row_ptrs), n_peers, "map_segment_reduce_rows_ex");
+        if (rc != MAP_OK) return rc;
+    } else {
+        rows_per_peer = 0;
+    }
+    MAP_REQUIRE((rows || row_ptrs) && occ_sorted && seg_start && n_unique && grad_compact, "map_segment_reduce_rows: null pointer");
     MAP_REQUIRE(D >= 1 && group >= 1 && n_ids > 0, "map_segment_reduce_rows: bad shape D=%d group=%d n=%lld", D, group, (long long)n_ids);
+    MAP_REQUIRE(row_ptrs == nullptr || (rows_per_peer > 0 && group == 1), "map_segment_reduce_rows: peer rows need rows_per_peer > 0, group == 1");
     cudaStream_t st = as_stream(stream);
+    // peer buffers come from map_p2p_alloc (256-byte aligned), so only the local pointers need the alignment check
     const bool vec = (D % 4 == 0) && (ld_rows % 4 == 0) && ((uintptr_t)rows % 16 == 0) && ((uintptr_t)grad_compact % 16 == 0);
     const int lanes = vec ? D / 4 : D;
     const int64_t max_elems = n_ids * D;
@@ -556,12 +609,19 @@ extern "C" int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D
     const int64_t tiles = ceil_div(n_ids, kSegTile);
     const unsigned blocks = (unsigned)ceil_div(tiles, 256 / lanes);
     if (vec)
-        segment_reduce_kernel<4><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique,
-                                                         n_ids, grad_compact, scalar_out, D);
+        segment_reduce_kernel<4><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids,
+                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer);
     else
-        segment_reduce_kernel<1><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique,
-                                                         n_ids, grad_compact, scalar_out, D);
+        segment_reduce_kernel<1><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids,
+                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer);
     return check_launch("map_segment_reduce_rows");
+}
+
+extern "C" int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
+                                       const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
+                                       int64_t n_ids, float* grad_compact, float* scalar_out, map_stream_t stream) {
+    return map_segment_reduce_rows_ex(rows, ld_rows, D, scale, group, occ_sorted, seg_start, n_unique, n_ids, nullptr, nullptr, nullptr,
+                                      0, 0, grad_compact, scalar_out, stream);
 }
 
 extern "C" int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const int32_t* n_unique,

@@ -7,10 +7,17 @@
 
 namespace mapb {
 
+// Row idx of the (possibly row-sharded) output tables: rank idx % R holds it at local row idx / R (R == 1: the plain table).
+__device__ __forceinline__ const float* nce_row(const PeerTable& t, int R, int64_t idx, int width) {
+    if (R == 1) return static_cast<const float*>(t.p[0]) + idx * width;
+    const int64_t lr = idx / R;
+    return static_cast<const float*>(t.p[idx - lr * R]) + lr * width;
+}
+
 template <int LANES>
 __global__ void __launch_bounds__(256) nce_fwd_kernel(const float* __restrict__ input, int64_t N, int K,
                                                       const int64_t* __restrict__ target, const int64_t* __restrict__ noise,
-                                                      const float* __restrict__ emb, const float* __restrict__ bias,
+                                                      const PeerTable emb_t, const PeerTable bias_t, int R,
                                                       const float* __restrict__ logq, float norm_term, int loss_type,
                                                       float grad_scale, float* __restrict__ logits,
                                                       int64_t* __restrict__ ids_out, float* __restrict__ loss_pos,
@@ -30,7 +37,54 @@ __global__ void __launch_bounds__(256) nce_fwd_kernel(const float* __restrict__ 
         float loss = 0.f;
         float tgt_logit = 0.f, max_noise = -INFINITY;
         const int steps = (K1 + RPW - 1) / RPW;
-        if (loss_type == MAP_NCE_LOSS_NCE) {
+        if (loss_type == MAP_NCE_LOSS_NCE && K1 <= 32) {
+            // All K+1 ids of the position are fetched with ONE coalesced load (lane j holds id j); the row, bias and
+            // log-noise loads of up to 8 steps are then issued back to back before the first use, so a position costs two
+            // dependent memory round trips (ids, then rows) instead of 2 x steps (r01d: 36 us -> this form).
+            int64_t my_idx = 0;
+            if (lane < K1) my_idx = (lane == 0) ? __ldg(target + n) : __ldg(noise + n * K + (lane - 1));
+            constexpr int BATCH = LANES < 8 ? LANES : 8;
+            for (int it0 = 0; it0 < steps; it0 += BATCH) {
+                float4 r[BATCH];
+                float bq[BATCH], lq[BATCH];
+                int64_t idx[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    const int j = (it0 + u) * RPW + grp;
+                    idx[u] = __shfl_sync(0xffffffffu, my_idx, j & 31);
+                    r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bq[u] = 0.f;
+                    lq[u] = 0.f;
+                    if (it0 + u < steps && j < K1) {
+                        r[u] = __ldg(reinterpret_cast<const float4*>(nce_row(emb_t, R, idx[u], P)) + sub);
+                        bq[u] = __ldg(nce_row(bias_t, R, idx[u], 1));
+                        lq[u] = __ldg(logq + idx[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    const int j = (it0 + u) * RPW + grp;
+                    const bool valid = it0 + u < steps && j < K1;
+                    float s = x.x * r[u].x + x.y * r[u].y + x.z * r[u].z + x.w * r[u].w;
+                    s = group_sum<LANES>(s);
+                    if (valid) {
+                        const float lg = s + bq[u] - norm_term;                  // nce_loss.py:171-172
+                        const float z = lg - lq[u] - ln_k;                        // nce_loss.py:222
+                        const float y = (j == 0) ? 1.f : 0.f;
+                        const float dz = (sigmoidf(z) - y) * grad_scale;
+                        acc.x = fmaf(dz, r[u].x, acc.x); acc.y = fmaf(dz, r[u].y, acc.y);
+                        acc.z = fmaf(dz, r[u].z, acc.z); acc.w = fmaf(dz, r[u].w, acc.w);
+                        if (j == 0) tgt_logit = lg; else max_noise = fmaxf(max_noise, lg);
+                        if (sub == 0) {
+                            loss += softplusf(z) - y * z;                         // BCEWithLogits, nce_loss.py:227
+                            logits[n * K1 + j] = lg;
+                            dz_out[n * K1 + j] = dz;
+                            if (ids_out != nullptr) ids_out[n * K1 + j] = idx[u];
+                        }
+                    }
+                }
+            }
+        } else if (loss_type == MAP_NCE_LOSS_NCE) {
             for (int it = 0; it < steps; ++it) {
                 const int j = it * RPW + grp;
                 const bool valid = j < K1;
@@ -38,12 +92,12 @@ __global__ void __launch_bounds__(256) nce_fwd_kernel(const float* __restrict__ 
                 float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
                     idx = (j == 0) ? __ldg(target + n) : __ldg(noise + n * K + (j - 1));
-                    r = __ldg(reinterpret_cast<const float4*>(emb + idx * P) + sub);
+                    r = __ldg(reinterpret_cast<const float4*>(nce_row(emb_t, R, idx, P)) + sub);
                 }
                 float s = x.x * r.x + x.y * r.y + x.z * r.z + x.w * r.w;
                 s = group_sum<LANES>(s);
                 if (valid) {
-                    const float lg = s + __ldg(bias + idx) - norm_term;     // nce_loss.py:171-172
+                    const float lg = s + __ldg(nce_row(bias_t, R, idx, 1)) - norm_term;     // nce_loss.py:171-172
                     const float z = lg - __ldg(logq + idx) - ln_k;           // nce_loss.py:222
                     const float y = (j == 0) ? 1.f : 0.f;
                     const float dz = (sigmoidf(z) - y) * grad_scale;
@@ -67,12 +121,12 @@ __global__ void __launch_bounds__(256) nce_fwd_kernel(const float* __restrict__ 
                 float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
                     idx = (j == 0) ? __ldg(target + n) : __ldg(noise + n * K + (j - 1));
-                    r = __ldg(reinterpret_cast<const float4*>(emb + idx * P) + sub);
+                    r = __ldg(reinterpret_cast<const float4*>(nce_row(emb_t, R, idx, P)) + sub);
                 }
                 float s = x.x * r.x + x.y * r.y + x.z * r.z + x.w * r.w;
                 s = group_sum<LANES>(s);
                 if (valid) {
-                    const float lg = s + __ldg(bias + idx) - norm_term;
+                    const float lg = s + __ldg(nce_row(bias_t, R, idx, 1)) - norm_term;
                     const float c = lg - __ldg(logq + idx);
                     mx = fmaxf(mx, c);
                     if (j == 0) tgt_logit = lg; else max_noise = fmaxf(max_noise, lg);
@@ -98,7 +152,7 @@ __global__ void __launch_bounds__(256) nce_fwd_kernel(const float* __restrict__ 
                 float dz = 0.f;
                 if (j < K1) {
                     const int64_t idx = (j == 0) ? __ldg(target + n) : __ldg(noise + n * K + (j - 1));
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(emb + idx * P) + sub);
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(nce_row(emb_t, R, idx, P)) + sub);
                     const float c = dz_out[n * K1 + j];
                     dz = (expf(c - lse) - ((j == 0) ? 1.f : 0.f)) * grad_scale;
                     acc.x = fmaf(dz, r.x, acc.x); acc.y = fmaf(dz, r.y, acc.y);
@@ -155,22 +209,22 @@ __global__ void __launch_bounds__(256) scatter_add_slices_kernel(const float* __
 
 }  // namespace mapb
 
-extern "C" int map_nce_fwd(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
-                           const float* emb, const float* bias, const float* logprob_noise, int64_t V, float norm_term,
-                           int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos, float* dz,
-                           float* d_input, int32_t* acc_count, map_stream_t stream) {
+static int nce_fwd_launch(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
+                          const mapb::PeerTable& emb_t, const mapb::PeerTable& bias_t, int R, const float* logprob_noise,
+                          float norm_term, int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos,
+                          float* dz, float* d_input, int32_t* acc_count, map_stream_t stream, const char* who) {
     using namespace mapb;
-    MAP_REQUIRE(input && target && noise && emb && bias && logprob_noise && logits && loss_pos && dz, "map_nce_fwd: null pointer");
-    MAP_REQUIRE(N >= 0 && K >= 1 && V > 0, "map_nce_fwd: bad shape N=%lld K=%d", (long long)N, K);
-    MAP_REQUIRE(loss_type == MAP_NCE_LOSS_NCE || loss_type == MAP_NCE_LOSS_SAMPLED, "map_nce_fwd: unknown loss_type %d", loss_type);
-    MAP_REQUIRE(((uintptr_t)input % 16 == 0) && ((uintptr_t)emb % 16 == 0) && (!d_input || (uintptr_t)d_input % 16 == 0),
-                "map_nce_fwd: input/emb/d_input must be 16-byte aligned");
+    MAP_REQUIRE(input && target && noise && logprob_noise && logits && loss_pos && dz, "%s: null pointer", who);
+    MAP_REQUIRE(N >= 0 && K >= 1, "%s: bad shape N=%lld K=%d", who, (long long)N, K);
+    MAP_REQUIRE(loss_type == MAP_NCE_LOSS_NCE || loss_type == MAP_NCE_LOSS_SAMPLED, "%s: unknown loss_type %d", who, loss_type);
+    MAP_REQUIRE(((uintptr_t)input % 16 == 0) && (!d_input || (uintptr_t)d_input % 16 == 0), "%s: input/d_input must be 16-byte aligned", who);
+    for (int r = 0; r < R; ++r) MAP_REQUIRE((uintptr_t)emb_t.p[r] % 16 == 0, "%s: emb must be 16-byte aligned", who);
     if (N == 0) return MAP_OK;
     int64_t blocks = ceil_div(N, 8);  // 8 warps (positions) per CTA
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     cudaStream_t st = as_stream(stream);
-#define LAUNCH(LN)                                                                                                        \
-    nce_fwd_kernel<LN><<<(unsigned)blocks, 256, 0, st>>>(input, N, K, target, noise, emb, bias, logprob_noise, norm_term, \
+#define LAUNCH(LN)                                                                                                           \
+    nce_fwd_kernel<LN><<<(unsigned)blocks, 256, 0, st>>>(input, N, K, target, noise, emb_t, bias_t, R, logprob_noise, norm_term, \
                                                          loss_type, grad_scale, logits, ids_out, loss_pos, dz, d_input, acc_count)
     switch (P) {
         case 4: LAUNCH(1); break;
@@ -180,11 +234,39 @@ extern "C" int map_nce_fwd(const float* input, int64_t N, int P, int K, const in
         case 64: LAUNCH(16); break;
         case 128: LAUNCH(32); break;
         default:
-            set_error("map_nce_fwd: proj_size P=%d not in {4,8,16,32,64,128}", P);
+            set_error("%s: proj_size P=%d not in {4,8,16,32,64,128}", who, P);
             return MAP_EUNSUPPORTED;
     }
 #undef LAUNCH
-    return check_launch("map_nce_fwd");
+    return check_launch(who);
+}
+
+extern "C" int map_nce_fwd(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
+                           const float* emb, const float* bias, const float* logprob_noise, int64_t V, float norm_term,
+                           int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos, float* dz,
+                           float* d_input, int32_t* acc_count, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(emb && bias && V > 0, "map_nce_fwd: null table");
+    PeerTable emb_t{}, bias_t{};
+    emb_t.p[0] = emb;
+    bias_t.p[0] = bias;
+    return nce_fwd_launch(input, N, P, K, target, noise, emb_t, bias_t, 1, logprob_noise, norm_term, loss_type, grad_scale, logits,
+                          ids_out, loss_pos, dz, d_input, acc_count, stream, "map_nce_fwd");
+}
+
+extern "C" int map_nce_fwd_sharded(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
+                                   const void* const* emb_shards, const void* const* bias_shards, int R,
+                                   const float* logprob_noise, float norm_term, int loss_type, float grad_scale, float* logits,
+                                   int64_t* ids_out, float* loss_pos, float* dz, float* d_input, int32_t* acc_count,
+                                   map_stream_t stream) {
+    using namespace mapb;
+    PeerTable emb_t, bias_t;
+    int rc = fill_peer_table(&emb_t, emb_shards, R, "map_nce_fwd_sharded");
+    if (rc != MAP_OK) return rc;
+    rc = fill_peer_table(&bias_t, bias_shards, R, "map_nce_fwd_sharded");
+    if (rc != MAP_OK) return rc;
+    return nce_fwd_launch(input, N, P, K, target, noise, emb_t, bias_t, R, logprob_noise, norm_term, loss_type, grad_scale, logits,
+                          ids_out, loss_pos, dz, d_input, acc_count, stream, "map_nce_fwd_sharded");
 }
 
 extern "C" int map_gather_slices(const float* enc, const int64_t* masked_index, int64_t N, int L, int F, int P, float* sel,

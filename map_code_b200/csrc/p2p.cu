@@ -1,0 +1,232 @@
+// K13 over NVLink peer memory: row-sharded tables addressed directly by every GPU of the node.
+// Table row `id` lives on rank id % R at local row id / R.  Each rank allocates its shards and its per-step compact
+// gradients with map_p2p_alloc (cudaMalloc + CUDA IPC handle); the other ranks map them with map_p2p_open, so the kernels
+// below read rows of ANY shard with plain loads that travel over NVLink / NVSwitch:
+//   forward   map_emb_gather_sharded_f32 / map_nce_fwd_sharded (nce.cu): the lookup IS the exchange — no id all-to-all,
+//             no row all-to-all, no staging buffers;
+//   backward  every rank reduces its own occurrences to a compact (unique id, row) list with the single-GPU pipeline;
+//             after one barrier the OWNER pulls the entries it owns from all R lists (map_owned_compact -> sort with the
+//             source rank in the low key bits -> map_segment_reduce_rows_ex over peer rows) and applies row-wise AdamW to
+//             its shard.  Traffic per rank = the rows it needs, independent of R.
+// The reference initialises NCCL (code/arguments.py:74) and never issues a collective; NCCL is kept here for the dense
+// gradient all-reduce and for the two barriers per step.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mapb {
+
+constexpr int kGatherUnroll = 4;
+
+// out[i, :] = shard[id % R][id / R, :]  — same lane mapping as emb_gather_vec4_kernel (embedding.cu)
+__global__ void __launch_bounds__(256) emb_gather_sharded_vec4_kernel(const PeerTable shards, int R, int64_t V, int vpr,
+                                                                      const int64_t* __restrict__ ids, int64_t n_vec,
+                                                                      float4* __restrict__ out, int32_t* oob_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; e < n_vec; e += stride * kGatherUnroll) {
+        int64_t row[kGatherUnroll];
+        int lane[kGatherUnroll];
+        float4 val[kGatherUnroll];
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int64_t eu = e + u * stride;
+            row[u] = -1;
+            lane[u] = 0;
+            if (eu < n_vec) {
+                const int64_t r = eu / vpr;
+                lane[u] = (int)(eu - r * vpr);
+                row[u] = __ldg(ids + r);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row[u] >= 0 && row[u] < V) {
+                const int owner = (int)(row[u] % R);
+                const float4* base = reinterpret_cast<const float4*>(shards.p[owner]);
+                val[u] = __ldg(base + (row[u] / R) * vpr + lane[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int64_t eu = e + u * stride;
+            if (eu < n_vec) {
+                st_stream_f4(out + eu, val[u]);
+                if (oob_flag != nullptr && (row[u] < 0 || row[u] >= V)) *oob_flag = 1;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) emb_gather_sharded_scalar_kernel(const PeerTable shards, int R, int64_t V, int D,
+                                                                        const int64_t* __restrict__ ids, int64_t n_elem,
+                                                                        float* __restrict__ out, int32_t* oob_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += stride) {
+        const int64_t r = e / D;
+        const int d = (int)(e - r * D);
+        const int64_t row = __ldg(ids + r);
+        float v = 0.f;
+        if (row >= 0 && row < V) v = __ldg(reinterpret_cast<const float*>(shards.p[row % R]) + (row / R) * D + d);
+        else if (oob_flag != nullptr) *oob_flag = 1;
+        out[e] = v;
+    }
+}
+
+struct PeerLists {
+    const int64_t* uniq[kMaxPeers];
+    const int32_t* n_unique[kMaxPeers];
+};
+
+// Scans the R per-rank unique-id lists (peer loads) and appends the entries this rank owns:
+//   keys[k] = (id / R) * R_pow2 + s     (local row in the high bits, source rank s in the low `shift` bits: a stable sort
+//                                        on the full key orders the contributions of a row by source rank -> deterministic sums)
+//   src[k]  = s * cap + u               (which row of which rank's compact gradient)
+// grid.y = source rank; warp-aggregated append.
+__global__ void __launch_bounds__(256) owned_compact_kernel(const PeerLists lists, int R, int rank, int shift, int64_t cap,
+                                                            int64_t* __restrict__ keys, int32_t* __restrict__ src,
+                                                            int32_t* __restrict__ n_out) {
+    const int s = blockIdx.y;
+    const int64_t n_s = (int64_t)__ldg(lists.n_unique[s]);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_s; base += stride) {
+        const int64_t u = base + threadIdx.x;
+        int64_t id = -1;
+        if (u < n_s) id = __ldg(lists.uniq[s] + u);
+        const bool mine = id >= 0 && (int)(id % R) == rank;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (m == 0) continue;
+        int pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(n_out, __popc(m));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (mine) {
+            const int k = pos0 + __popc(m & ((1u << lane) - 1u));
+            keys[k] = ((id / R) << shift) | (int64_t)s;
+            src[k] = (int32_t)(s * cap + u);
+        }
+    }
+}
+
+}  // namespace mapb
+
+extern "C" int map_p2p_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+    using namespace mapb;
+    MAP_REQUIRE(ptr && handle64 && bytes > 0, "map_p2p_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        set_error("map_p2p_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
+    e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        set_error("map_p2p_alloc: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaFree(p);
+        return MAP_ECUDA;
+    }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return MAP_OK;
+}
+
+extern "C" int map_p2p_open(const unsigned char* handle64, void** ptr) {
+    using namespace mapb;
+    MAP_REQUIRE(ptr && handle64, "map_p2p_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        set_error("map_p2p_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
+    *ptr = p;
+    return MAP_OK;
+}
+
+extern "C" int map_p2p_close(void* ptr) {
+    using namespace mapb;
+    if (ptr == nullptr) return MAP_OK;
+    const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) {
+        set_error("map_p2p_close: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
+    return MAP_OK;
+}
+
+extern "C" int map_p2p_free(void* ptr) {
+    using namespace mapb;
+    if (ptr == nullptr) return MAP_OK;
+    const cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) {
+        set_error("map_p2p_free: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
+    return MAP_OK;
+}
+
+extern "C" int map_emb_gather_sharded_f32(const void* const* shard_ptrs, int R, int64_t V, int D, const int64_t* ids,
+                                          int64_t n_ids, float* out, int32_t* oob_flag, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(V > 0 && D > 0 && n_ids >= 0, "map_emb_gather_sharded_f32: bad shape V=%lld D=%d n=%lld", (long long)V, D, (long long)n_ids);
+    PeerTable t;
+    const int rc = fill_peer_table(&t, shard_ptrs, R, "map_emb_gather_sharded_f32");
+    if (rc != MAP_OK) return rc;
+    if (n_ids == 0) return MAP_OK;
+    MAP_REQUIRE(ids && out, "map_emb_gather_sharded_f32: null pointer");
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (D % 4 == 0 && (uintptr_t)out % 16 == 0) {  // shards come from map_p2p_alloc: 256-byte aligned
+        const int vpr = D / 4;
+        const int64_t n_vec = n_ids * vpr;
+        int64_t blocks = ceil_div(n_vec, 256 * kGatherUnroll);
+        if (blocks > cap) blocks = cap;
+        emb_gather_sharded_vec4_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(t, R, V, vpr, ids, n_vec,
+                                                                                        reinterpret_cast<float4*>(out), oob_flag);
+    } else {
+        const int64_t n_elem = n_ids * D;
+        int64_t blocks = ceil_div(n_elem, 256);
+        if (blocks > cap) blocks = cap;
+        emb_gather_sharded_scalar_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(t, R, V, D, ids, n_elem, out, oob_flag);
+    }
+    return check_launch("map_emb_gather_sharded_f32");
+}
+
+extern "C" int map_owned_compact(const void* const* uniq_ptrs, const void* const* n_unique_ptrs, int R, int rank, int64_t cap,
+                                 int64_t* keys, int32_t* src, int32_t* n_out, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(R >= 1 && R <= kMaxPeers && rank >= 0 && rank < R && cap > 0 && uniq_ptrs && n_unique_ptrs && keys && src && n_out,
+                "map_owned_compact: bad argument");
+    MAP_REQUIRE((int64_t)R * cap < ((int64_t)1 << 31), "map_owned_compact: R * cap must fit in int32");
+    PeerLists l;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        l.uniq[r] = nullptr;
+        l.n_unique[r] = nullptr;
+    }
+    for (int r = 0; r < R; ++r) {
+        MAP_REQUIRE(uniq_ptrs[r] && n_unique_ptrs[r], "map_owned_compact: peer pointer %d is null", r);
+        l.uniq[r] = static_cast<const int64_t*>(uniq_ptrs[r]);
+        l.n_unique[r] = static_cast<const int32_t*>(n_unique_ptrs[r]);
+    }
+    int shift = 0;
+    while ((1 << shift) < R) ++shift;
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(n_out, 0, sizeof(int32_t), st) != cudaSuccess) {
+        set_error("map_owned_compact: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MAP_ECUDA;
+    }
+    int64_t bx = ceil_div(cap, 256);
+    if (bx > kNumSMs * 2) bx = kNumSMs * 2;
+    owned_compact_kernel<<<dim3((unsigned)bx, (unsigned)R), 256, 0, st>>>(l, R, rank, shift, cap, keys, src, n_out);
+    return check_launch("map_owned_compact");
+}

@@ -69,14 +69,17 @@ class ShardExchange:
         if out is None:
             out = torch.empty((self.R,) + tuple(local.shape), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=self.group)
+        _lib.mark("nccl_all_gather", ("bytes_out", out.numel() * out.element_size()))
         return out
 
     def reduce_scatter(self, full: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         dist.reduce_scatter_tensor(out.view(-1), full.view(-1), op=dist.ReduceOp.SUM, group=self.group)
+        _lib.mark("nccl_reduce_scatter", ("bytes_in", full.numel() * full.element_size()))
         return out
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        _lib.mark("nccl_all_reduce", ("bytes", t.numel() * t.element_size()))
         return t
 
     # -- embedding
@@ -106,8 +109,9 @@ class ShardExchange:
 
 
 # ------------------------------------------------------------------------------------------------ the sharded fused step
-class ShardedFusedStep(FusedStep):
-    """FusedStep with row-sharded tables.  `batch_size` is the per-rank batch; the global batch is batch_size * world."""
+class CollectiveShardedFusedStep(FusedStep):
+    """FusedStep with row-sharded tables, exchanges as fixed-size NCCL collectives (portable variant; moves R x the rows an
+    exact exchange would).  `batch_size` is the per-rank batch; the global batch is batch_size * world."""
 
     def __init__(self, model, *, world: int, rank: int, group=None, **kw):
         from . import ops
@@ -214,6 +218,258 @@ class ShardedFusedStep(FusedStep):
         for name, V in self._full_shapes.items():
             shard = sd[name]
             parts = self.xch.all_gather(shard)
+            sd[name] = unshard_table([parts[r] for r in range(self.world)], V)
+        return sd
+
+
+# ------------------------------------------------------------------------------------------------ NVLink peer memory
+class PeerBuffer:
+    """One allocation per rank, mapped into every rank of the node: `local` is this rank's tensor, `ptrs` a ctypes array of the
+    R device base pointers (valid in THIS process) that the *_sharded / *_ex kernels take."""
+
+    def __init__(self, local: torch.Tensor, ptrs, raw_local: int, raw_peers: List[int]):
+        self.local, self.ptrs, self._raw_local, self._raw_peers = local, ptrs, raw_local, raw_peers
+
+
+class _CudaArrayView:
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(ptr, False), version=2)
+
+
+_TYPESTR = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4"}
+
+
+class PeerMemory:
+    """CUDA-IPC peer memory of one NVSwitch node: map_p2p_alloc on every rank, handles exchanged through the process group,
+    map_p2p_open for the other ranks' allocations (lazy peer access).  Collective: every rank calls alloc() in the same order."""
+
+    def __init__(self, world: int, rank: int, device, group=None):
+        self.R, self.rank, self.dev, self.group = world, rank, device, group
+        self.buffers: List[PeerBuffer] = []
+
+    def alloc(self, shape, dtype) -> PeerBuffer:
+        import ctypes as C
+        lib = _lib.load()
+        n = 1
+        for s_ in shape:
+            n *= int(s_)
+        nbytes = max(n, 1) * torch.empty(0, dtype=dtype).element_size()
+        nbytes = (nbytes + 255) // 256 * 256
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.dev):
+            _lib.call("map_p2p_alloc", nbytes, C.byref(ptr), handle)
+        handles = [None] * self.R
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        raw = []
+        for r in range(self.R):
+            if r == self.rank:
+                raw.append(int(ptr.value))
+            else:
+                p = C.c_void_p()
+                h = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                with torch.cuda.device(self.dev):
+                    _lib.call("map_p2p_open", h, C.byref(p))
+                raw.append(int(p.value))
+        local = torch.as_tensor(_CudaArrayView(raw[self.rank], (max(n, 1),), _TYPESTR[dtype]), device=self.dev)[:n].view(*shape)
+        buf = PeerBuffer(local, (C.c_void_p * self.R)(*raw), raw[self.rank], raw)
+        self.buffers.append(buf)
+        return buf
+
+
+class ShardedFusedStep(FusedStep):
+    """FusedStep with row-sharded tables in NVLink peer memory (default multi-GPU path).
+
+    forward   the embedding gather and the fused NCE kernel read rows of ANY rank's shard directly (peer loads over NVLink):
+              no id exchange, no row exchange, no staging;
+    backward  every rank reduces its own occurrences to a compact (unique id, gradient row) list exactly like the single-GPU
+              step; after a barrier the OWNER of each row pulls the entries it owns from all R lists, sums them in source-rank
+              order (deterministic) and applies row-wise AdamW to its shard;
+    dense     parameters are replicated; ONE all-reduce of the flat gradient buffer, issued after the table updates so that
+              its completion also tells every rank that all shards are up to date for the next step's gathers.
+    `batch_size` is the per-rank batch; the global batch is batch_size * world.  Philox counters are indexed by the global
+    row, so the R-rank run reproduces the single-GPU run on the concatenated batch."""
+
+    def __init__(self, model, *, world: int, rank: int, group=None, **kw):
+        self.world, self.rank, self.group = world, rank, group
+        if world > 8:
+            raise NotImplementedError("peer-memory sharding covers one NVSwitch node (<= 8 GPUs)")
+        B = kw["batch_size"]
+        kw.setdefault("use_graph", False)
+        kw["row0"] = rank * B
+        kw["global_batch"] = B * world
+        if model.model_name.lower() == "deepfm":
+            raise NotImplementedError("DeepFM's first-order table is not row-sharded yet: run DeepFM on one GPU")
+        self.pm = PeerMemory(world, rank, next(model.parameters()).device, group)
+        self._full_shapes: Dict[str, int] = {}
+        super().__init__(model, **kw)
+        self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+    # -- setup: shards, peer-visible compact gradients, merge plans
+    def _shard_param(self, name: str, param: torch.nn.Parameter) -> PeerBuffer:
+        V, D = param.shape
+        self._full_shapes[name] = V
+        rows = shard_rows(V, self.world)
+        buf = self.pm.alloc((rows, D), torch.float32)
+        buf.local.copy_(shard_table(param.data, self.world, self.rank))
+        param.data = buf.local
+        return buf
+
+    def _peer_table(self, name, param, n_ids, plan):
+        V_full = param.shape[0]
+        shard = self._shard_param(name, param)
+        t = _Table(name, param, n_ids, 0.0 if is_no_decay(name) else self.wd, self.dev)
+        t.shard, t.V_full = shard, V_full
+        t.gbuf = self.pm.alloc((n_ids, t.D), torch.float32)
+        t.grad = t.gbuf.local
+        t.plan = plan   # local dedup of this rank's occurrences; the merge reads its uniq / n_unique from every rank
+        return t
+
+    def _make_plan(self, n_ids, V_full):
+        from . import ops
+        bufs = []
+        plan = ops.DedupPlan(n_ids, V_full, self.dev, alloc=lambda shape, dtype: self._alloc_peer(bufs, shape, dtype))
+        plan.uniq_buf, plan.n_unique_buf = bufs
+        return plan
+
+    def _alloc_peer(self, sink, shape, dtype):
+        b = self.pm.alloc(shape, dtype)
+        sink.append(b)
+        return b.local
+
+    def _make_merge(self, plan, shard_rows_):
+        """owner-side merge state of one id stream: compacted keys / sources (capacity R * n) and their dedup plan"""
+        from . import ops
+        R, cap = self.world, plan.n
+        m = type("Merge", (), {})()
+        m.cap = cap
+        m.keys = torch.zeros(R * cap, dtype=torch.int64, device=self.dev)
+        m.src = torch.zeros(R * cap, dtype=torch.int32, device=self.dev)
+        m.n_owned = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        shift = max(0, (R - 1).bit_length())
+        m.plan = ops.DedupPlan(R * cap, shard_rows_ << shift, self.dev, seg_shift=shift, n_dev=m.n_owned)
+        return m
+
+    def _make_embed_table(self):
+        name = "embed.embedding.weight"
+        n = self.B * self.F
+        plan = self._make_plan(n, self.embed_w.shape[0])
+        t = self._peer_table(name, self.embed_w, n, plan)
+        t.merge = self._make_merge(plan, t.p.shape[0])
+        t.grad_owned = torch.zeros(self.world * n, t.D, dtype=torch.float32, device=self.dev)
+        self.tables[name] = t
+
+    def _make_nce_tables(self):
+        crit = self.model.mfp_criterion
+        n_occ = max(self.N, 1) * (self.K + 1)
+        plan = self._make_plan(n_occ, crit.emb.weight.shape[0])
+        te = self._peer_table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, plan)
+        tb = self._peer_table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, plan)
+        te.merge = tb.merge = self._make_merge(plan, te.p.shape[0])
+        te.grad_owned = torch.zeros(self.world * n_occ, te.D, dtype=torch.float32, device=self.dev)
+        tb.grad_owned = torch.zeros(self.world * n_occ, tb.D, dtype=torch.float32, device=self.dev)
+        self.tables[te.name], self.tables[tb.name] = te, tb
+
+    # -- exchange primitives
+    def _barrier(self):
+        """stream-ordered barrier over the ranks (a 4-byte all-reduce): everything every rank issued before it on the calling
+        stream is complete and visible to peer loads after it"""
+        dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.group)
+        _lib.mark("nccl_barrier")
+
+    def _merge(self, tables):
+        """tables share one id stream (plan + merge): pull the owned entries of all ranks and reduce them per local row"""
+        from . import ops
+        t0 = tables[0]
+        m, plan = t0.merge, t0.plan
+        ops.owned_compact(plan.uniq_buf.ptrs, plan.n_unique_buf.ptrs, self.world, self.rank, m.cap, m.keys, m.src, m.n_owned)
+        m.plan.run(m.keys)
+        for t in tables:
+            m.plan.reduce_peer_rows(t.gbuf.ptrs, self.world, m.cap, t.D, m.src, out=t.grad_owned)
+
+    # -- hooks of FusedStep
+    def _embed_lookup(self, ids):
+        from . import ops
+        t = self.tables["embed.embedding.weight"]
+        self._fork("tab")
+        with self._on("tab"):
+            self._draw_noise()
+            t.plan.run(ids.view(-1))
+        ops.emb_gather_sharded(t.shard.ptrs, self.world, t.V_full, self.D, ids, out=self.X0)
+
+    def _embed_backward(self):
+        self._join("tab")
+        t = self.tables["embed.embedding.weight"]
+        t.plan.reduce_rows(self.dE, self.D, out=t.grad)
+
+    def _nce_core(self):
+        from . import ops
+        P, K, L = self.P, self.K, self.L
+        crit = self.model.mfp_criterion
+        te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
+        self.acc_count.zero_()
+        n_global = self.global_batch * L
+        ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, None, None, crit.logprob_noise, self.norm_term, self.loss_type,
+                    grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all, loss_pos=self.loss_pos, dz=self.dz,
+                    d_input=self.d_sel, acc_count=self.acc_count, shards=(te.shard.ptrs, tb.shard.ptrs, self.world))
+        self._fork("tab")
+        with self._on("tab"):
+            ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
+            te.plan.run(self.ids_all.view(-1))
+            te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad.view(-1))
+            # every rank has finished reading the NCE tables (its nce_fwd precedes this point) and its compact gradients are
+            # complete: owners pull now, off the critical path of the backward pass
+            self._barrier()
+            self._merge([te, tb])
+
+    def reduce_gradients(self):
+        self._barrier()          # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
+        self._merge([self.tables["embed.embedding.weight"]])
+
+    def optimizer_step(self):
+        from . import ops
+        b1, b2 = self.betas
+        ops.adamw_hyper_step(self.hyper, self.step_counter, self.lr, b1, b2, self.eps, self.sched, self.warmup_steps, self.total_steps)
+        for t in self.tables.values():
+            if self.optimizer_mode == "sparse":
+                ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
+            else:
+                ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
+        # after the table updates: the completion of this all-reduce on any rank implies every rank's shards are up to date
+        dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
+        _lib.mark("nccl_all_reduce", ("bytes", self.grad_flat.numel() * 4))
+        ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
+
+    def dense_table_grad(self, name: str) -> torch.Tensor:
+        """[shard_rows, D] dense view of the merged gradient of this rank's shard"""
+        t = self.tables[name]
+        dense = torch.zeros(t.p.shape[0], t.D, dtype=torch.float32, device=self.dev)
+        t.merge.plan.scatter_dense(t.grad_owned, t.D, dense)
+        return dense
+
+    def _all_reduce_small(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def outputs(self):
+        """global metrics: sums of the per-rank partial means / counts (tiny all-reduces, issued only when metrics are read)"""
+        if self.mode == "MFP":
+            loss = self._all_reduce_small(self.loss.clone())
+            acc = self._all_reduce_small(self.acc_count.clone())
+            return (loss.view(()), self.global_batch * self.L, acc.view(()))
+        st = self._all_reduce_small(torch.stack([self.stats[0] * (self.B / self.global_batch), self.stats[1], self.stats[2]]))
+        cnt = self.global_batch * self.F
+        if self.mode == "RFD":
+            return (st[0], cnt, st[1] / cnt, st[2] / cnt)
+        return (st[0], self.ctr_logits)
+
+    def full_state_dict(self) -> Dict[str, torch.Tensor]:
+        """state_dict in the reference's layout: shards of every table are all-gathered and re-interleaved to [V, D]."""
+        sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        for name, V in self._full_shapes.items():
+            shard = sd[name].contiguous()
+            parts = torch.empty((self.world,) + tuple(shard.shape), dtype=shard.dtype, device=shard.device)
+            dist.all_gather_into_tensor(parts.view(-1), shard.view(-1), group=self.group)
             sd[name] = unshard_table([parts[r] for r in range(self.world)], V)
         return sd
 

@@ -54,26 +54,53 @@ def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tenso
     return out
 
 
+def emb_gather_sharded(shard_ptrs, R: int, V: int, D: int, ids: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[i,:] = shard[ids[i] % R][ids[i] // R, :]; shard_ptrs: ctypes array of R device base pointers (peer memory)."""
+    _check(ids, torch.int64, "ids")
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+        _lib.CURRENT_TAG = ("gather", ids.numel(), D)
+    call("map_emb_gather_sharded_f32", shard_ptrs, R, V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), None, _stream())
+    return out
+
+
+def owned_compact(uniq_ptrs, n_unique_ptrs, R: int, rank: int, cap: int, keys: torch.Tensor, src: torch.Tensor, n_out: torch.Tensor):
+    call("map_owned_compact", uniq_ptrs, n_unique_ptrs, R, rank, cap, keys.data_ptr(), src.data_ptr(), n_out.data_ptr(), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ K2
 class DedupPlan:
     """Pre-allocated buffers for the dedup pipeline of one id stream of fixed length n (graph-capturable)."""
 
-    def __init__(self, n: int, V: int, device):
+    def __init__(self, n: int, V: int, device, alloc=None, seg_shift: int = 0, n_dev: Optional[torch.Tensor] = None):
+        """alloc(shape, dtype) -> tensor places `uniq` and `n_unique` (what the owner-side merge of the sharded tables reads
+        from the other ranks) in peer-visible memory; seg_shift / n_dev: see map_dedup_ids_ex."""
         self.n, self.V = int(n), int(V)
         self.key_bits = key_bits(V)
-        self.uniq = torch.empty(self.n, dtype=torch.int64, device=device)
+        self.seg_shift, self.n_dev = int(seg_shift), n_dev
+        mk = alloc if alloc is not None else (lambda shape, dtype: torch.zeros(shape, dtype=dtype, device=device))
+        self.uniq = mk((self.n,), torch.int64)
         self.seg_start = torch.empty(self.n + 1, dtype=torch.int32, device=device)
         self.occ_sorted = torch.empty(self.n, dtype=torch.int32, device=device)
-        self.n_unique = torch.zeros(1, dtype=torch.int32, device=device)
+        self.n_unique = mk((1,), torch.int32)
         self.ws_bytes = int(_lib.load().map_dedup_workspace_bytes(self.n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
 
     def run(self, ids: torch.Tensor):
         _check(ids, torch.int64, "ids")
         assert ids.numel() == self.n
-        call("map_dedup_ids", ids.data_ptr(), self.n, self.key_bits, self.uniq.data_ptr(), self.seg_start.data_ptr(),
-             self.occ_sorted.data_ptr(), self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws_bytes, _stream())
+        call("map_dedup_ids_ex", ids.data_ptr(), self.n, _ptr(self.n_dev), self.key_bits, self.seg_shift, self.uniq.data_ptr(),
+             self.seg_start.data_ptr(), self.occ_sorted.data_ptr(), self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws_bytes, _stream())
         return self
+
+    def reduce_peer_rows(self, row_ptrs, n_peers: int, rows_per_peer: int, D: int, occ_map: torch.Tensor, out: torch.Tensor):
+        """segment sums over rows that live in the R ranks' compact gradients (row_ptrs: ctypes array of R device pointers,
+        peer memory): row code = occ_map[occurrence] = peer * rows_per_peer + row."""
+        if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+            _lib.CURRENT_TAG = ("segred_peer", self.n, D)
+        call("map_segment_reduce_rows_ex", None, D, D, None, 1, self.occ_sorted.data_ptr(), self.seg_start.data_ptr(),
+             self.n_unique.data_ptr(), self.n, _ptr(self.n_dev), occ_map.data_ptr(), row_ptrs, n_peers, rows_per_peer, out.data_ptr(),
+             None, _stream())
+        return out
 
     def reduce_rows(self, rows: torch.Tensor, D: int, ld_rows: Optional[int] = None, scale: Optional[torch.Tensor] = None,
                     group: int = 1, out: Optional[torch.Tensor] = None, scalar_out: Optional[torch.Tensor] = None):
@@ -81,9 +108,9 @@ class DedupPlan:
             out = torch.empty(self.n, D, dtype=torch.float32, device=rows.device)
         if _lib.PROFILE is not None or _lib.TIMELINE is not None:
             _lib.CURRENT_TAG = ("segred", self.n, D)
-        call("map_segment_reduce_rows", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
-             self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, out.data_ptr(),
-             _ptr(scalar_out), _stream())
+        call("map_segment_reduce_rows_ex", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
+             self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, _ptr(self.n_dev), None, None, 0, 0,
+             out.data_ptr(), _ptr(scalar_out), _stream())
         return out
 
     def scatter_dense(self, grad_compact: torch.Tensor, D: int, dense: torch.Tensor):
@@ -206,7 +233,8 @@ def alias_draw(prob: torch.Tensor, alias: torch.Tensor, seed: int, offset: int, 
 
 # ------------------------------------------------------------------------------------------------ K6 / K7
 def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: str = "nce", grad_scale: Optional[float] = None,
-            logits=None, ids_out=None, loss_pos=None, dz=None, d_input=None, acc_count=None, want_ids=True, want_d_input=True):
+            logits=None, ids_out=None, loss_pos=None, dz=None, d_input=None, acc_count=None, want_ids=True, want_d_input=True,
+            shards=None):
     """inp [N,P]; target [N]; noise [N,K].  Returns (logits [N,K+1], ids [N,K+1] | None, loss_pos [N], dz [N,K+1], d_input | None)."""
     if loss_type not in _lib.NCE_LOSS:
         raise NotImplementedError(f"loss type {loss_type} not implemented")  # reference: nce_loss.py:126-132
@@ -230,6 +258,12 @@ def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: st
         grad_scale = 1.0 / max(N, 1)
     if _lib.PROFILE is not None or _lib.TIMELINE is not None:
         _lib.CURRENT_TAG = ("nce", N, K, P)
+    if shards is not None:   # (emb_ptrs, bias_ptrs, R): row-sharded output tables in peer memory
+        emb_ptrs, bias_ptrs, R = shards
+        call("map_nce_fwd_sharded", inp.data_ptr(), N, P, K, target.data_ptr(), noise.data_ptr(), emb_ptrs, bias_ptrs, R,
+             logq.data_ptr(), float(norm_term), _lib.NCE_LOSS[loss_type], float(grad_scale), logits.data_ptr(),
+             _ptr(ids_out), loss_pos.data_ptr(), dz.data_ptr(), _ptr(d_input), _ptr(acc_count), _stream())
+        return logits, ids_out, loss_pos, dz, d_input
     call("map_nce_fwd", inp.data_ptr(), N, P, K, target.data_ptr(), noise.data_ptr(), emb.data_ptr(), bias.data_ptr(),
          logq.data_ptr(), emb.shape[0], float(norm_term), _lib.NCE_LOSS[loss_type], float(grad_scale), logits.data_ptr(),
          _ptr(ids_out), loss_pos.data_ptr(), dz.data_ptr(), _ptr(d_input), _ptr(acc_count), _stream())

@@ -35,16 +35,17 @@ def _setup(pt_type, B, seed=0):
     return BaseModel.from_config(Config.from_dict(cfg)), X, V
 
 
-def _rank_main(rank, world, port, pt_type, Bl, out_path):
+def _rank_main(rank, world, port, pt_type, Bl, out_path, exchange, opt_mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from map_code_b200.dist import ShardedFusedStep
+        from map_code_b200 import dist as mdist
+        cls = mdist.ShardedFusedStep if exchange == "p2p" else mdist.CollectiveShardedFusedStep
         model, X, V = _setup(pt_type, Bl * world)
         model.cuda()
-        eng = ShardedFusedStep(model, world=world, rank=rank, batch_size=Bl, mask_ratio=0.1, lr=1e-3, weight_decay=5e-2, sched="cosine",
-                               warmup_steps=1, total_steps=10, seed=42, optimizer_mode="dense_exact", x_train=X.cuda())
+        eng = cls(model, world=world, rank=rank, batch_size=Bl, mask_ratio=0.1, lr=1e-3, weight_decay=5e-2, sched="cosine",
+                  warmup_steps=1, total_steps=10, seed=42, optimizer_mode=opt_mode, x_train=X.cuda())
         losses = []
         for s in range(3):
             gb = X[s * Bl * world:(s + 1) * Bl * world]
@@ -57,19 +58,22 @@ def _rank_main(rank, world, port, pt_type, Bl, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("pt_type", ["MFP", "RFD"])
-def test_sharded_step_equals_single_gpu(pt_type, tmp_path):
+@pytest.mark.parametrize("pt_type,exchange,opt_mode", [("MFP", "p2p", "dense_exact"), ("MFP", "p2p", "sparse"), ("RFD", "p2p", "dense_exact"),
+                                                       ("MFP", "nccl", "dense_exact"), ("RFD", "nccl", "dense_exact")])
+def test_sharded_step_equals_single_gpu(pt_type, exchange, opt_mode, tmp_path):
+    """exchange = p2p: tables in NVLink peer memory (direct remote gathers + owner-side gradient pull, the default path);
+    nccl: the fixed-size collective variant.  Both must reproduce the single-GPU step on the concatenated batch."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from map_code_b200.engine import FusedStep
     world, Bl = 2, 256
     out = str(tmp_path / "sharded.pt")
-    mp.spawn(_rank_main, args=(world, _free_port(), pt_type, Bl, out), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, _free_port(), pt_type, Bl, out, exchange, opt_mode), nprocs=world, join=True)
     got = torch.load(out)
     model, X, V = _setup(pt_type, Bl * world)
     model.cuda()
     eng = FusedStep(model, batch_size=Bl * world, mask_ratio=0.1, lr=1e-3, weight_decay=5e-2, sched="cosine", warmup_steps=1,
-                    total_steps=10, seed=42, optimizer_mode="dense_exact", use_graph=False, x_train=X.cuda())
+                    total_steps=10, seed=42, optimizer_mode=opt_mode, use_graph=False, x_train=X.cuda())
     sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     for s in range(3):
         eng.step(X[s * Bl * world:(s + 1) * Bl * world].contiguous().cuda())
