@@ -304,6 +304,13 @@ class ShardedFusedStep(FusedStep):
         self._full_shapes: Dict[str, int] = {}
         super().__init__(model, **kw)
         self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        # barriers travel on their own communicator: collectives of ONE communicator execute in issue order, and the barriers
+        # must not queue behind the 23 MB dense all-reduce that overlaps the embedding merge
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        self.bar_group = dist.new_group(ranks=ranks, backend="nccl")
+        if self.multi_stream:
+            for k in ("nce", "comm"):
+                self.streams[k] = torch.cuda.Stream(device=self.dev, priority=-1)
 
     # -- setup: shards, peer-visible compact gradients, merge plans
     def _shard_param(self, name: str, param: torch.nn.Parameter) -> PeerBuffer:
@@ -374,7 +381,7 @@ class ShardedFusedStep(FusedStep):
     def _barrier(self):
         """stream-ordered barrier over the ranks (a 4-byte all-reduce): everything every rank issued before it on the calling
         stream is complete and visible to peer loads after it"""
-        dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.bar_group)
         _lib.mark("nccl_barrier")
 
     def _merge(self, tables):
@@ -412,8 +419,9 @@ class ShardedFusedStep(FusedStep):
         ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, None, None, crit.logprob_noise, self.norm_term, self.loss_type,
                     grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all, loss_pos=self.loss_pos, dz=self.dz,
                     d_input=self.d_sel, acc_count=self.acc_count, shards=(te.shard.ptrs, tb.shard.ptrs, self.world))
-        self._fork("tab")
-        with self._on("tab"):
+        # the NCE table-gradient chain has its own stream: the embedding backward (which joins 'tab') must not wait for it
+        self._fork("nce")
+        with self._on("nce"):
             ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
             te.plan.run(self.ids_all.view(-1))
             te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad.view(-1))
@@ -422,7 +430,17 @@ class ShardedFusedStep(FusedStep):
             self._barrier()
             self._merge([te, tb])
 
+    def _join_streams(self):
+        for name in self.streams:   # the NCE merge chain keeps running; the optimizer joins it
+            if name != "nce":
+                self._join(name)
+
     def reduce_gradients(self):
+        # dense gradients: one all-reduce on the 'comm' stream, overlapping the embedding merge below
+        self._fork("comm")
+        with self._on("comm"):
+            dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
+            _lib.mark("nccl_all_reduce", ("bytes", self.grad_flat.numel() * 4))
         self._barrier()          # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
         self._merge([self.tables["embed.embedding.weight"]])
 
@@ -430,14 +448,16 @@ class ShardedFusedStep(FusedStep):
         from . import ops
         b1, b2 = self.betas
         ops.adamw_hyper_step(self.hyper, self.step_counter, self.lr, b1, b2, self.eps, self.sched, self.warmup_steps, self.total_steps)
+        self._join("nce")
         for t in self.tables.values():
             if self.optimizer_mode == "sparse":
                 ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
             else:
                 ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
-        # after the table updates: the completion of this all-reduce on any rank implies every rank's shards are up to date
-        dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
-        _lib.mark("nccl_all_reduce", ("bytes", self.grad_flat.numel() * 4))
+        # end-of-step barrier: every rank's pulls are complete (compact gradients may be overwritten) and every shard is
+        # up to date (the next step's gathers may read it)
+        self._barrier()
+        self._join("comm")
         ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
 
     def dense_table_grad(self, name: str) -> torch.Tensor:
