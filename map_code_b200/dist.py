@@ -222,6 +222,35 @@ class CollectiveShardedFusedStep(FusedStep):
         return sd
 
 
+# ------------------------------------------------------------------------------------------------ owner-side merge (layout)
+def merge_key_layout(world: int, n_shard_rows: int):
+    """(shift, key_bits) of the merge keys  ((id // R) << shift) | source_rank  built by map_owned_compact: the source rank
+    sits in the low `shift` bits so that a stable sort orders the contributions of one row by source rank."""
+    shift = max(0, (world - 1).bit_length())
+    return shift, max(1, ((n_shard_rows << shift) - 1).bit_length())
+
+
+def peer_merge_torch(uniq_lists: List[torch.Tensor], grad_lists: List[torch.Tensor], world: int, rank: int, n_shard_rows: int):
+    """torch restatement of the owner-side pull (map_owned_compact -> map_dedup_ids_ex(seg_shift) -> map_segment_reduce_rows_ex
+    over peer rows) for the CPU tests: uniq_lists[s] / grad_lists[s] are rank s's sorted unique ids and compact gradient rows.
+    Returns (local_rows [U] ascending, merged_grad [U, D]); contributions of a row are summed in source-rank order."""
+    shift, _ = merge_key_layout(world, n_shard_rows)
+    keys, rows = [], []
+    for s_, (u, g) in enumerate(zip(uniq_lists, grad_lists)):
+        mine = (u % world) == rank
+        keys.append(((u[mine] // world) << shift) | s_)
+        rows.append(g[mine])
+    keys, rows = torch.cat(keys), torch.cat(rows)
+    order = torch.argsort(keys, stable=True)
+    keys, rows = keys[order], rows[order]
+    local = keys >> shift
+    uniq, inv = torch.unique_consecutive(local, return_inverse=True)
+    merged = torch.zeros(uniq.numel(), rows.shape[1], dtype=rows.dtype)
+    for i in range(keys.numel()):  # explicit order: exactly the order the kernel adds in
+        merged[inv[i]] += rows[i]
+    return uniq, merged
+
+
 # ------------------------------------------------------------------------------------------------ NVLink peer memory
 class PeerBuffer:
     """One allocation per rank, mapped into every rank of the node: `local` is this rank's tensor, `ptrs` a ctypes array of the
@@ -353,8 +382,8 @@ class ShardedFusedStep(FusedStep):
         m.keys = torch.zeros(R * cap, dtype=torch.int64, device=self.dev)
         m.src = torch.zeros(R * cap, dtype=torch.int32, device=self.dev)
         m.n_owned = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        shift = max(0, (R - 1).bit_length())
-        m.plan = ops.DedupPlan(R * cap, shard_rows_ << shift, self.dev, seg_shift=shift, n_dev=m.n_owned)
+        shift, bits = merge_key_layout(R, shard_rows_)
+        m.plan = ops.DedupPlan(R * cap, 1 << bits, self.dev, seg_shift=shift, n_dev=m.n_owned)
         return m
 
     def _make_embed_table(self):

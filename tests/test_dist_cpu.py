@@ -109,6 +109,33 @@ def _embedding_case(rank, world):
     assert torch.equal(unshard_table([parts[r] for r in range(world)], V), table)
 
 
+def _peer_merge_case(rank, world):
+    """The default multi-GPU path (tables in NVLink peer memory): every rank dedups its OWN occurrences, the owner of a row
+    pulls the matching entries of all ranks' compact lists and sums them in source-rank order.  Peer memory is emulated by an
+    all_gather_object of the lists; the result must equal the dense reference gradient of the global batch."""
+    from map_code_b200.dist import merge_key_layout, peer_merge_torch, shard_rows
+    g, V, D, P, K, F, Bl, L, table, emb, bias, fc = _problem()
+    ids_all = torch.randint(0, V, (world * Bl, F), generator=g)
+    ids_all[:, 0] = 3
+    dE_all = torch.randn(world * Bl, F * D, generator=g)
+    ids = ids_all[rank * Bl:(rank + 1) * Bl].reshape(-1)
+    dE = dE_all[rank * Bl:(rank + 1) * Bl].reshape(-1, D)
+    uniq, inv = torch.unique(ids, return_inverse=True)                       # local dedup (sorted ascending, like the radix sort)
+    compact = torch.zeros(uniq.numel(), D).index_add_(0, inv, dE)
+    lists = [None] * world
+    dist.all_gather_object(lists, (uniq, compact))                           # "peer loads"
+    n_rows = shard_rows(V, world)
+    shift, bits = merge_key_layout(world, n_rows)
+    assert (1 << shift) >= world and ((n_rows - 1) << shift | (world - 1)) < (1 << bits)
+    rows, merged = peer_merge_torch([l[0] for l in lists], [l[1] for l in lists], world, rank, n_rows)
+    ref = torch.zeros(V, D).index_add_(0, ids_all.view(-1), dE_all.view(-1, D))[rank::world]
+    touched = torch.zeros(V, dtype=torch.bool)
+    touched[ids_all.view(-1)] = True
+    want_rows = torch.nonzero(touched[rank::world]).view(-1)
+    assert torch.equal(rows, want_rows)                                       # exactly the owned rows the global batch touched
+    torch.testing.assert_close(merged, ref[want_rows], rtol=1e-5, atol=1e-5)
+
+
 def _nce_case(rank, world):
     from map_code_b200.dist import ShardExchange, shard_table
     g, V, D, P, K, F, Bl, L, table, emb, bias, fc = _problem()
@@ -188,3 +215,11 @@ def test_shard_table_roundtrip():
     t = torch.arange(35.0).view(7, 5)
     for R in (1, 2, 3, 4, 8):
         assert torch.equal(unshard_table([shard_table(t, R, r) for r in range(R)], 7), t)
+
+
+def test_peer_memory_merge_world2():
+    run2(_peer_merge_case)
+
+
+def test_peer_memory_merge_world3_uneven():
+    run2(_peer_merge_case, world=3)

@@ -556,3 +556,51 @@ def test_gemm_tcgen05_strided_views(ops):
     want = torch.relu(X.double() @ W.double().t() + b.double())
     _check_tf32(final[:, 624:].cpu().double(), want, 624, scale=1 / 25)
     assert final[:, :624].abs().sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ K13b peer-memory path
+@pytest.mark.parametrize("R", [1, 2, 3, 8])
+def test_peer_sharded_gather_and_merge_single_process(ops, R):
+    """The peer-memory kernels with all R 'ranks' emulated on one GPU (the pointer tables simply point at local buffers):
+    sharded gather == plain gather (bit-exact), and owned_compact -> dedup(seg_shift, device-side n) -> peer segment reduce
+    == the torch restatement in map_code_b200/dist.py (same summation order)."""
+    import ctypes as C
+    from map_code_b200.dist import merge_key_layout, peer_merge_torch, shard_rows, shard_table
+    g = torch.Generator().manual_seed(R)
+    V, D, cap = 5003, 16, 700
+    table = torch.randn(V, D, generator=g)
+    shards = [dev(shard_table(table, R, r)) for r in range(R)]
+    ptrs = (C.c_void_p * R)(*[s.data_ptr() for s in shards])
+    ids = torch.randint(0, V, (4096,), generator=g)
+    out = torch.empty(ids.numel(), D, device="cuda")
+    ops.emb_gather_sharded(ptrs, R, V, D, dev(ids), out)
+    assert torch.equal(out.cpu(), table[ids])
+    # per-"rank" compact lists (sorted unique ids, gradient rows), as the local dedup of each rank leaves them
+    uniq, grads, n_dev = [], [], []
+    for s in range(R):
+        u = torch.unique(torch.cat([torch.randint(0, V, (cap - 50,), generator=g), torch.tensor([3, 4, 5])]))
+        gr = torch.randn(cap, D, generator=g)
+        ub = torch.full((cap,), -7, dtype=torch.int64)
+        ub[:u.numel()] = u
+        uniq.append(dev(ub)); grads.append(dev(gr)); n_dev.append(torch.tensor([u.numel()], dtype=torch.int32, device="cuda"))
+    uptr = (C.c_void_p * R)(*[t.data_ptr() for t in uniq])
+    nptr = (C.c_void_p * R)(*[t.data_ptr() for t in n_dev])
+    gptr = (C.c_void_p * R)(*[t.data_ptr() for t in grads])
+    n_rows = shard_rows(V, R)
+    shift, bits = merge_key_layout(R, n_rows)
+    for rank in range(R):
+        keys = torch.zeros(R * cap, dtype=torch.int64, device="cuda")
+        src = torch.zeros(R * cap, dtype=torch.int32, device="cuda")
+        n_owned = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.owned_compact(uptr, nptr, R, rank, cap, keys, src, n_owned)
+        plan = ops.DedupPlan(R * cap, 1 << bits, "cuda", seg_shift=shift, n_dev=n_owned)
+        plan.run(keys)
+        merged = torch.zeros(R * cap, D, device="cuda")
+        plan.reduce_peer_rows(gptr, R, cap, D, src, out=merged)
+        torch.cuda.synchronize()
+        want_rows, want = peer_merge_torch([uniq[s].cpu()[:int(n_dev[s])] for s in range(R)],
+                                           [grads[s].cpu()[:int(n_dev[s])] for s in range(R)], R, rank, n_rows)
+        U = int(plan.n_unique)
+        assert U == want_rows.numel() and int(n_owned) == sum(int(((uniq[s].cpu()[:int(n_dev[s])] % R) == rank).sum()) for s in range(R))
+        assert torch.equal(plan.uniq[:U].cpu(), want_rows)
+        torch.testing.assert_close(merged[:U].cpu(), want, rtol=1e-6, atol=1e-6)
