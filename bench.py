@@ -316,8 +316,6 @@ def main_ours(args):
     X_dev = X_train.to(dev)
     trainer = Trainer(model, model.config, targs, DS(X_dev), DS(X_dev))
     total_steps = 100000
-    if world > 1 and WORKLOAD == "c4":
-        raise SystemExit("c4 (DeepFM) runs on one GPU in this revision: the first-order table is not row-sharded yet")
     if world > 1:
         from map_code_b200 import dist as mdist
         eng = mdist.make_sharded_step(trainer, total_steps, 0, world, rank)

@@ -193,7 +193,8 @@ int map_bce_logits_fwd(const float* logits, const float* labels, int64_t n, floa
 
 /* ------------------------------------------------------------------ K11  FM second-order + LR term (DeepFM)
  * replaces LR.forward (code/models.py:137-143) + InnerProductLayer product_sum (code/layers.py:125-131):
- * out[b] = sum_f w[ids[b,f]] + lr_bias + 0.5 * sum_d ((sum_f e[b,f,d])^2 - sum_f e[b,f,d]^2) */
+ * out[b] = sum_f w[ids[b,f]] + lr_bias + 0.5 * sum_d ((sum_f e[b,f,d])^2 - sum_f e[b,f,d]^2)
+ * ids == NULL: lr_w holds one weight per occurrence [B*F] (already gathered, e.g. from a row-sharded table). */
 int map_fm_lr_fwd(const float* feat_embed, const int64_t* ids, const float* lr_w, const float* lr_bias, int64_t B,
                   int F, int D, float* out, int64_t ld_out, map_stream_t stream);
 /* d_embed[b,f,d] (+)= g[b] * (sum_f' e[b,f',d] - e[b,f,d]) ; d_w_occ[b*F+f] = g[b] (per-occurrence LR grad, fed to the

@@ -370,6 +370,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    // Programmatic dependent launch: everything above (barrier init, tensor-map prefetch, TMEM allocation) may overlap the
+    // tail of the previous kernel of the stream; nothing below may start before that kernel has completed and flushed
+    // (every global read of this kernel — TMA operand loads and the epilogue's prefetches — is after this point).  The next
+    // kernel of the stream is released right away: its CTAs become resident as ours retire and then wait at this same line.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (trace != nullptr && threadIdx.x == 0) trace[2] = (unsigned long long)clock64();
 
     if (warp == 0) {
@@ -683,6 +689,26 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
     }
     dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)p.split_k);
     p.trace = ((int64_t)n_tiles * m_tiles * p.split_k <= g_trace_records) ? g_trace_buf : nullptr;
-    kernel<<<grid, kGemmThreads, smem_bytes, st>>>(tmap_a, tmap_b, p);
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("MAP_B200_PDL");
+        use_pdl = (e != nullptr && atoi(e) != 0) ? 1 : 0;  // opt-in: measured neutral-to-negative on the step (r01f)
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_b, p);
+    if (le != cudaSuccess) {
+        set_error("map_gemm_tf32_tcgen05: launch failed: %s", cudaGetErrorString(le));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
     return check_launch("map_gemm_tf32_tcgen05");
 }

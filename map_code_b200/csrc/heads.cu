@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) fm_lr_fwd_kernel(const float* __restrict_
         fm += s * s - sq;
     }
     float lr = 0.f;
-    for (int f = lane; f < F; f += 32) lr += __ldg(w + ids[b * F + f]);
+    for (int f = lane; f < F; f += 32) lr += (ids != nullptr) ? __ldg(w + ids[b * F + f]) : __ldg(w + b * F + f);  // ids == NULL: w is per occurrence
     const float tot = warp_sum(0.5f * fm + lr);
     if (lane == 0) out[b * ld_out] = tot + lr_bias[0];
 }
@@ -322,7 +322,7 @@ extern "C" int map_transpose_f32(const float* in, int64_t ld_in, int64_t M, int6
 extern "C" int map_fm_lr_fwd(const float* feat_embed, const int64_t* ids, const float* lr_w, const float* lr_bias, int64_t B, int F,
                              int D, float* out, int64_t ld_out, map_stream_t stream) {
     using namespace mapb;
-    MAP_REQUIRE(feat_embed && ids && lr_w && lr_bias && out && B > 0 && F > 0 && D > 0, "map_fm_lr_fwd: bad argument");
+    MAP_REQUIRE(feat_embed && lr_w && lr_bias && out && B > 0 && F > 0 && D > 0, "map_fm_lr_fwd: bad argument");
     fm_lr_fwd_kernel<<<(unsigned)ceil_div(B * 32, 256), 256, 0, as_stream(stream)>>>(feat_embed, ids, lr_w, lr_bias, B, F, D, out, ld_out);
     return check_launch("map_fm_lr_fwd");
 }

@@ -327,8 +327,6 @@ class ShardedFusedStep(FusedStep):
         kw.setdefault("use_graph", False)
         kw["row0"] = rank * B
         kw["global_batch"] = B * world
-        if model.model_name.lower() == "deepfm":
-            raise NotImplementedError("DeepFM's first-order table is not row-sharded yet: run DeepFM on one GPU")
         self.pm = PeerMemory(world, rank, next(model.parameters()).device, group)
         self._full_shapes: Dict[str, int] = {}
         super().__init__(model, **kw)
@@ -395,6 +393,22 @@ class ShardedFusedStep(FusedStep):
         t.grad_owned = torch.zeros(self.world * n, t.D, dtype=torch.float32, device=self.dev)
         self.tables[name] = t
 
+    def _make_lr_table(self):
+        """DeepFM's first-order table lr_layer.embed_w [V,1]: same id stream as the embedding -> same plan and merge"""
+        name = "lr_layer.embed_w.weight"
+        te = self.tables["embed.embedding.weight"]
+        t = self._peer_table(name, self.lr_w, self.B * self.F, te.plan)
+        t.merge = te.merge
+        t.grad_owned = torch.zeros(self.world * self.B * self.F, 1, dtype=torch.float32, device=self.dev)
+        self.tables[name] = t
+        self.w_occ = torch.zeros(self.B * self.F, dtype=torch.float32, device=self.dev)
+
+    def _lr_fm_forward(self, ids, out, ld_out):
+        from . import ops
+        t = self.tables["lr_layer.embed_w.weight"]
+        ops.emb_gather_sharded(t.shard.ptrs, self.world, t.V_full, 1, ids, out=self.w_occ)   # remote 4-byte rows over NVLink
+        ops.fm_lr_fwd(self.X0.view(self.B, self.F, self.D), None, self.w_occ, self.lr_b.data, out=out, ld_out=ld_out)
+
     def _make_nce_tables(self):
         crit = self.model.mfp_criterion
         n_occ = max(self.N, 1) * (self.K + 1)
@@ -437,6 +451,9 @@ class ShardedFusedStep(FusedStep):
         self._join("tab")
         t = self.tables["embed.embedding.weight"]
         t.plan.reduce_rows(self.dE, self.D, out=t.grad)
+        if self.has_fm:
+            tl = self.tables["lr_layer.embed_w.weight"]
+            tl.plan.reduce_rows(self.d_w_occ, 1, out=tl.grad)
 
     def _nce_core(self):
         from . import ops
@@ -471,7 +488,7 @@ class ShardedFusedStep(FusedStep):
             dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
             _lib.mark("nccl_all_reduce", ("bytes", self.grad_flat.numel() * 4))
         self._barrier()          # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
-        self._merge([self.tables["embed.embedding.weight"]])
+        self._merge([self.tables[n] for n in ("embed.embedding.weight", "lr_layer.embed_w.weight") if n in self.tables])
 
     def optimizer_step(self):
         from . import ops

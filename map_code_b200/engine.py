@@ -390,10 +390,9 @@ class FusedStep:
         self._embed_lookup(ids)
         if self.has_fm:  # lr_fm = LR(ids) + FM2(E): written straight into its column of `final` (pretrain) or kept apart (CTR)
             if self.cfg.pretrain:
-                ops.fm_lr_fwd(self.X0.view(B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=self.final[:, self.fm_col:],
-                              ld_out=self.ld_final)
+                self._lr_fm_forward(ids, self.final[:, self.fm_col:], self.ld_final)
             else:
-                ops.fm_lr_fwd(self.X0.view(B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=self.lr_fm, ld_out=1)
+                self._lr_fm_forward(ids, self.lr_fm, 1)
         nh = len(self.mlp)
         if nh:  # MLP tower on its own stream, concurrent with CrossNet (both only read X0)
             self._fork("mlp")
@@ -410,6 +409,9 @@ class FusedStep:
                        aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i])
         if nh:
             self._join("mlp")
+
+    def _lr_fm_forward(self, ids, out, ld_out):
+        ops.fm_lr_fwd(self.X0.view(self.B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=out, ld_out=ld_out)
 
     def _backward_backbone(self, head_W, dHead, n_head):
         """head_W [n_head, final_dim] is the weight of the first head layer, dHead [B, n_head] the gradient at its

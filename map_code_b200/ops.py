@@ -322,7 +322,7 @@ def fm_lr_fwd(feat_embed, ids, lr_w, lr_bias, out=None, ld_out: int = 1):
     B, F, D = feat_embed.shape
     if out is None:
         out = torch.empty(B, 1, dtype=torch.float32, device=feat_embed.device)
-    call("map_fm_lr_fwd", feat_embed.data_ptr(), ids.data_ptr(), lr_w.data_ptr(), lr_bias.data_ptr(), B, F, D, out.data_ptr(), ld_out, _stream())
+    call("map_fm_lr_fwd", feat_embed.data_ptr(), _ptr(ids), lr_w.data_ptr(), lr_bias.data_ptr(), B, F, D, out.data_ptr(), ld_out, _stream())
     return out
 
 
