@@ -194,6 +194,8 @@ def algorithmic(tag):
     if kind == "gemm":
         _, M, N, Kd = tag[:4]
         return 4.0 * (M * Kd + N * Kd + M * N), 2.0 * M * N * Kd
+    if kind == "gemm_group":   # one grouped launch: the sum over its problems
+        return (sum(4.0 * (M * Kd + N * Kd + M * N) for M, N, Kd in tag[1:]), sum(2.0 * M * N * Kd for M, N, Kd in tag[1:]))
     if kind == "gather":
         _, n, d = tag
         return n * (8 + 2 * 4 * d), 0.0
@@ -207,6 +209,40 @@ def algorithmic(tag):
         _, n, d = tag
         return n * (8 + 7 * 4 * d), 0.0
     return 0.0, 0.0
+
+
+def replay_kernel_class(records, reps=20):
+    """The launches of ONE kernel class of the step (same arguments, same order), back to back on one stream inside a CUDA
+    graph: device time per launch without the event / host-launch overhead of the eager profiling pass and without the
+    other streams' kernels competing for the SMs.  Returns (seconds per pass over the class, launches per pass)."""
+    lib = _lib_mod().load()
+    calls = [(getattr(lib, n), a) for n, a, _ in records]
+    s = torch.cuda.Stream()
+    st = s.cuda_stream
+
+    def body():
+        for fn, a in calls:
+            fn(*a[:-1], st)
+    with torch.cuda.stream(s):
+        body()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        body()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps, len(calls)
+
+
+def _lib_mod():
+    from map_code_b200 import _lib
+    return _lib
 
 
 def _stage(msg):
@@ -271,6 +307,11 @@ def main_ours(args):
     import faulthandler
     import torch.distributed as dist
     faulthandler.enable()  # a SIGSEGV in native code prints the Python stack of every thread
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 (NCCL prints its version banner there) are
+    # sent to stderr for the whole run, the result line goes to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     from map_code_b200 import _lib, synthetic as S
     from map_code_b200.arguments import Config, TrainingArguments
     from map_code_b200.models import BaseModel
@@ -392,6 +433,10 @@ def main_ours(args):
         eng.step(batch(i + 1))
     torch.cuda.synchronize()
     prof_records, _lib.PROFILE = _lib.PROFILE, None
+    _lib.RECORD = []
+    eng.step(batch(0))
+    torch.cuda.synchronize()
+    call_records, _lib.RECORD = _lib.RECORD, None
     eng.multi_stream = ms_flag
     if world > 1:
         dist.barrier()
@@ -433,10 +478,20 @@ def main_ours(args):
         top = breakdown[0]
         d = agg[top["kernel"]]
         if "gemm" in top["kernel"]:
-            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tensor_sustained"], "traffic": None,
-                    "note": f"TF32 operands (half the bf16 rate); peak = {pk['src']} sustained bf16 cuBLAS; aggregated over all tcgen05 GEMM launches of the step"}
+            # the tcgen05 GEMM class (grouped + single-problem launches): average launch duration from a graph replay of exactly
+            # these launches (world 1; the eager event-bracketed figure stays in kernels[])
+            gemm_recs = [r for r in call_records if "gemm_tf32" in r[0]]
+            fl = sum(algorithmic(r[2])[1] for r in gemm_recs)
+            if world == 1 and gemm_recs:
+                sec, n_l = replay_kernel_class(gemm_recs)
+            else:
+                sec, n_l = sum(agg[k]["ms"] for k in agg if "gemm_tf32" in k) * 1e-3 / args.profile_steps, len(gemm_recs)
+            ach = fl / sec / 1e12
+            roof = {"kernel": "map_gemm_tf32_group + map_gemm_tf32_tcgen05 (tcgen05 TF32 GEMM)", "bound": "tensor", "achieved": ach,
+                    "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"], "traffic": None,
+                    "launches_per_step": n_l, "us_per_launch": 1e6 * sec / max(n_l, 1), "flops_per_step": fl,
+                    "note": f"TF32 operands (nominal rate = half of bf16); peak = {pk['src']} sustained bf16 cuBLAS; achieved = algorithmic "
+                            "flops of all tcgen05 GEMM launches of one step / their device time, launches replayed back to back in a CUDA graph on one stream"}
         else:
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
@@ -469,7 +524,8 @@ def main_ours(args):
         "gpu_launches": (n_launch * args.steps) if n_launch else None, "launches_per_step": n_launch,
         "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown, "loss_after": loss_after,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(result_fd, (json.dumps(line) + "\n").encode())
     _shutdown(world)
 
 

@@ -245,6 +245,12 @@ typedef struct {
 int map_gemm_f32_simt(const map_gemm_args* args, map_stream_t stream);
 /* tcgen05 (kind::tf32) + TMA + TMEM, fp32 accumulate.  Requires 16-byte aligned base pointers and lda/ldb % 4 == 0. */
 int map_gemm_tf32_tcgen05(const map_gemm_args* args, map_stream_t stream);
+/* Up to 4 INDEPENDENT problems (none reads what another writes) in ONE persistent launch: one CTA per SM walks the tiles of
+ * all problems, two TMEM accumulators overlap each tile's epilogue with the next tile's main loop.  Same per-problem
+ * contract as map_gemm_tf32_tcgen05 (every problem must satisfy map_gemm_tf32_supported).  This is how the step issues the
+ * CrossNet / MLP layers of one depth (code/layers.py:187-201 run them back to back) and the dgrad + wgrad GEMMs that consume
+ * the same upstream gradient. */
+int map_gemm_tf32_group(const map_gemm_args* args, int count, map_stream_t stream);
 /* 1 if map_gemm_tf32_tcgen05 accepts these arguments (shape / alignment), else 0 */
 int map_gemm_tf32_supported(const map_gemm_args* args);
 /* Tuning aid (scripts/trace_gemm.py): while dev_buf != NULL every CTA of the following tcgen05 GEMM launches (grids of at

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "map_fm_lr_bwd": (_i, [_p, _p, _l, _l, _i, _i, _i, _p, _p, _p]),
     "map_gemm_f32_simt": (_i, [C.POINTER(GemmArgs), _p]),
     "map_gemm_tf32_tcgen05": (_i, [C.POINTER(GemmArgs), _p]),
+    "map_gemm_tf32_group": (_i, [C.POINTER(GemmArgs), _i, _p]),
     "map_gemm_tf32_supported": (_i, [C.POINTER(GemmArgs)]),
     "map_gemm_set_trace": (_i, [_p, _l]),
     "map_emb_gather_owned_f32": (_i, [_p, _l, _i, _p, _l, _i, _i, _p, _p]),
@@ -148,6 +149,7 @@ KERNELS_PER_CALL = {
 PROFILE = None        # set to a list: every call is bracketed by CUDA events -> (name, tag, start_event, end_event)
 CURRENT_TAG = None    # free-form shape tag set by ops.* just before a call (e.g. "4096x1000x624 tn")
 LAUNCHES = None       # set to a dict: name -> number of kernels launched
+RECORD = None         # set to a list: (name, args, tag) of every call (arguments kept alive), for replaying one kernel class alone
 TIMELINE = None       # set to dict(buf=<device int64 tensor>, ops=[]): a timestamp marker follows every call on its stream
 HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace", "map_p2p_alloc", "map_p2p_open", "map_p2p_close", "map_p2p_free"}
 
@@ -171,6 +173,10 @@ def call(name: str, *args):
     if LAUNCHES is not None:
         k = KERNELS_PER_CALL.get(name, 1)
         LAUNCHES[name] = LAUNCHES.get(name, 0) + (k(args) if callable(k) else k)
+    if RECORD is not None:
+        RECORD.append((name, args, CURRENT_TAG))
+        if PROFILE is None and TIMELINE is None:
+            CURRENT_TAG = None
     if PROFILE is not None:
         import torch
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -15,6 +15,7 @@
 // memory, so one CTA's epilogue overlaps the other's main loop.  Small wgrad grids use split-K with fp32 red.global.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -92,6 +93,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// same without the message (a printf call site makes every live register caller-saved around it)
+__device__ __forceinline__ void mbar_wait_quiet(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -99,6 +108,39 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
 }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {  // arrives on `bar` when all prior tcgen05.mma retire
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: one MMA of M = 256 spans the two SMs of a TPC; each CTA stages its own 128 rows of A and
+// HALF of the B tile, so a 128 x N output tile per CTA costs (128 + N/2) x 32 floats per K block instead of (128 + N) x 32
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_cta0(uint32_t addr) {  // shared::cluster address of `addr` in CTA 0 of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the transaction bytes are credited to `bar_cluster`, a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {  // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -122,9 +164,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 // instruction descriptor: D=f32 [4,6)=1 | A=tf32 [7,10)=2 | B=tf32 [10,13)=2 | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc_tf32(int block_n, int a_mn_major, int b_mn_major) {
+__device__ __forceinline__ uint32_t make_idesc_tf32(int block_n, int a_mn_major, int b_mn_major, int m = kBlockM) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+           ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
@@ -477,6 +519,245 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tf32_tcgen05_kernel(const _
     }
 }
 
+// ------------------------------------------------------------------------------------------------ grouped kernel
+// One launch = up to kMaxGroup INDEPENDENT GEMM problems (CrossNet layer i and MLP layer i, which both read X0; the dgrad
+// and wgrad GEMMs that consume the same upstream gradient).  The grid is the concatenation of the problems' tile grids, one
+// 128 x BLOCK_N tile per CTA, two co-resident CTAs per SM exactly like the single-problem kernel — the hardware block
+// scheduler keeps every SM slot busy across problem boundaries, and the ~6 us launch / drain gap that each of these small
+// GEMMs pays (4096 x 624 x 624 is ~10 us of kernel) is paid once per level of the step's dependency graph.
+// The epilogue kind of every slot is a template parameter (E0..E3, -1 = unused) and the slot's parameters are read from the
+// kernel parameter space with a STATIC index, so they stay constant-bank operands (a run-time indexed parameter block costs
+// ~35 registers per epilogue thread and spills at the 168 registers that two 192-thread CTAs per SM allow).
+// (A persistent one-CTA-per-SM variant with two TMEM accumulators was measured slower at these sizes: 2-4 tiles per CTA do
+// not amortise its pipeline fill and quantise badly over 148 SMs; profiles/r01g_gemm_group.txt.)
+constexpr int kMaxGroup = 4;
+
+struct GroupArgs {
+    CUtensorMap tmap[2 * kMaxGroup];  // A, B of slot i at [2i], [2i+1]
+    GemmParams p[kMaxGroup];
+    int tile_end[kMaxGroup];          // exclusive prefix sums of the per-slot tile counts
+    int n_tiles[kMaxGroup];
+    int m_tiles[kMaxGroup];
+    int count, total_tiles;
+    unsigned long long* trace;        // optional (map_gemm_set_trace): same record layout as the single-problem kernel
+};
+
+template <int EPI, bool SPLIT>
+__device__ __forceinline__ void epi_tile(const GemmParams& p, float* stg, int lane, uint32_t lane_addr, int row_base, int m0, int n0,
+                                         uint32_t full_bar, unsigned long long* trace) {
+    constexpr int CW = epi_chunk_w(EPI);
+    const bool full_tile = (m0 + kBlockM <= p.M) && (n0 + p.block_n <= p.N);
+    EpiRegs e;
+    if (p.block_n >= CW) epi_prefetch<EPI, CW>(p, lane, row_base, n0, full_tile, e);
+    else epi_prefetch<EPI, 16>(p, lane, row_base, n0, full_tile, e);
+    mbar_wait(full_bar, 0);
+    tcgen05_fence_after();
+    if (trace != nullptr && threadIdx.x == 64) trace[5] = (unsigned long long)clock64();
+    int c = 0;
+    for (; c + CW <= p.block_n; c += CW) {
+        epi_chunk<EPI, SPLIT, CW>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
+        if (c + 2 * CW <= p.block_n) epi_prefetch<EPI, CW>(p, lane, row_base, n0 + c + CW, full_tile, e);
+        else if (CW == 32 && c + CW < p.block_n) epi_prefetch<EPI, 16>(p, lane, row_base, n0 + c + CW, full_tile, e);
+    }
+    if (CW == 32 && c < p.block_n)  // block_n % 32 == 16
+        epi_chunk<EPI, SPLIT, 16>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
+    if (trace != nullptr && threadIdx.x == 64) trace[6] = (unsigned long long)clock64();
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_slot(const GemmParams& p, float* stg, int lane, uint32_t lane_addr, int row_base, int m0, int n0,
+                                         uint32_t full_bar, unsigned long long* trace) {
+    if constexpr (EPI == MAP_EPI_NONE) {
+        if (p.split_k > 1) epi_tile<MAP_EPI_NONE, true>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace);
+        else epi_tile<MAP_EPI_NONE, false>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace);
+    } else if constexpr (EPI > MAP_EPI_NONE) {
+        epi_tile<EPI, false>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace);
+    }
+}
+
+template <bool PAIR, int E0, int E1, int E2, int E3>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_tf32_group_kernel(const __grid_constant__ GroupArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // ---- which slot / tile is this CTA (all parameter reads below use static indices)
+    const int t = blockIdx.x;
+    int gi = 0, start = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxGroup - 1; ++i)
+        if (t >= g.tile_end[i]) {  // unused slots repeat total_tiles
+            gi = i + 1;
+            start = g.tile_end[i];
+        }
+    int block_n, trans_a, trans_b, num_k_blocks, k_blocks_total, stages, stage_bytes, b_tile_bytes, tmem_cols, nt, mt;
+#define MAP_LOAD_SLOT(i)                                                                                      \
+    {                                                                                                         \
+        block_n = g.p[i].block_n; trans_a = g.p[i].trans_a; trans_b = g.p[i].trans_b;                        \
+        num_k_blocks = g.p[i].num_k_blocks; k_blocks_total = g.p[i].k_blocks_total; stages = g.p[i].stages;   \
+        stage_bytes = g.p[i].stage_bytes; b_tile_bytes = g.p[i].b_tile_bytes; tmem_cols = g.p[i].tmem_cols;   \
+        nt = g.n_tiles[i]; mt = g.m_tiles[i];                                                                 \
+    }
+    if (gi == 0) MAP_LOAD_SLOT(0) else if (gi == 1) MAP_LOAD_SLOT(1) else if (gi == 2) MAP_LOAD_SLOT(2) else MAP_LOAD_SLOT(3)
+#undef MAP_LOAD_SLOT
+    const CUtensorMap* tmap_a = &g.tmap[2 * gi];
+    const CUtensorMap* tmap_b = tmap_a + 1;
+    const int local = t - start;
+    int n_tile, m_tile, ks;
+    if (PAIR) {  // m fastest (mt is even): CTAs 2i and 2i+1 of the grid = the two M halves of one 256 x block_n pair tile
+        m_tile = local % mt;
+        const int r = local / mt;
+        n_tile = r % nt;
+        ks = r / nt;
+    } else {
+        n_tile = local % nt;
+        const int r = local / nt;
+        m_tile = r % mt;
+        ks = r / mt;
+    }
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const int half_n = PAIR ? (block_n >> 1) : block_n;   // B columns this CTA stages
+    const int m0 = m_tile * kBlockM, n0 = n_tile * block_n, kb0 = ks * num_k_blocks;
+    int nkb = k_blocks_total - kb0;
+    if (nkb > num_k_blocks) nkb = num_k_blocks;
+
+    unsigned long long* trace = g.trace != nullptr ? g.trace + (size_t)kTraceWords * blockIdx.x : nullptr;
+    if (trace != nullptr && threadIdx.x == 0) {
+        trace[0] = globaltimer_ns();
+        trace[1] = (unsigned long long)clock64();
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(tmap_b) : "memory");
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        if (PAIR) {  // warp-collective in BOTH CTAs of the pair: the same columns are reserved on both SMs
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything of this CTA can arrive on them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    if (trace != nullptr && threadIdx.x == 0) trace[2] = (unsigned long long)clock64();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===================== TMA producer =====================
+            const uint32_t tx_bytes = (uint32_t)(kATileBytes + b_tile_bytes);
+            const int b_chunks = (half_n + 31) >> 5;
+            const int nb = n0 + (int)cta_rank * half_n;   // first B column of this CTA's share
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t a_dst = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
+                const uint32_t b_dst = a_dst + kATileBytes;
+                const int k0 = (kb0 + i) * kBlockK;
+                if (PAIR) {
+                    // both CTAs' loads complete on the LEADER's full barrier (its MMA reads both shared memories); the leader
+                    // expects the bytes of both
+                    if (cta_rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * tx_bytes);
+                    const uint32_t fb = mapa_cta0(smem_u32(&full_bar[s]));
+                    if (!trans_a) {
+                        tma_load_2d_pair(a_dst, tmap_a, fb, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockM / 32; ++c) tma_load_2d_pair(a_dst + c * 4096, tmap_a, fb, m0 + c * 32, k0);
+                    }
+                    if (!trans_b) {
+                        tma_load_2d_pair(b_dst, tmap_b, fb, k0, nb);
+                    } else {
+                        for (int c = 0; c < b_chunks; ++c) tma_load_2d_pair(b_dst + c * 4096, tmap_b, fb, nb + c * 32, k0);
+                    }
+                } else {
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, tx_bytes);
+                    if (!trans_a) {
+                        tma_load_2d(a_dst, tmap_a, fb, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockM / 32; ++c) tma_load_2d(a_dst + c * 4096, tmap_a, fb, m0 + c * 32, k0);
+                    }
+                    if (!trans_b) {
+                        tma_load_2d(b_dst, tmap_b, fb, k0, n0);
+                    } else {
+                        for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * 4096, tmap_b, fb, n0 + c * 32, k0);
+                    }
+                }
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && cta_rank == 0) {  // ===================== MMA issuer (the pair's leader) =====================
+            const uint32_t idesc = make_idesc_tf32(block_n, trans_a, trans_b, PAIR ? 2 * kBlockM : kBlockM);
+            const uint32_t a_lbo = trans_a ? 4096u : 16u, a_sbo = trans_a ? 512u : 1024u, a_adv = trans_a ? 1024u : 32u;
+            const uint32_t b_lbo = trans_b ? 4096u : 16u, b_sbo = trans_b ? 512u : 1024u, b_adv = trans_b ? 1024u : 32u;
+            const uint32_t a_lt = trans_a ? 1u : 2u, b_lt = trans_b ? 1u : 2u;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tcgen05_fence_after();
+                if (trace != nullptr && i == 0) trace[3] = (unsigned long long)clock64();
+                const uint32_t a_src = smem_base + (uint32_t)s * (uint32_t)stage_bytes;
+                const uint32_t b_src = a_src + kATileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint64_t da = make_smem_desc(a_src + k * a_adv, a_lbo, a_sbo, a_lt);
+                    const uint64_t db = make_smem_desc(b_src + k * b_adv, b_lbo, b_sbo, b_lt);
+                    if (PAIR) umma_tf32_pair(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+                    else umma_tf32(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+                }
+                if (PAIR) tcgen05_commit_pair(smem_u32(&empty_bar[s])); else tcgen05_commit(smem_u32(&empty_bar[s]));
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            if (PAIR) tcgen05_commit_pair(smem_u32(&tmem_full_bar)); else tcgen05_commit(smem_u32(&tmem_full_bar));
+            if (trace != nullptr) trace[4] = (unsigned long long)clock64();
+        }
+    } else {
+        // ===================== epilogue warps (staging tiles alias the ring, idle once tmem_full has fired) =====================
+        const int q = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + q * (32 * kStageLd);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int row_base = m0 + q * 32;
+        const uint32_t fb = smem_u32(&tmem_full_bar);
+        if (gi == 0) epi_slot<E0>(g.p[0], stg, lane, lane_addr, row_base, m0, n0, fb, trace);
+        else if (gi == 1) epi_slot<E1>(g.p[1], stg, lane, lane_addr, row_base, m0, n0, fb, trace);
+        else if (gi == 2) epi_slot<E2>(g.p[2], stg, lane, lane_addr, row_base, m0, n0, fb, trace);
+        else epi_slot<E3>(g.p[3], stg, lane, lane_addr, row_base, m0, n0, fb, trace);
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        trace[7] = (globaltimer_ns() & 0xFFFFFFFFFFFFull) | ((unsigned long long)smid << 48);
+    }
+    if (PAIR) cluster_sync_all();  // neither CTA retires (shared memory, barriers, TMEM) while the other may still reference it
+    if (warp == 1) {
+        tcgen05_fence_after();
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -711,4 +992,218 @@ extern "C" int map_gemm_tf32_tcgen05(const map_gemm_args* g, map_stream_t stream
         return MAP_ECUDA;
     }
     return check_launch("map_gemm_tf32_tcgen05");
+}
+
+// ------------------------------------------------------------------------------------------------ grouped launch (host)
+namespace mapb {
+
+typedef void (*GroupKernelFn)(const GroupArgs);
+struct GroupCombo {
+    int e[kMaxGroup];  // epilogue kinds in DESCENDING order, -1 = unused slot
+    GroupKernelFn fn[2];  // [0] one CTA per tile, [1] CTA pairs (cta_group::2)
+};
+#define MAP_COMBO(a, b, c, d) {{a, b, c, d}, {gemm_tf32_group_kernel<false, a, b, c, d>, gemm_tf32_group_kernel<true, a, b, c, d>}}
+// the epilogue combinations the step issues (engine.py): forward level (CrossNet + MLP layer), head dgrads + encoder wgrad,
+// backward level (two dgrads + two wgrads), and the dgrad + wgrad pairs of the MLP-only backbones
+static const GroupCombo kCombos[] = {
+    MAP_COMBO(MAP_EPI_CROSS, MAP_EPI_BIAS_RELU, -1, -1),
+    MAP_COMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, -1),
+    MAP_COMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, MAP_EPI_NONE),
+    MAP_COMBO(MAP_EPI_CROSS_BWD, MAP_EPI_NONE, -1, -1),
+    MAP_COMBO(MAP_EPI_ADD3, MAP_EPI_NONE, -1, -1),
+    MAP_COMBO(MAP_EPI_ADD3, MAP_EPI_NONE, MAP_EPI_NONE, -1),
+    MAP_COMBO(MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, -1, -1),
+    MAP_COMBO(MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, MAP_EPI_NONE, -1),
+    MAP_COMBO(MAP_EPI_NONE, MAP_EPI_NONE, -1, -1),
+    MAP_COMBO(MAP_EPI_NONE, MAP_EPI_NONE, MAP_EPI_NONE, -1),
+    // single problems (pair mode only; without it they go through map_gemm_tf32_tcgen05)
+    MAP_COMBO(MAP_EPI_NONE, -1, -1, -1),
+    MAP_COMBO(MAP_EPI_BIAS, -1, -1, -1),
+    MAP_COMBO(MAP_EPI_BIAS_RELU, -1, -1, -1),
+    MAP_COMBO(MAP_EPI_MUL_RELUMASK, -1, -1, -1),
+    MAP_COMBO(MAP_EPI_ADD3, -1, -1, -1),
+};
+#undef MAP_COMBO
+constexpr int kNumCombos = (int)(sizeof(kCombos) / sizeof(kCombos[0]));
+
+static int find_combo(const int* e, int count) {
+    for (int c = 0; c < kNumCombos; ++c) {
+        bool ok = true;
+        for (int i = 0; i < kMaxGroup; ++i) ok = ok && kCombos[c].e[i] == (i < count ? e[i] : -1);
+        if (ok) return c;
+    }
+    return -1;
+}
+
+// CTA-pair tiles: 256 x block_n per pair.  Operand bytes per K block and CTA are 128 x 32 (A) + block_n/2 x 32 (B half), so wide
+// tiles are cheap: the widest block_n in [128, 256] that wastes the fewest padded columns; split-K so that a CTA's share of a
+// long reduction (wgrad, K = batch) is about as long as a dgrad tile's (32 K blocks).
+static TileChoice choose_tiles_pair(int N, int K, bool mn_major_b, bool allow_split) {
+    const int step = mn_major_b ? 32 : 16;
+    TileChoice best{step, 1};
+    int best_cols = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= step) {
+        const int cols = (int)ceil_div(N, bn) * bn;
+        if (cols < best_cols) {
+            best_cols = cols;
+            best.block_n = bn;
+        }
+    }
+    if (N < 128) best.block_n = (int)ceil_div(N, step) * step;
+    const int kb = (int)ceil_div(K, kBlockK);
+    if (allow_split && kb >= 64) {
+        best.split_k = (int)ceil_div(kb, 32);
+        if (best.split_k > 16) best.split_k = 16;
+    }
+    return best;
+}
+
+// launches sorted[0..count) (epilogue kinds descending) as ONE grouped kernel; combo = index into kCombos
+static int launch_group(const map_gemm_args* sorted, int count, int combo, bool pair, cudaStream_t st) {
+    GroupArgs ga{};
+    ga.count = count;
+    int total = 0, max_smem = 0;
+    for (int i = 0; i < count; ++i) {
+        const map_gemm_args* g = &sorted[i];
+        GemmParams& p = ga.p[i];
+        const bool allow_split = g->epilogue == MAP_EPI_NONE && g->colsum_out == nullptr;
+        const TileChoice tc = pair ? choose_tiles_pair(g->N, g->K, g->trans_b != 0, allow_split)
+                                   : choose_tiles(g->M, g->N, g->K, g->trans_b != 0, allow_split);
+        p.M = g->M; p.N = g->N; p.K = g->K;
+        p.trans_a = g->trans_a ? 1 : 0;
+        p.trans_b = g->trans_b ? 1 : 0;
+        p.block_n = tc.block_n;
+        p.epilogue = g->epilogue;
+        p.C = g->C; p.ldc = g->ldc;
+        p.bias = g->bias;
+        p.aux0 = g->aux0; p.ld_aux0 = g->ld_aux0;
+        p.aux1 = g->aux1; p.ld_aux1 = g->ld_aux1;
+        p.aux_out = g->aux_out; p.ld_aux_out = g->ld_aux_out;
+        p.aux2 = g->aux2; p.ld_aux2 = g->ld_aux2;
+        p.acc_out = g->acc_out; p.ld_acc_out = g->ld_acc_out;
+        p.acc_accumulate = g->acc_accumulate;
+        p.colsum_out = g->colsum_out;
+        const int half_n = pair ? p.block_n / 2 : p.block_n;   // B columns staged by one CTA
+        p.b_tile_bytes = p.trans_b ? ((half_n + 31) / 32) * 4096 : half_n * 128;
+        p.stage_bytes = (kATileBytes + p.b_tile_bytes + 1023) & ~1023;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
+        p.k_blocks_total = (int)ceil_div(g->K, kBlockK);
+        p.num_k_blocks = (int)ceil_div(p.k_blocks_total, tc.split_k);
+        p.split_k = (int)ceil_div(p.k_blocks_total, p.num_k_blocks);
+        int stages = (110 * 1024) / p.stage_bytes;   // two co-resident CTAs
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages > p.num_k_blocks) stages = p.num_k_blocks > 1 ? p.num_k_blocks : 1;
+        if (stages < 1) stages = 1;
+        p.stages = stages;
+        if (stages * p.stage_bytes > max_smem) max_smem = stages * p.stage_bytes;
+        p.trace = nullptr;
+        ga.m_tiles[i] = (int)ceil_div(g->M, kBlockM);
+        if (pair) ga.m_tiles[i] = (ga.m_tiles[i] + 1) & ~1;   // whole pairs: a padding tile is all out of bounds (zero-filled loads, no stores)
+        ga.n_tiles[i] = (int)ceil_div(g->N, p.block_n);
+        total += ga.m_tiles[i] * ga.n_tiles[i] * p.split_k;
+        ga.tile_end[i] = total;
+        int rc;
+        if (!p.trans_a) rc = make_tmap(&ga.tmap[2 * i], g->A, g->K, g->M, g->lda, kBlockM, false);
+        else rc = make_tmap(&ga.tmap[2 * i], g->A, g->M, g->K, g->lda, kBlockK, true);
+        if (rc != MAP_OK) return rc;
+        if (!p.trans_b) rc = make_tmap(&ga.tmap[2 * i + 1], g->B, g->K, g->N, g->ldb, half_n, false);
+        else rc = make_tmap(&ga.tmap[2 * i + 1], g->B, g->N, g->K, g->ldb, kBlockK, true);
+        if (rc != MAP_OK) return rc;
+        if (p.split_k > 1) {
+            if (cudaMemset2DAsync(g->C, (size_t)g->ldc * sizeof(float), 0, (size_t)g->N * sizeof(float), (size_t)g->M, st) != cudaSuccess) {
+                set_error("map_gemm_tf32_group: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MAP_ECUDA;
+            }
+        }
+    }
+    for (int i = count; i < kMaxGroup; ++i) ga.tile_end[i] = total;
+    ga.total_tiles = total;
+    if (max_smem < 4 * 32 * kStageLd * 4) max_smem = 4 * 32 * kStageLd * 4;  // the epilogue staging tiles alias the ring
+    const size_t smem_bytes = (size_t)max_smem + 1024;
+    const GroupKernelFn fn = kCombos[combo].fn[pair ? 1 : 0];
+    static bool attr_set[kNumCombos][2] = {};
+    if (!attr_set[combo][pair ? 1 : 0]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048) != cudaSuccess) {
+            set_error("map_gemm_tf32_group: cannot raise dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+            return MAP_ECUDA;
+        }
+        attr_set[combo][pair ? 1 : 0] = true;
+    }
+    ga.trace = (total <= g_trace_records) ? g_trace_buf : nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)total);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, fn, ga);
+    if (le != cudaSuccess) {
+        set_error("map_gemm_tf32_group: launch failed: %s", cudaGetErrorString(le));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
+    return check_launch("map_gemm_tf32_group");
+}
+
+// CTA pairs pay off when every problem has at least one full pair of M tiles and a tile-wide N
+static bool want_pair(const map_gemm_args* a, int count) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("MAP_B200_GEMM_PAIR");
+        enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }
+    if (!enabled) return false;
+    for (int i = 0; i < count; ++i)
+        if (a[i].M < 2 * kBlockM || a[i].N < 64) return false;
+    return true;
+}
+
+}  // namespace mapb
+
+extern "C" int map_gemm_tf32_group(const map_gemm_args* args, int count, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(args != nullptr && count >= 1 && count <= kMaxGroup, "map_gemm_tf32_group: count=%d must be in [1, %d]", count, kMaxGroup);
+    cudaStream_t st = as_stream(stream);
+    for (int i = 0; i < count; ++i) {
+        int rc = validate_gemm_args(&args[i], "map_gemm_tf32_group");
+        if (rc != MAP_OK) return rc;
+        if (!tf32_supported(&args[i], true)) return MAP_EUNSUPPORTED;
+        MAP_REQUIRE(args[i].epilogue >= MAP_EPI_NONE && args[i].epilogue <= MAP_EPI_ADD3, "map_gemm_tf32_group: unknown epilogue %d", args[i].epilogue);
+    }
+    // canonical order: epilogue kind descending (stable), which is how the instantiated combinations are listed
+    map_gemm_args sorted[kMaxGroup];
+    for (int i = 0; i < count; ++i) sorted[i] = args[i];
+    for (int i = 1; i < count; ++i)
+        for (int j = i; j > 0 && sorted[j].epilogue > sorted[j - 1].epilogue; --j) {
+            const map_gemm_args tmp = sorted[j]; sorted[j] = sorted[j - 1]; sorted[j - 1] = tmp;
+        }
+    // greedy cover: the longest prefix of what is left that is an instantiated combination goes out as one grouped launch,
+    // a problem no combination starts with goes through the single-problem kernel
+    int pos = 0;
+    while (pos < count) {
+        int e[kMaxGroup], len = 0, combo = -1;
+        for (int n = count - pos; n >= 1 && combo < 0; --n) {
+            for (int i = 0; i < n; ++i) e[i] = sorted[pos + i].epilogue;
+            combo = find_combo(e, n);
+            len = n;
+        }
+        const bool pair = combo >= 0 && want_pair(&sorted[pos], len);
+        int rc;
+        if (combo >= 0 && (len >= 2 || pair)) {
+            rc = launch_group(&sorted[pos], len, combo, pair, st);
+            pos += len;
+        } else {
+            rc = map_gemm_tf32_tcgen05(&sorted[pos], stream);
+            pos += 1;
+        }
+        if (rc != MAP_OK) return rc;
+    }
+    return MAP_OK;
 }

@@ -297,6 +297,19 @@ class FusedStep:
     def _gemm(self, *a, **k):
         return ops.gemm(*a, backend=self.gemm_backend, **k)
 
+    def _gemm_group(self, problems):
+        """independent GEMMs of one level of the step's dependency graph -> one grouped launch (ops.gemm_group)"""
+        problems = [pr for pr in problems if pr is not None]
+        if problems:
+            ops.gemm_group(problems, backend=self.gemm_backend)
+
+    def _wgrad_problem(self, dZ, X_in, layer_name, M, N, K):
+        """dW = dZ^T X as a problem of a grouped launch (the bias gradient comes from the colsum_out of the GEMM that wrote dZ)"""
+        wname = layer_name + ".weight"
+        if wname in self._pad_cols:  # column-padded head weight: compute on the aligned [N, ld_final] storage
+            return dict(A=dZ, B=self.final, C_out=self.grads_padded[wname], M=N, N=self.ld_final, K=M, trans_a=True, trans_b=True)
+        return dict(A=dZ, B=X_in, C_out=self.grads[wname], M=N, N=K, K=M, trans_a=True, trans_b=True)
+
     def _on(self, name):
         """context: issue on side stream `name` (or stay on the main stream when multi_stream is off)"""
         import contextlib
@@ -393,74 +406,80 @@ class FusedStep:
                 self._lr_fm_forward(ids, self.final[:, self.fm_col:], self.ld_final)
             else:
                 self._lr_fm_forward(ids, self.lr_fm, 1)
-        nh = len(self.mlp)
-        if nh:  # MLP tower on its own stream, concurrent with CrossNet (both only read X0)
-            self._fork("mlp")
-            with self._on("mlp"):
-                x, k = self.X0, in_dim
-                for i, layer in enumerate(self.mlp):         # layers.py:187-188, ReLU fused
-                    out = self.mlp_out if i == nh - 1 else self.Hs[i]
-                    self._gemm(x, layer.weight.data, out, B, H, k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data)
-                    x, k = out, H
-        nc = len(self.cross)
-        for i, layer in enumerate(self.cross):       # layers.py:197-201 with the product fused in the epilogue
-            out = self.cross_out if i == nc - 1 else self.Xc[i + 1]
-            self._gemm(self.Xc[i], layer.weight.data, out, B, in_dim, in_dim, epilogue=_lib.EPI_CROSS, bias=layer.bias.data,
-                       aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i])
-        if nh:
-            self._join("mlp")
+        nh, nc = len(self.mlp), len(self.cross)
+        # CrossNet layer i (layers.py:197-201, product fused in the epilogue) and MLP layer i (layers.py:187-188, ReLU fused) only
+        # depend on layer i-1 of their own tower: one grouped launch per depth
+        x, k = self.X0, in_dim
+        for i in range(max(nh, nc)):
+            probs = []
+            if i < nc:
+                out = self.cross_out if i == nc - 1 else self.Xc[i + 1]
+                layer = self.cross[i]
+                probs.append(dict(A=self.Xc[i], B=layer.weight.data, C_out=out, M=B, N=in_dim, K=in_dim, epilogue=_lib.EPI_CROSS,
+                                  bias=layer.bias.data, aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i]))
+            if i < nh:
+                out = self.mlp_out if i == nh - 1 else self.Hs[i]
+                layer = self.mlp[i]
+                probs.append(dict(A=x, B=layer.weight.data, C_out=out, M=B, N=H, K=k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data))
+                x, k = out, H
+            self._gemm_group(probs)
 
     def _lr_fm_forward(self, ids, out, ld_out):
         ops.fm_lr_fwd(self.X0.view(self.B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=out, ld_out=ld_out)
 
-    def _backward_backbone(self, head_W, dHead, n_head):
+    def _backward_backbone(self, head_W, dHead, n_head, head_wgrad=None):
         """head_W [n_head, final_dim] is the weight of the first head layer, dHead [B, n_head] the gradient at its
-        pre-activation.  Propagates into the towers and the embedding table."""
+        pre-activation, head_wgrad the (optional) weight-gradient problem of that layer: it consumes dHead like the two
+        tower dgrads and goes out in the same grouped launch.  Propagates into the towers and the embedding table.
+        CrossNet (autograd of layers.py:200, every elementwise stage inside a GEMM epilogue):
+          G_i = d(loss)/d(X_i);  dU_i = G_{i+1} * X0;  dX0 += G_{i+1} * U_i;  G_i = G_{i+1} + dU_i W_i;  db_i = colsum(dU_i)
+        the GEMM that produces G_{i+1} also writes dU_i, accumulates dX0 and db_i (MAP_EPI_CROSS_BWD); the last one adds
+        everything into dE (MAP_EPI_ADD3).  MLP: the gradient through each ReLU and the bias gradient (column sums of dZ) are
+        fused into the dgrad GEMM's epilogue.  One grouped launch per depth: {dgrad, wgrad} x {CrossNet, MLP}."""
         B, in_dim, H = self.B, self.in_dim, self.H
         nc, nh = len(self.cross), len(self.mlp)
         pref_c = "cross_net.cross_layers"
         pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
-        # ---- MLP tower (stream 'mlp'): the gradient through each ReLU and the bias gradient (column sums of dZ) are fused into
-        # the dgrad GEMM's epilogue
+        probs = [head_wgrad]
         if nh:
-            self._fork("mlp")
-            with self._on("mlp"):
-                dZ = self.dZ[nh - 1]
-                self._gemm(dHead, head_W[:, self.mlp_off:self.mlp_off + H], dZ, B, H, n_head, trans_b=True,
-                           epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out, colsum_out=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"])
-                for i in range(nh - 1, -1, -1):
-                    layer = self.mlp[i]
-                    x_in = self.X0 if i == 0 else self.Hs[i - 1]
-                    k_in = in_dim if i == 0 else H
-                    self._wgrad(dZ, x_in, f"{pref_m}.{3 * i}", B, H, k_in, bias_done=True)
-                    if i > 0:
-                        self._gemm(dZ, layer.weight.data, self.dZ[i - 1], B, k_in, H, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK,
-                                   aux0=self.Hs[i - 1], colsum_out=self.grads[f"{pref_m}.{3 * (i - 1)}.bias"])
-                        dZ = self.dZ[i - 1]
-                    else:
-                        self._gemm(dZ, layer.weight.data, self.dX0_mlp, B, k_in, H, trans_b=True)
-        # ---- CrossNet (main stream), autograd of layers.py:200 with every elementwise stage inside a GEMM epilogue:
-        #   G_{i} = d(loss)/d(X_i);  dU_i = G_{i+1} * X0;  dX0 += G_{i+1} * U_i;  G_i = G_{i+1} + dU_i W_i;  db_i = colsum(dU_i)
-        # The GEMM that produces G_{i+1} (the head dgrad for i = nc-1, the dgrad of layer i+1 otherwise) also writes dU_i,
-        # accumulates dX0 and db_i (MAP_EPI_CROSS_BWD); the last one adds everything into dE (MAP_EPI_ADD3).
+            probs.append(dict(A=dHead, B=head_W[:, self.mlp_off:self.mlp_off + H], C_out=self.dZ[nh - 1], M=B, N=H, K=n_head, trans_b=True,
+                              epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out, colsum_out=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"]))
         if nc:
-            self._gemm(dHead, head_W[:, self.cross_off:self.cross_off + in_dim], self.dUs[nc - 1], B, in_dim, n_head, trans_b=True,
-                       epilogue=_lib.EPI_CROSS_BWD, aux0=None, aux1=self.X0, aux2=self.U[nc - 1], aux_out=self.Gc[nc],
-                       acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"])
-            for i in range(nc - 1, -1, -1):
-                layer = self.cross[i]
-                self._wgrad(self.dUs[i], self.Xc[i], f"{pref_c}.{i}", B, in_dim, in_dim, bias_done=True)
-                if i > 0:
-                    self._gemm(self.dUs[i], layer.weight.data, self.dUs[i - 1], B, in_dim, in_dim, trans_b=True,
-                               epilogue=_lib.EPI_CROSS_BWD, aux0=self.Gc[i + 1], aux1=self.X0, aux2=self.U[i - 1], aux_out=self.Gc[i],
-                               acc_out=self.dX0_acc, acc_accumulate=True, colsum_out=self.grads[f"{pref_c}.{i - 1}.bias"])
+            probs.append(dict(A=dHead, B=head_W[:, self.cross_off:self.cross_off + in_dim], C_out=self.dUs[nc - 1], M=B, N=in_dim, K=n_head,
+                              trans_b=True, epilogue=_lib.EPI_CROSS_BWD, aux0=None, aux1=self.X0, aux2=self.U[nc - 1], aux_out=self.Gc[nc],
+                              acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"]))
+        self._gemm_group(probs)
+        last = []   # the final level: dE needs dX0_mlp, which the last MLP dgrad of the loop below produces
+        for s_ in range(max(nc, nh)):
+            ic, im = nc - 1 - s_, nh - 1 - s_
+            probs = []
+            if ic >= 0:
+                layer = self.cross[ic]
+                wg = self._wgrad_problem(self.dUs[ic], self.Xc[ic], f"{pref_c}.{ic}", B, in_dim, in_dim)
+                if ic > 0:
+                    probs.append(wg)
+                    probs.append(dict(A=self.dUs[ic], B=layer.weight.data, C_out=self.dUs[ic - 1], M=B, N=in_dim, K=in_dim, trans_b=True,
+                                      epilogue=_lib.EPI_CROSS_BWD, aux0=self.Gc[ic + 1], aux1=self.X0, aux2=self.U[ic - 1], aux_out=self.Gc[ic],
+                                      acc_out=self.dX0_acc, acc_accumulate=True, colsum_out=self.grads[f"{pref_c}.{ic - 1}.bias"]))
                 else:
-                    if nh:
-                        self._join("mlp")
-                    self._gemm(self.dUs[0], layer.weight.data, self.dE, B, in_dim, in_dim, trans_b=True, epilogue=_lib.EPI_ADD3,
-                               aux0=self.Gc[1], aux1=self.dX0_acc, aux2=self.dX0_mlp if nh else None)
+                    last.append(wg)
+                    last.append(dict(A=self.dUs[0], B=layer.weight.data, C_out=self.dE, M=B, N=in_dim, K=in_dim, trans_b=True,
+                                     epilogue=_lib.EPI_ADD3, aux0=self.Gc[1], aux1=self.dX0_acc, aux2=self.dX0_mlp if nh else None))
+            if im >= 0:
+                layer = self.mlp[im]
+                dZ = self.dZ[im]
+                x_in = self.X0 if im == 0 else self.Hs[im - 1]
+                k_in = in_dim if im == 0 else H
+                probs.append(self._wgrad_problem(dZ, x_in, f"{pref_m}.{3 * im}", B, H, k_in))
+                if im > 0:
+                    probs.append(dict(A=dZ, B=layer.weight.data, C_out=self.dZ[im - 1], M=B, N=k_in, K=H, trans_b=True,
+                                      epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.Hs[im - 1], colsum_out=self.grads[f"{pref_m}.{3 * (im - 1)}.bias"]))
+                else:
+                    probs.append(dict(A=dZ, B=layer.weight.data, C_out=self.dX0_mlp, M=B, N=k_in, K=H, trans_b=True))
+            self._gemm_group(probs)
+        if nc:
+            self._gemm_group(last)
         else:
-            self._join("mlp")
             ops.copy2d(self.dX0_mlp, self.dE)
         if self.has_fm:  # d(lr_fm) flows into the embeddings (FM term) and into the first-order table + its bias
             if self.cfg.pretrain:
@@ -491,21 +510,24 @@ class FusedStep:
         m = self.model
         enc_W, enc_b = m.feat_encoder.weight.data, m.feat_encoder.bias.data
         crit = m.mfp_criterion
-        self._gemm(self.final_v, enc_W, self.enc, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b)   # models.py:74
+        self._gemm_group([dict(A=self.final_v, B=enc_W, C_out=self.enc, M=B, N=F * P, K=self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b)])   # models.py:74
         ops.gather_slices(self.enc, self.mi, F, P, out=self.sel)                                                   # models.py:75
         self._join("tab")  # noise drawn on the 'tab' stream
         self._nce_core()
         # ---- backward of the encoder
         self.d_enc.zero_()
         ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
-        self._wgrad(self.d_enc, self.final_v, "feat_encoder", B, F * P, self.final_dim)
-        self._backward_backbone(enc_W, self.d_enc, F * P)
+        self._fork("dw")
+        with self._on("dw"):   # bias gradient of the encoder: off the critical path
+            ops.colsum(self.d_enc, out=self.grads["feat_encoder.bias"], ws=self.colsum_ws)
+        self._backward_backbone(enc_W, self.d_enc, F * P, head_wgrad=self._wgrad_problem(self.d_enc, self.final_v, "feat_encoder", B, F * P, self.final_dim))
 
     def _head_rfd(self):
         cfg, B, F, Fp = self.cfg, self.B, self.F, self.Fp
         P = cfg.proj_size
         l0 = getattr(self.model.pred_rfd, "0")
-        self._gemm(self.final_v, l0.weight.data, self.rfd_h, B, F * P, self.final_dim, epilogue=_lib.EPI_BIAS_RELU, bias=l0.bias.data)
+        self._gemm_group([dict(A=self.final_v, B=l0.weight.data, C_out=self.rfd_h, M=B, N=F * P, K=self.final_dim, epilogue=_lib.EPI_BIAS_RELU,
+                               bias=l0.bias.data)])
         self._gemm(self.rfd_h, self.W2p, self.rfd_logits_p, B, Fp, F * P, epilogue=_lib.EPI_BIAS, bias=self.b2p)   # models.py:80
         ops.copy2d(self.rfd_logits_p[:, :F], self.rfd_logits)
         ops.bce_logits(self.rfd_logits.view(-1), self.labels.view(-1), stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
@@ -515,12 +537,13 @@ class FusedStep:
         # backward
         self._fork("dw")
         with self._on("dw"):
-            self._gemm(self.d_logits_p, self.rfd_h, self.grads_padded["pred_rfd.2.weight"], Fp, F * P, B, trans_a=True, trans_b=True)
             ops.colsum(self.d_logits_p, out=self.grads_padded["pred_rfd.2.bias"].view(-1), ws=self.colsum_ws)
-        self._gemm(self.d_logits_p, self.W2p, self.d_h, B, F * P, Fp, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.rfd_h,
-                   colsum_out=self.grads["pred_rfd.0.bias"])
-        self._wgrad(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim, bias_done=True)
-        self._backward_backbone(l0.weight.data, self.d_h, F * P)
+        self._gemm_group([
+            dict(A=self.d_logits_p, B=self.rfd_h, C_out=self.grads_padded["pred_rfd.2.weight"], M=Fp, N=F * P, K=B, trans_a=True, trans_b=True),
+            dict(A=self.d_logits_p, B=self.W2p, C_out=self.d_h, M=B, N=F * P, K=Fp, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK,
+                 aux0=self.rfd_h, colsum_out=self.grads["pred_rfd.0.bias"])])
+        self._backward_backbone(l0.weight.data, self.d_h, F * P,
+                                head_wgrad=self._wgrad_problem(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim))
 
     def _head_ctr(self):
         B = self.B

@@ -48,7 +48,7 @@ def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tenso
         out = torch.empty(*ids.shape, D, dtype=torch.float32, device=table.device)
     if ids.numel() == 0:
         return out
-    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
         _lib.CURRENT_TAG = ("gather", ids.numel(), D)
     call("map_emb_gather_f32", table.data_ptr(), V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), _ptr(oob_flag), _stream())
     return out
@@ -57,7 +57,7 @@ def emb_gather(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tenso
 def emb_gather_sharded(shard_ptrs, R: int, V: int, D: int, ids: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """out[i,:] = shard[ids[i] % R][ids[i] // R, :]; shard_ptrs: ctypes array of R device base pointers (peer memory)."""
     _check(ids, torch.int64, "ids")
-    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
         _lib.CURRENT_TAG = ("gather", ids.numel(), D)
     call("map_emb_gather_sharded_f32", shard_ptrs, R, V, D, ids.data_ptr(), ids.numel(), out.data_ptr(), None, _stream())
     return out
@@ -95,7 +95,7 @@ class DedupPlan:
     def reduce_peer_rows(self, row_ptrs, n_peers: int, rows_per_peer: int, D: int, occ_map: torch.Tensor, out: torch.Tensor):
         """segment sums over rows that live in the R ranks' compact gradients (row_ptrs: ctypes array of R device pointers,
         peer memory): row code = occ_map[occurrence] = peer * rows_per_peer + row."""
-        if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+        if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
             _lib.CURRENT_TAG = ("segred_peer", self.n, D)
         call("map_segment_reduce_rows_ex", None, D, D, None, 1, self.occ_sorted.data_ptr(), self.seg_start.data_ptr(),
              self.n_unique.data_ptr(), self.n, _ptr(self.n_dev), occ_map.data_ptr(), row_ptrs, n_peers, rows_per_peer, out.data_ptr(),
@@ -106,7 +106,7 @@ class DedupPlan:
                     group: int = 1, out: Optional[torch.Tensor] = None, scalar_out: Optional[torch.Tensor] = None):
         if out is None:
             out = torch.empty(self.n, D, dtype=torch.float32, device=rows.device)
-        if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+        if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
             _lib.CURRENT_TAG = ("segred", self.n, D)
         call("map_segment_reduce_rows_ex", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
              self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, _ptr(self.n_dev), None, None, 0, 0,
@@ -150,7 +150,7 @@ def adamw_multi_tensor(table: torch.Tensor, n: int, max_elems: int, hyper: torch
 
 def adamw_sparse_rows(table, m, v, plan: DedupPlan, grad_compact, hyper, weight_decay: float):
     D = table.shape[1]
-    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
         _lib.CURRENT_TAG = ("sparse_adamw", plan.n, D)
     call("map_adamw_sparse_rows", table.data_ptr(), m.data_ptr(), v.data_ptr(), D, plan.uniq.data_ptr(), grad_compact.data_ptr(),
          plan.n_unique.data_ptr(), plan.n, hyper.data_ptr(), float(weight_decay), _stream())
@@ -256,7 +256,7 @@ def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: st
         d_input = torch.empty(N, P, dtype=torch.float32, device=dev)
     if grad_scale is None:
         grad_scale = 1.0 / max(N, 1)
-    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
         _lib.CURRENT_TAG = ("nce", N, K, P)
     if shards is not None:   # (emb_ptrs, bias_ptrs, R): row-sharded output tables in peer memory
         emb_ptrs, bias_ptrs, R = shards
@@ -343,12 +343,10 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
 
 
-def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
-         epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, aux2=None, acc_out=None,
-         acc_accumulate: bool = False, colsum_out=None, backend: Optional[str] = None):
-    """acc[m,n] = sum_k A[m,k]*B[n,k] with storage transposes; see include/map_b200.h.  Operands are 2-D row-major views
-    (row stride = leading dimension, so column slices of wider buffers work)."""
-    g = GemmArgs()
+def _gemm_args(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
+               epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, aux2=None, acc_out=None,
+               acc_accumulate: bool = False, colsum_out=None, g: Optional[GemmArgs] = None) -> GemmArgs:
+    g = GemmArgs() if g is None else g
     g.M, g.N, g.K = M, N, K
     g.trans_a, g.trans_b, g.epilogue = int(trans_a), int(trans_b), int(epilogue)
     g.A, g.lda = A.data_ptr(), _ld(A)
@@ -362,15 +360,57 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, 
     g.acc_out, g.ld_acc_out = (acc_out.data_ptr(), _ld(acc_out)) if acc_out is not None else (None, 0)
     g.acc_accumulate = int(bool(acc_accumulate))
     g.colsum_out = _ptr(colsum_out)
+    return g
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
+         epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, aux2=None, acc_out=None,
+         acc_accumulate: bool = False, colsum_out=None, backend: Optional[str] = None):
+    """acc[m,n] = sum_k A[m,k]*B[n,k] with storage transposes; see include/map_b200.h.  Operands are 2-D row-major views
+    (row stride = leading dimension, so column slices of wider buffers work)."""
+    g = _gemm_args(A, B, C_out, M, N, K, trans_a, trans_b, epilogue, bias, aux0, aux1, aux_out, aux2, acc_out, acc_accumulate, colsum_out)
     backend = backend or gemm_backend()
     lib = _lib.load()
-    if _lib.PROFILE is not None or _lib.TIMELINE is not None:
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
         _lib.CURRENT_TAG = ("gemm", M, N, K, int(trans_a), int(trans_b), int(epilogue))
     if backend == "tcgen05" and lib.map_gemm_tf32_supported(C.byref(g)):
         call("map_gemm_tf32_tcgen05", C.byref(g), _stream())
     else:  # skinny / unaligned shapes (N < 16, N % 4 != 0) and the exact-fp32 test mode
         call("map_gemm_f32_simt", C.byref(g), _stream())
     return C_out
+
+
+GEMM_GROUP_MAX = 4
+
+
+def gemm_group_enabled() -> bool:
+    """MAP_B200_GEMM_GROUP=0 issues every problem of a group as its own launch (A/B switch for the persistent kernel)."""
+    return os.environ.get("MAP_B200_GEMM_GROUP", "1") != "0"
+
+
+def gemm_group(problems, backend: Optional[str] = None):
+    """problems: list of dicts with the keyword arguments of `gemm` (A, B, C_out, M, N, K, ...), all INDEPENDENT of each other.
+    Problems the tensor-core path supports go into persistent grouped launches (map_gemm_tf32_group, <= 4 per launch); the rest
+    (skinny shapes, the exact-fp32 test backend) are issued one by one."""
+    backend = backend or gemm_backend()
+    lib = _lib.load()
+    grouped, single = [], []
+    for pr in problems:
+        g = _gemm_args(**pr)
+        if backend == "tcgen05" and gemm_group_enabled() and lib.map_gemm_tf32_supported(C.byref(g)):
+            grouped.append(g)
+        else:
+            single.append(pr)
+    for i in range(0, len(grouped), GEMM_GROUP_MAX):
+        chunk = grouped[i:i + GEMM_GROUP_MAX]
+        arr = (GemmArgs * len(chunk))()
+        for j, g in enumerate(chunk):
+            C.memmove(C.byref(arr, j * C.sizeof(GemmArgs)), C.byref(g), C.sizeof(GemmArgs))
+        if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
+            _lib.CURRENT_TAG = ("gemm_group",) + tuple((g.M, g.N, g.K) for g in chunk)
+        call("map_gemm_tf32_group", arr, len(chunk), _stream())
+    for pr in single:
+        gemm(backend=backend, **pr)
 
 
 _colsum_ws = {}

@@ -543,6 +543,72 @@ def test_gemm_tcgen05_epilogues(ops, epi, accumulate):
         assert ((ga - wa).norm() / wa.norm()) < 1e-3
 
 
+def _gemm_problem(M, N, K, ta, tb, epi, seed=0, accumulate=False, colsum=True):
+    """(kwargs for ops.gemm / ops.gemm_group, verify()) for one problem with its own buffers"""
+    from map_code_b200 import _lib as L
+    gen = torch.Generator().manual_seed(seed)
+    A, B, As, Bs = _gemm_case(gen, M, N, K, ta, tb)
+    bias = torch.randn(N, generator=gen)
+    aux0, aux1, aux2 = (torch.randn(M, N, generator=gen) for _ in range(3))
+    acc_prev = torch.randn(M, N, generator=gen) if accumulate else None
+    acc = A.double() @ B.double().t()
+    want, want_aux, want_acc = _epilogue_ref(epi, acc, bias.double(), aux0.double(), aux1.double(), aux2.double(),
+                                             acc_prev.double() if accumulate else None)
+    Cd = torch.full((M, N), float("nan"), device="cuda")
+    auxo = torch.full((M, N), float("nan"), device="cuda")
+    acco = dev(acc_prev) if accumulate else torch.full((M, N), float("nan"), device="cuda")
+    cs = torch.full((N,), 0.5, device="cuda") if (colsum and N % 4 == 0) else None
+    kw = dict(A=dev(As), B=dev(Bs), C_out=Cd, M=M, N=N, K=K, trans_a=ta, trans_b=tb, epilogue=epi, bias=dev(bias), aux0=dev(aux0),
+              aux1=dev(aux1), aux_out=auxo, aux2=dev(aux2), acc_out=acco if epi == L.EPI_CROSS_BWD else None,
+              acc_accumulate=accumulate, colsum_out=cs)
+
+    def verify():
+        got = Cd.cpu().double()
+        assert torch.isfinite(got).all(), f"unwritten output in problem {(M, N, K, ta, tb, epi)}"
+        assert (got - want).abs().max() < 8 * 2 ** -10 * math.sqrt(K) * 4 + 1e-4
+        assert ((got - want).norm() / want.norm()) < 2e-3
+        if want_aux is not None:
+            assert ((auxo.cpu().double() - want_aux).norm() / want_aux.norm()) < 1e-3
+        if want_acc is not None:
+            assert ((acco.cpu().double() - want_acc).norm() / want_acc.norm()) < 2e-3
+        if cs is not None:
+            got_cs, want_cs = cs.cpu().double() - 0.5, got.sum(0)
+            assert (got_cs - want_cs).abs().max() < 1e-3 * max(1.0, float(want_cs.abs().max())), "fused column sums"
+    return kw, verify
+
+
+GROUPS = {
+    "fwd_level": [(4096, 624, 624, False, False, 3, False, True), (4096, 1000, 624, False, False, 2, False, True)],
+    "bwd_head": [(4096, 624, 1248, False, True, 7, False, True), (4096, 1000, 1248, False, True, 4, True, True),
+                 (1248, 1624, 4096, True, True, 0, False, False)],
+    "bwd_level": [(624, 624, 4096, True, True, 0, False, False), (1000, 1000, 4096, True, True, 0, False, False),
+                  (4096, 624, 624, False, True, 7, True, True), (4096, 1000, 1000, False, True, 4, False, True)],
+    "single_ragged": [(515, 624, 624, False, False, 1, False, True)],
+    "uncovered_combo": [(300, 1000, 1000, False, False, 1, False, True), (257, 48, 308, False, False, 5, False, True),
+                        (640, 624, 624, False, False, 3, False, True), (640, 1000, 624, False, False, 2, False, True)],
+    "tiny": [(129, 16, 40, False, False, 0, False, False), (64, 64, 16, True, True, 0, False, True)],
+    "add3_addmul": [(4096, 624, 624, False, True, 8, False, True), (300, 1000, 1000, True, False, 6, False, True),
+                    (257, 48, 77 * 4, False, False, 5, False, True)],
+    "five_problems": [(384, 624, 624, False, False, 3, False, True), (384, 1000, 624, False, False, 2, False, True),
+                      (384, 1000, 1000, False, False, 2, False, True), (384, 1248, 1624, False, False, 1, False, True),
+                      (1000, 624, 384, True, True, 0, False, False)],
+}
+
+
+@pytest.mark.parametrize("name", sorted(GROUPS))
+def test_gemm_group_tf32(ops, name):
+    """persistent grouped launch (map_gemm_tf32_group): every problem of the group against its own fp64 reference"""
+    probs, checks = [], []
+    for i, (M, N, K, ta, tb, epi, accumulate, colsum) in enumerate(GROUPS[name]):
+        kw, verify = _gemm_problem(M, N, K, ta, tb, epi, seed=10 * i + epi, accumulate=accumulate and epi == 7, colsum=colsum)
+        probs.append(kw)
+        checks.append(verify)
+    ops.gemm_group(probs, backend="tcgen05")
+    torch.cuda.synchronize()
+    for verify in checks:
+        verify()
+
+
 def test_gemm_tcgen05_strided_views(ops):
     """forward writes into column slices of the concatenated [B, 1624] buffer (no torch.cat, models.py:312)"""
     gen = torch.Generator().manual_seed(0)
