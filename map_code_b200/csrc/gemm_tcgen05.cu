@@ -542,25 +542,43 @@ struct GroupArgs {
     unsigned long long* trace;        // optional (map_gemm_set_trace): same record layout as the single-problem kernel
 };
 
+// chunk width of the grouped kernel's epilogue: it keeps TWO prefetched operand sets in registers (see epi_tile), so every
+// epilogue that streams two or more operands uses 16-column chunks (36-52 registers per set)
+__host__ __device__ constexpr int epi_chunk_w_group(int e) { return epi_has_aux1(e) ? 16 : 32; }
+
+template <int EPI, int CW>
+__device__ __forceinline__ void epi_prefetch_any(const GemmParams& p, int lane, int row_base, int n0, int c, bool full_tile, EpiRegs& e) {
+    if (CW == 16 || c + CW <= p.block_n) epi_prefetch<EPI, CW>(p, lane, row_base, n0 + c, full_tile, e);
+    else epi_prefetch<EPI, 16>(p, lane, row_base, n0 + c, full_tile, e);   // trailing half chunk (block_n % 32 == 16)
+}
+template <int EPI, bool SPLIT, int CW>
+__device__ __forceinline__ void epi_chunk_any(const GemmParams& p, float* stg, int lane, uint32_t lane_addr, int row_base, int n0, int c,
+                                              bool full_tile, const EpiRegs& e) {
+    if (CW == 16 || c + CW <= p.block_n) epi_chunk<EPI, SPLIT, CW>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
+    else epi_chunk<EPI, SPLIT, 16>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
+}
+
+// Epilogue of one tile.  The operands of chunk i+1 (bias / aux0 / aux1 / aux2 rows) are requested BEFORE chunk i is pulled out
+// of TMEM and written, into the other of two register sets: their L2 round trip (the whole cost of a chunk in the
+// single-buffered version: ~2000 clk per 16-32 columns) overlaps the TMEM read, the transpose and the stores of chunk i.
 template <int EPI, bool SPLIT>
 __device__ __forceinline__ void epi_tile(const GemmParams& p, float* stg, int lane, uint32_t lane_addr, int row_base, int m0, int n0,
                                          uint32_t full_bar, unsigned long long* trace) {
-    constexpr int CW = epi_chunk_w(EPI);
+    constexpr int CW = epi_chunk_w_group(EPI);
     const bool full_tile = (m0 + kBlockM <= p.M) && (n0 + p.block_n <= p.N);
-    EpiRegs e;
-    if (p.block_n >= CW) epi_prefetch<EPI, CW>(p, lane, row_base, n0, full_tile, e);
-    else epi_prefetch<EPI, 16>(p, lane, row_base, n0, full_tile, e);
+    const int bn = p.block_n;
+    EpiRegs ea, eb;
+    epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, 0, full_tile, ea);
     mbar_wait(full_bar, 0);
     tcgen05_fence_after();
     if (trace != nullptr && threadIdx.x == 64) trace[5] = (unsigned long long)clock64();
-    int c = 0;
-    for (; c + CW <= p.block_n; c += CW) {
-        epi_chunk<EPI, SPLIT, CW>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
-        if (c + 2 * CW <= p.block_n) epi_prefetch<EPI, CW>(p, lane, row_base, n0 + c + CW, full_tile, e);
-        else if (CW == 32 && c + CW < p.block_n) epi_prefetch<EPI, 16>(p, lane, row_base, n0 + c + CW, full_tile, e);
+    for (int c = 0; c < bn; c += 2 * CW) {
+        if (c + CW < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c + CW, full_tile, eb);
+        epi_chunk_any<EPI, SPLIT, CW>(p, stg, lane, lane_addr, row_base, n0, c, full_tile, ea);
+        if (c + CW >= bn) break;
+        if (c + 2 * CW < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c + 2 * CW, full_tile, ea);
+        epi_chunk_any<EPI, SPLIT, CW>(p, stg, lane, lane_addr, row_base, n0, c + CW, full_tile, eb);
     }
-    if (CW == 32 && c < p.block_n)  // block_n % 32 == 16
-        epi_chunk<EPI, SPLIT, 16>(p, stg, lane, lane_addr + (uint32_t)c, row_base, n0 + c, full_tile, e);
     if (trace != nullptr && threadIdx.x == 64) trace[6] = (unsigned long long)clock64();
 }
 

@@ -95,6 +95,8 @@ class FusedStep:
         self.streams = ({k: torch.cuda.Stream(device=self.dev, priority=(-1 if k == "tab" else 0)) for k in ("tab", "mlp", "dw")}
                         if multi_stream else {})
         self._forked = set()
+        self._early = False          # set by _step_body: optimizer work may start inside the backward
+        self._tables_done = set()    # tables whose AdamW already ran inside the step
 
     # ------------------------------------------------------------------------------------------------ setup
     def _collect_params(self):
@@ -376,12 +378,15 @@ class FusedStep:
         self._fork("tab")
         with self._on("tab"):
             self._draw_noise()   # first: the NCE head waits for the noise, nothing waits for the sort until the backward
+            if self._early:      # every Philox consumer of this step has been issued: the step counter may advance
+                self._hyper_step()
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
 
     def _draw_noise(self):
         if self.mode != "MFP":
             return
+        self.d_enc.zero_()   # (20 MB memset for the backward of the slice gather: off the critical path here)
         crit = self.model.mfp_criterion
         if self.overrides is not None and "noise" in self.overrides:
             self.noise.copy_(self.overrides["noise"].reshape(self.N, self.K))
@@ -504,6 +509,11 @@ class FusedStep:
             ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
             te.plan.run(self.ids_all.view(-1))
             te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
+            if self._early and self.optimizer_mode == "sparse":
+                # nothing reads the two NCE tables again in this step: their row-wise AdamW runs here, under the backward GEMMs
+                for t in (te, tb):
+                    ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.plan, t.grad, self.hyper, t.wd)
+                    self._tables_done.add(t.name)
 
     def _head_mfp(self):
         cfg, B, F, P, K, N, L = self.cfg, self.B, self.F, self.P, self.K, self.N, self.L
@@ -514,8 +524,7 @@ class FusedStep:
         ops.gather_slices(self.enc, self.mi, F, P, out=self.sel)                                                   # models.py:75
         self._join("tab")  # noise drawn on the 'tab' stream
         self._nce_core()
-        # ---- backward of the encoder
-        self.d_enc.zero_()
+        # ---- backward of the encoder (d_enc was zeroed on the 'tab' stream at the start of the step)
         ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
         self._fork("dw")
         with self._on("dw"):   # bias gradient of the encoder: off the critical path
@@ -569,6 +578,7 @@ class FusedStep:
         """mask -> forward -> backward; gradients land in self.grads / self.tables[*].grad.  On return every side stream has
         been joined back into the current stream."""
         self._forked.clear()
+        self._tables_done.clear()
         if self.bias_grad_flat.numel():
             self.bias_grad_flat.zero_()
         self.ids_cur = self._draw_and_mask()
@@ -588,20 +598,38 @@ class FusedStep:
     def reduce_gradients(self):
         """hook for data-parallel runs (dist.py installs the all-reduce / all-to-all here)."""
 
-    def optimizer_step(self):
+    def _hyper_step(self):
         b1, b2 = self.betas
         ops.adamw_hyper_step(self.hyper, self.step_counter, self.lr, b1, b2, self.eps, self.sched, self.warmup_steps, self.total_steps)
-        ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
+
+    def optimizer_step(self):
+        if not self._early:
+            self._hyper_step()
+        # dense parameters on the 'dw' stream, next to the table updates on the main stream
+        self._fork("dw")
+        with self._on("dw"):
+            ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
         for t in self.tables.values():
+            if t.name in self._tables_done:
+                continue
             if self.optimizer_mode == "sparse":
                 ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.plan, t.grad, self.hyper, t.wd)
             else:
                 ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.plan, t.grad, self.hyper, t.wd)
+        self._join("dw")
 
     def _step_body(self):
-        self.forward_backward()
-        self.reduce_gradients()
-        self.optimizer_step()
+        # the fused single-GPU schedule advances the step counter and updates the NCE tables inside the step (see _embed_lookup,
+        # _nce_core); a subclass with its own exchange schedule (dist.py) or a caller driving forward_backward() /
+        # optimizer_step() separately gets the plain order
+        self._early = (type(self).optimizer_step is FusedStep.optimizer_step and type(self)._nce_core is FusedStep._nce_core
+                       and type(self)._embed_lookup is FusedStep._embed_lookup)
+        try:
+            self.forward_backward()
+            self.reduce_gradients()
+            self.optimizer_step()
+        finally:
+            self._early = False
 
     # ------------------------------------------------------------------------------------------------ public API
     def capture(self):
