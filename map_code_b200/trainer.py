@@ -76,6 +76,17 @@ class DeviceBatcher:
             yield xb, yb
 
 
+class PendingStep:
+    """Result handle of Trainer.train_step_async: the loss of that step, readable once its device work is done."""
+
+    def __init__(self, done, host_buf):
+        self._done, self._host = done, host_buf
+
+    def loss(self) -> float:
+        self._done.synchronize()
+        return float(self._host[0])
+
+
 class Trainer:
     def __init__(self, model, model_config, training_args, train_dataset, eval_dataset):
         self.model = model
@@ -97,6 +108,7 @@ class Trainer:
         self._mask_calls = 0
         self._x_train_dev = None
         self._h2d = None
+        self._pipe = None
 
     # ------------------------------------------------------------------------------------------------ data
     def get_dataloader(self, dataset, is_training=True):
@@ -203,6 +215,43 @@ class Trainer:
         eng.step(X, Y)
         self.global_step += 1
         return eng.outputs()
+
+    def train_step_async(self, X, Y=None) -> "PendingStep":
+        """Pipelined form of train_step for HOST batches: the H2D copy of this batch runs on a copy stream (two staging buffers),
+        the step is enqueued behind it, and the loss is copied to pinned host memory behind the step.  Nothing blocks here:
+        `PendingStep.loss()` waits for that step only, so a loop that reads step i-1 after submitting step i overlaps every
+        transfer with the neighbouring steps' compute."""
+        eng = self._fused
+        if eng is None:
+            raise RuntimeError("call fused_step(total_steps, warmup_steps) (or MFP_pretrain/RFD_pretrain/train) first")
+        if self._pipe is None:
+            dev = self.device
+            self._pipe = dict(copy_stream=torch.cuda.Stream(device=dev), k=0,
+                              stage=[torch.empty(eng.B, eng.F, dtype=torch.int64, device=dev) for _ in range(2)],
+                              stage_y=[None, None], loaded=[torch.cuda.Event(), torch.cuda.Event()],
+                              consumed=[torch.cuda.Event(), torch.cuda.Event()], used=[False, False],
+                              host=[torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)])
+        pp = self._pipe
+        k = pp["k"]
+        pp["k"] = 1 - k
+        main = torch.cuda.current_stream()
+        cs = pp["copy_stream"]
+        if pp["used"][k]:
+            cs.wait_event(pp["consumed"][k])      # the step that last read this staging buffer has copied it into the graph input
+        with torch.cuda.stream(cs):
+            pp["stage"][k].copy_(X, non_blocking=True)
+            if Y is not None:
+                pp["stage_y"][k] = Y.to(self.device, non_blocking=True)
+            pp["loaded"][k].record(cs)
+        main.wait_event(pp["loaded"][k])
+        out = eng.step(pp["stage"][k], pp["stage_y"][k] if Y is not None else None)
+        pp["consumed"][k].record(main)
+        pp["used"][k] = True
+        done = torch.cuda.Event()
+        pp["host"][k].copy_(out.detach().view(1), non_blocking=True)
+        done.record(main)
+        self.global_step += 1
+        return PendingStep(done, pp["host"][k])
 
     # ------------------------------------------------------------------------------------------------ loops
     def _log_header(self, t_total, t_warmup):

@@ -92,3 +92,30 @@ def test_dynamic_mask_api_and_errors(tmp_path):
     cfg.model_name = "xdeepfm"
     with pytest.raises(NotImplementedError):
         BaseModel.from_config(cfg)
+
+
+@pytest.mark.parametrize("pt_type", ["MFP", "RFD"])
+def test_train_step_async_matches_train_step(pt_type, tmp_path):
+    """the pipelined host-batch API (H2D on a copy stream, loss read one step late) produces the same losses as train_step"""
+    from map_code_b200.trainer import Trainer
+    losses = {}
+    for mode in ("sync", "async"):
+        model, cfg, args, train, valid = make(pt_type, True, "DCNv2", tmp_path)
+        model.cuda()
+        tr = Trainer(model, cfg, args, train, valid)
+        tr.fused_step(100, 0)
+        batches = [torch.from_numpy(train.X[i * 256:(i + 1) * 256]).pin_memory() for i in range(4)]
+        if mode == "sync":
+            losses[mode] = [float(tr.train_step(b)[0]) for b in batches + batches]
+        else:
+            pend, out = None, []
+            for b in batches + batches:
+                nxt = tr.train_step_async(b)
+                if pend is not None:
+                    out.append(pend.loss())
+                pend = nxt
+            out.append(pend.loss())
+            losses[mode] = out
+        assert tr.global_step == 8
+    assert np.allclose(losses["sync"], losses["async"], rtol=1e-4), losses
+    assert losses["sync"][-1] < losses["sync"][0]
