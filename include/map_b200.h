@@ -75,14 +75,20 @@ int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const flo
  *              fix the order of the occurrences, e.g. by source rank);
  *   occ_map    (may be NULL) occurrence o of the sorted list refers to row code occ_map[o] instead of o;
  *   row_ptrs   (may be NULL) host array of n_peers device pointers: row code c lives at row_ptrs[c / rows_per_peer] + (c % rows_per_peer) * ld_rows
- *              (peer memory mapped with map_p2p_open; the loads travel over NVLink). */
+ *              (peer memory mapped with map_p2p_open; the loads travel over NVLink);
+ *   pos_seg    (may be NULL) int32 [n_ids]: map_dedup_ids_ex writes the segment index of every sorted position; given to
+ *              map_segment_reduce_rows_ex it replaces the per-tile binary search over seg_start.
+ * map_dedup_ids_ex runs the whole pipeline as ONE launch of persistent CTAs with grid barriers (one barrier per radix pass);
+ * the environment variable MAP_B200_DEDUP=multi selects the multi-launch pipeline (histogram / scan / scatter per pass). */
 int map_dedup_ids_ex(const int64_t* ids, int64_t n_ids, const int32_t* n_dev, int key_bits, int seg_shift, int64_t* uniq_ids,
-                     int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,
-                     map_stream_t stream);
+                     int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, int32_t* pos_seg, void* workspace,
+                     size_t workspace_bytes, map_stream_t stream);
+int map_dedup_single_launch(void);
 int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
-                               const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique, int64_t n_ids,
-                               const int32_t* n_dev, const int32_t* occ_map, const float* const* row_ptrs, int n_peers,
-                               int64_t rows_per_peer, float* grad_compact, float* scalar_out, map_stream_t stream);
+                               const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
+                               const int32_t* pos_seg, int64_t n_ids, const int32_t* n_dev, const int32_t* occ_map,
+                               const float* const* row_ptrs, int n_peers, int64_t rows_per_peer, float* grad_compact,
+                               float* scalar_out, map_stream_t stream);
 /* dense[uniq_ids[u], :] = grad_compact[u, :]  (dense must be zero-filled by the caller): the `.grad` the reference sees */
 int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const int32_t* n_unique, int64_t max_unique,
                      int D, float* dense, map_stream_t stream);
@@ -295,6 +301,16 @@ int map_nce_fwd_sharded(const float* input, int64_t N, int P, int K, const int64
                         const void* const* emb_shards, const void* const* bias_shards, int R, const float* logprob_noise,
                         float norm_term, int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos,
                         float* dz, float* d_input, int32_t* acc_count, map_stream_t stream);
+/* ids_out[n, 0] = target[n], ids_out[n, 1 + k] = noise[n, k] (the [N, K+1] id list map_nce_fwd emits as ids_out): lets the sort of
+ * the NCE tables' gradient ids start as soon as the noise is drawn (code/nce/index_linear.py:79-83 builds the same cat). */
+int map_nce_ids_concat(const int64_t* target, const int64_t* noise, int64_t N, int K, int64_t* ids_out, map_stream_t stream);
+/* Stream-ordered barrier over the R ranks through peer memory: flag_ptrs[r] = rank r's uint32 flags[n_sites][8] from
+ * map_p2p_alloc (zero-initialised), epochs = this rank's device uint32[n_sites] (zero-initialised, advanced by the kernel, so a
+ * captured graph replays it), site = which barrier of the step's schedule (barriers of different sites may overlap in time),
+ * error_word (may be NULL) is set to 1 if a peer does not arrive within seconds instead of hanging the GPU.  Everything earlier
+ * kernels of `stream` wrote on any rank is visible to peer loads of kernels launched after the barrier. */
+int map_p2p_barrier(const void* const* flag_ptrs, int R, int rank, int site, int n_sites, uint32_t* epochs, uint32_t* error_word,
+                    map_stream_t stream);
 /* Owner-side merge, step 1: scan the R per-rank unique-id lists (uniq_ptrs[s] = int64 ids ascending, n_unique_ptrs[s] =
  * device int32 count) and append the entries this rank owns: keys[k] = ((id / R) << ceil_log2(R)) | s, src[k] = s * cap + u,
  * *n_out = number of entries.  Then map_dedup_ids_ex(keys, R * cap, n_out, key_bits, ceil_log2(R), ...) and

@@ -2,6 +2,9 @@
 //   radix sort (id, occurrence)  ->  unique ids + segment starts  ->  segmented row sums.
 // Replaces aten::embedding_dense_backward (thrust sort + dense [V,D] grad) behind code/layers.py:98 and the dense
 // index_add behind code/nce/index_linear.py:99-100.  Everything is integer / HBM-L2 bound; no tensor cores.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mapb {
@@ -12,6 +15,9 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per CTA
 constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
 
 // The number of keys may live on the device (n_dev != nullptr: the owner-side merge of the row-sharded tables compacts a
 // data-dependent number of entries): grids are sized for the capacity n, every kernel clamps to min(n, *n_dev).
@@ -53,8 +59,12 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t*
 // out[block][bin] = #keys with a smaller digit + #keys with this digit in earlier blocks.
 // One CTA of 1024 threads = 4 groups x 256 bins; each group walks a quarter of the blocks with 8 independent loads in
 // flight per thread (the old single-CTA linear scan was a 20 us latency chain per pass).
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int nblocks) {
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int nblocks, int64_t n, const int32_t* n_dev) {
     __shared__ uint32_t tot[4][kRadixBins];
+    {   // with a device-side count only the tiles that hold keys are scanned (the grids are sized for the capacity)
+        const int64_t live = (eff_n(n, n_dev) + kSortTile - 1) / kSortTile;
+        if (live < nblocks) nblocks = live > 0 ? (int)live : 1;
+    }
     __shared__ uint32_t bin_excl[kRadixBins];
     __shared__ uint32_t warp_tot[8];
     const int bin = threadIdx.x & (kRadixBins - 1);
@@ -114,8 +124,12 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ 
 }
 
 // In-place exclusive scan of `data[0..len)` by ONE CTA of 1024 threads (len <= a few million: bins*nblocks).
-__global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint32_t* data, int64_t len) {
+__global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint32_t* data, int64_t len, int64_t n, const int32_t* n_dev) {
     __shared__ uint32_t warp_tot[32];
+    {
+        const int64_t live = (eff_n(n, n_dev) + kScanTile - 1) / kScanTile;
+        if (live < len) len = live > 0 ? live : 1;
+    }
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -251,10 +265,6 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32
 }
 
 // ---------------------------------------------------------------------------------------------- unique / segments
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
 // keys that agree above `seg_shift` belong to one segment (the low bits order the occurrences of a row deterministically,
 // e.g. by source rank in the sharded merge)
 __device__ __forceinline__ uint32_t head_flag(const uint32_t* keys, int64_t i, int seg_shift) {
@@ -287,7 +297,8 @@ __global__ void __launch_bounds__(kScanThreads) heads_emit_kernel(const uint32_t
                                                                   const uint32_t* __restrict__ tile_offsets,
                                                                   int64_t* __restrict__ uniq_ids,
                                                                   int32_t* __restrict__ seg_start,
-                                                                  int32_t* __restrict__ n_unique) {
+                                                                  int32_t* __restrict__ n_unique,
+                                                                  int32_t* __restrict__ pos_seg) {
     __shared__ uint32_t warp_tot[kScanThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     n = eff_n(n, n_dev);
@@ -324,6 +335,7 @@ __global__ void __launch_bounds__(kScanThreads) heads_emit_kernel(const uint32_t
             seg_start[u] = (int32_t)(base + k);
             ++u;
         }
+        if (pos_seg != nullptr && base + k < n) pos_seg[base + k] = (int32_t)u - 1;
         if (base + k == n - 1) {  // the last element closes the list
             seg_start[u] = (int32_t)n;
             *n_unique = (int32_t)u;
@@ -373,7 +385,8 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
                                                              float* __restrict__ grad, float* __restrict__ scalar_out,
                                                              int D, const int32_t* __restrict__ n_dev,
                                                              const int32_t* __restrict__ occ_map,
-                                                             const PeerTable row_tab, int64_t rows_per_peer) {
+                                                             const PeerTable row_tab, int64_t rows_per_peer,
+                                                             const int32_t* __restrict__ pos_seg) {
     __shared__ int slot_seg[2 * 256];                  // segment id of every head (2g) / tail (2g+1) slot, -1 = empty
     __shared__ float slot_sc[2 * 256];
     __shared__ __align__(16) float slot_vec[2 * 256 * VEC];  // [slot][lanes * VEC] with 2 * G * lanes * VEC <= 512 * VEC
@@ -394,13 +407,19 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
         slot_seg[2 * g + 1] = -1;
     }
     if (active) {
-        // segment containing t0: largest s with seg_start[s] <= t0
-        int lo = 0, hi = U - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if ((int64_t)seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+        // segment containing t0: read from the position -> segment map when the dedup produced one, else the largest s
+        // with seg_start[s] <= t0 (a 20-step chain of dependent loads per group at 1e6 unique rows)
+        int s;
+        if (pos_seg != nullptr) {
+            s = __ldg(pos_seg + t0);
+        } else {
+            int lo = 0, hi = U - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((int64_t)seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
+            }
+            s = lo;
         }
-        int s = lo;
         int64_t s_end = seg_start[s + 1];
         RowVec<VEC> r[kSegTile];
         float sc[kSegTile];
@@ -507,14 +526,303 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------- single-launch pipeline
+// The whole of K2a (key extraction, every radix pass, head flags, unique ids / segment starts / position -> segment map) as
+// ONE launch of persistent CTAs that meet at grid barriers.  At the step's sizes (n = 1.6e5 .. 3.2e5 keys) the multi-launch
+// pipeline above is a chain of 13 dependent launches of a few microseconds each — launch/drain latency, not bandwidth; here a
+// pass costs one barrier:
+//   H   CTA g builds the digit-0 histogram of its contiguous key range                              -> hist[0][g][256]
+//   S_p thread b sums column b of hist[p] (all G rows: totals; rows < g: its own prefix), the CTA scans the 256 totals, then
+//       ranks / reorders / scatters its tiles exactly like sort_scatter_kernel; while writing key k to position `pos` it also
+//       counts k's NEXT digit into hist[p+1][owner CTA of pos] (global reductions), so pass p+1 needs no histogram sweep
+//   U   head flags of the sorted keys: per-CTA counts -> barrier -> every CTA emits its range at its prefix
+// G <= 2 CTAs per SM (256 threads, < 32 KB shared memory), so all CTAs are co-resident on an otherwise idle GPU; beside other
+// kernels the late CTAs simply arrive late (nothing they wait for depends on this kernel).  Cross-CTA data is read with
+// ld.global.cg (L2): the buffers are rewritten between passes, so the non-coherent / L1 paths must not be used for them.
+constexpr int kPersistMaxCtas = 2 * kNumSMs;
+constexpr unsigned kSpinLimit = 1u << 22;   // ~ seconds; a barrier that is not met sets the error word instead of hanging
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// sync[0] = arrival counter (zeroed by the host before the launch), sync[1] = error word
+__device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned target, int* ok_s) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(sync, 1u);
+        int ok = 1;
+        unsigned spins = 0;
+        while (ld_acquire_u32(sync) < target) {
+            if (++spins > kSpinLimit || ld_acquire_u32(sync + 1) != 0u) {
+                atomicExch(sync + 1, 1u);
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence();
+        *ok_s = ok;
+    }
+    __syncthreads();
+    return *ok_s != 0;
+}
+
+struct PersistSmem {
+    uint32_t warp_cnt[kSortWarps][kRadixBins];
+    uint32_t tile_run[kRadixBins];
+    uint32_t tile_excl[kRadixBins];
+    uint32_t gbase[kRadixBins];
+    uint32_t warp_tot[kSortWarps];
+    uint32_t keys_s[kSortTile];
+    uint32_t vals_s[kSortTile];
+    uint32_t carry;
+    int ok;
+};
+
+// exclusive scan of one value per thread over the 256 threads of the CTA (warp_tot: scratch); returns the exclusive prefix,
+// *total = sum over the CTA
+__device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t t, uint32_t* warp_tot, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __syncthreads();   // warp_tot may still be read by the previous use
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t x = warp_tot[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    if (total != nullptr) *total = tot;
+    return off + incl - t;
+}
+
+__global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
+    const int64_t* __restrict__ ids, int64_t n_cap, const int32_t* __restrict__ n_dev, int passes, int seg_shift, uint32_t* keys_a,
+    uint32_t* keys_b, uint32_t* vals_a, uint32_t* occ, uint32_t* hist, uint32_t* cnt, unsigned* sync, int64_t* __restrict__ uniq_ids,
+    int32_t* __restrict__ seg_start, int32_t* __restrict__ n_unique, int32_t* __restrict__ pos_seg) {
+    __shared__ PersistSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, g = blockIdx.x;
+    const int64_t n = eff_n(n_cap, n_dev);
+    const int64_t ntiles = (n + kSortTile - 1) / kSortTile;
+    int64_t tpc = (ntiles + G - 1) / G;
+    if (tpc < 1) tpc = 1;
+    const int64_t tile0 = (int64_t)g * tpc;
+    const int64_t tile1 = (tile0 + tpc < ntiles) ? tile0 + tpc : ntiles;   // (tile0 >= tile1: this CTA only attends the barriers)
+    unsigned epoch = 0;
+
+    // ---- H: digit-0 histogram of the own range (keys come straight from the int64 ids); rows of the later passes start at 0
+    sm.tile_run[tid] = 0;
+    for (int p = 1; p < passes; ++p) hist[((size_t)p * G + g) * kRadixBins + tid] = 0u;
+    __syncthreads();
+    for (int64_t t = tile0; t < tile1; ++t) {
+        const int64_t base = t * kSortTile;
+#pragma unroll
+        for (int it = 0; it < kSortItems; ++it) {
+            const int64_t i = base + it * kSortThreads + tid;
+            if (i < n) atomicAdd(&sm.tile_run[(uint32_t)ids[i] & (kRadixBins - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    hist[(size_t)g * kRadixBins + tid] = sm.tile_run[tid];
+    if (!grid_barrier(sync, (++epoch) * G, &sm.ok)) return;
+
+    // ---- S_p
+    for (int p = 0; p < passes; ++p) {
+        const int shift = p * kRadixBits;
+        const bool last = (p + 1 == passes);
+        const uint32_t* kin = (p & 1) ? keys_a : keys_b;              // written by pass p-1 (unused for p == 0)
+        uint32_t* kout = (p & 1) ? keys_b : keys_a;
+        const uint32_t* vin = ((passes - p) & 1) ? vals_a : occ;      // pass p-1 wrote where ((passes-1-(p-1)) even ? occ : vals_a)
+        uint32_t* vout = ((passes - 1 - p) & 1) ? vals_a : occ;       // the last pass lands in occ_sorted
+        uint32_t* hnext = hist + (size_t)(p + 1) * G * kRadixBins;
+        {   // column sums of this pass's histogram: thread = digit
+            const uint32_t* h = hist + (size_t)p * G * kRadixBins + tid;
+            uint32_t tot = 0, pre = 0;
+            int r = 0;
+            for (; r + 8 <= G; r += 8) {
+                uint32_t c[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c[k] = __ldcg(h + (size_t)(r + k) * kRadixBins);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    tot += c[k];
+                    if (r + k < g) pre += c[k];
+                }
+            }
+            for (; r < G; ++r) {
+                const uint32_t c = __ldcg(h + (size_t)r * kRadixBins);
+                tot += c;
+                if (r < g) pre += c;
+            }
+            const uint32_t excl = cta_excl_scan_256(tot, sm.warp_tot, nullptr);
+            sm.gbase[tid] = excl + pre;
+        }
+        __syncthreads();
+        for (int64_t t = tile0; t < tile1; ++t) {
+            const int64_t base = t * kSortTile;
+            const int tile_n = (int)((n - base < kSortTile) ? (n - base) : kSortTile);
+            sm.tile_run[tid] = 0;
+            uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+            // pass A: load, rank every key among the keys of the same digit that precede it in the tile
+            for (int it = 0; it < kSortItems; ++it) {
+#pragma unroll
+                for (int w = 0; w < kSortWarps; ++w) sm.warp_cnt[w][tid] = 0;
+                __syncthreads();
+                const int li = it * kSortThreads + tid;
+                const bool valid = li < tile_n;
+                if (p == 0) {
+                    key[it] = valid ? (uint32_t)ids[base + li] : 0u;
+                    val[it] = (uint32_t)(base + li);
+                } else {
+                    key[it] = valid ? __ldcg(kin + base + li) : 0u;
+                    val[it] = valid ? __ldcg(vin + base + li) : 0u;
+                }
+                const uint32_t digit = valid ? ((key[it] >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+                const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+                if (valid && rank_in_warp == 0) sm.warp_cnt[warp][digit] = __popc(peers);
+                __syncthreads();
+                {
+                    uint32_t run = sm.tile_run[tid];
+#pragma unroll
+                    for (int w = 0; w < kSortWarps; ++w) {
+                        const uint32_t c = sm.warp_cnt[w][tid];
+                        sm.warp_cnt[w][tid] = run;
+                        run += c;
+                    }
+                    sm.tile_run[tid] = run;
+                }
+                __syncthreads();
+                rank[it] = valid ? sm.warp_cnt[warp][digit] + rank_in_warp : 0u;
+                __syncthreads();
+            }
+            sm.tile_excl[tid] = cta_excl_scan_256(sm.tile_run[tid], sm.warp_tot, nullptr);
+            __syncthreads();
+            // pass B: stable reorder by digit in shared memory
+#pragma unroll
+            for (int it = 0; it < kSortItems; ++it) {
+                const int li = it * kSortThreads + tid;
+                if (li < tile_n) {
+                    const uint32_t digit = (key[it] >> shift) & (kRadixBins - 1);
+                    const uint32_t lp = sm.tile_excl[digit] + rank[it];
+                    sm.keys_s[lp] = key[it];
+                    sm.vals_s[lp] = val[it];
+                }
+            }
+            __syncthreads();
+            // pass C: coalesced runs to global memory + the next pass's histogram of the destination range
+            for (int i = tid; i < tile_n; i += kSortThreads) {
+                const uint32_t k = sm.keys_s[i];
+                const uint32_t digit = (k >> shift) & (kRadixBins - 1);
+                const uint32_t pos = sm.gbase[digit] + ((uint32_t)i - sm.tile_excl[digit]);
+                kout[pos] = k;
+                vout[pos] = sm.vals_s[i];
+                if (!last) {
+                    const uint32_t owner = (uint32_t)((pos / kSortTile) / tpc);
+                    atomicAdd(hnext + (size_t)owner * kRadixBins + ((k >> (shift + kRadixBits)) & (kRadixBins - 1)), 1u);
+                }
+            }
+            __syncthreads();
+            sm.gbase[tid] += sm.tile_run[tid];
+            __syncthreads();
+        }
+        if (!grid_barrier(sync, (++epoch) * G, &sm.ok)) return;
+    }
+
+    // ---- U: head flags.  sorted keys are in the buffer the last pass wrote
+    const uint32_t* ks = ((passes - 1) & 1) ? keys_b : keys_a;
+    uint32_t my_heads = 0;
+    for (int64_t t = tile0; t < tile1; ++t) {
+        const int64_t base = t * kSortTile + (int64_t)tid * kSortItems;
+        uint32_t prev = (base > 0 && base < n) ? (__ldcg(ks + base - 1) >> seg_shift) : 0u;
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            if (base + k < n) {
+                const uint32_t cur = __ldcg(ks + base + k) >> seg_shift;
+                my_heads += (base + k == 0 || cur != prev) ? 1u : 0u;
+                prev = cur;
+            }
+        }
+    }
+    {
+        uint32_t total;
+        (void)cta_excl_scan_256(my_heads, sm.warp_tot, &total);
+        if (tid == 0) cnt[g] = total;
+    }
+    if (!grid_barrier(sync, (++epoch) * G, &sm.ok)) return;
+    {
+        uint32_t part = 0;
+        for (int r = tid; r < g; r += kSortThreads) part += __ldcg(cnt + r);
+        uint32_t total;
+        (void)cta_excl_scan_256(part, sm.warp_tot, &total);
+        if (tid == 0) sm.carry = total;
+        __syncthreads();
+    }
+    for (int64_t t = tile0; t < tile1; ++t) {
+        const int64_t base = t * kSortTile + (int64_t)tid * kSortItems;
+        uint32_t seg[kSortItems];
+        uint32_t f = 0, tsum = 0;
+        uint32_t prev = (base > 0 && base < n) ? (__ldcg(ks + base - 1) >> seg_shift) : 0u;
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            seg[k] = 0;
+            if (base + k < n) {
+                const uint32_t cur = __ldcg(ks + base + k) >> seg_shift;
+                seg[k] = cur;
+                if (base + k == 0 || cur != prev) {
+                    f |= 1u << k;
+                    ++tsum;
+                }
+                prev = cur;
+            }
+        }
+        uint32_t tile_total;
+        uint32_t u = sm.carry + cta_excl_scan_256(tsum, sm.warp_tot, &tile_total);
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+            if (base + k < n) {
+                if (f & (1u << k)) {
+                    uniq_ids[u] = (int64_t)seg[k];
+                    seg_start[u] = (int32_t)(base + k);
+                    ++u;
+                }
+                if (pos_seg != nullptr) pos_seg[base + k] = (int32_t)u - 1;
+                if (base + k == n - 1) {  // the last element closes the list
+                    seg_start[u] = (int32_t)n;
+                    *n_unique = (int32_t)u;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sm.carry += tile_total;
+        __syncthreads();
+    }
+    if (n == 0 && g == 0 && tid == 0) {  // empty list (possible with a device-side count)
+        seg_start[0] = 0;
+        *n_unique = 0;
+    }
+}
+
 struct DedupLayout {
-    size_t keys_a, keys_b, vals_a, hist, tiles, total;
-    int nblocks_sort, nblocks_scan;
+    size_t keys_a, keys_b, vals_a, hist, tiles, phist, pcnt, psync, total;
+    int nblocks_sort, nblocks_scan, persist_ctas;
 };
 static DedupLayout dedup_layout(int64_t n) {
     DedupLayout L;
     L.nblocks_sort = (int)ceil_div(n > 0 ? n : 1, kSortTile);
     L.nblocks_scan = (int)ceil_div(n > 0 ? n : 1, kScanTile);
+    L.persist_ctas = L.nblocks_sort < kPersistMaxCtas ? L.nblocks_sort : kPersistMaxCtas;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     L.keys_a = off; off += align((size_t)n * 4);
@@ -522,8 +830,20 @@ static DedupLayout dedup_layout(int64_t n) {
     L.vals_a = off; off += align((size_t)n * 4);
     L.hist = off; off += align((size_t)kRadixBins * L.nblocks_sort * 4);
     L.tiles = off; off += align((size_t)(L.nblocks_scan + 1) * 4);
+    L.phist = off; off += align((size_t)4 * L.persist_ctas * kRadixBins * 4);   // one histogram per pass (key_bits <= 32)
+    L.pcnt = off; off += align((size_t)L.persist_ctas * 4);
+    L.psync = off; off += 256;
     L.total = off;
     return L;
+}
+
+// MAP_B200_DEDUP=multi selects the multi-launch pipeline (A/B measurements, fallback); default: the single-launch kernel
+static bool dedup_use_persistent() {
+    static const int mode = [] {
+        const char* e = getenv("MAP_B200_DEDUP");
+        return (e != nullptr && strcmp(e, "multi") == 0) ? 0 : 1;
+    }();
+    return mode != 0;
 }
 
 }  // namespace mapb
@@ -531,7 +851,7 @@ static DedupLayout dedup_layout(int64_t n) {
 extern "C" size_t map_dedup_workspace_bytes(int64_t n_ids) { return mapb::dedup_layout(n_ids).total; }
 
 extern "C" int map_dedup_ids_ex(const int64_t* ids, int64_t n, const int32_t* n_dev, int key_bits, int seg_shift, int64_t* uniq_ids,
-                                int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, void* workspace,
+                                int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, int32_t* pos_seg, void* workspace,
                                 size_t workspace_bytes, map_stream_t stream) {
     using namespace mapb;
     MAP_REQUIRE(ids && uniq_ids && seg_start && occ_sorted && n_unique && workspace, "map_dedup_ids: null pointer");
@@ -552,6 +872,17 @@ extern "C" int map_dedup_ids_ex(const int64_t* ids, int64_t n, const int32_t* n_
     uint32_t* tiles = reinterpret_cast<uint32_t*>(ws + L.tiles);
     uint32_t* occ = reinterpret_cast<uint32_t*>(occ_sorted);
     const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+    if (dedup_use_persistent()) {
+        unsigned* sync = reinterpret_cast<unsigned*>(ws + L.psync);
+        if (cudaMemsetAsync(sync, 0, 8, st) != cudaSuccess) {
+            set_error("map_dedup_ids: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MAP_ECUDA;
+        }
+        dedup_persistent_kernel<<<L.persist_ctas, kSortThreads, 0, st>>>(
+            ids, n, n_dev, passes, seg_shift, keys_a, keys_b, vals_a, occ, reinterpret_cast<uint32_t*>(ws + L.phist),
+            reinterpret_cast<uint32_t*>(ws + L.pcnt), sync, uniq_ids, seg_start, n_unique, pos_seg);
+        return check_launch("map_dedup_ids");
+    }
     // ping-pong so that the final values land in occ_sorted
     uint32_t* vin = (passes % 2 == 0) ? occ : vals_a;
     uint32_t* vout = (passes % 2 == 0) ? vals_a : occ;
@@ -561,27 +892,31 @@ extern "C" int map_dedup_ids_ex(const int64_t* ids, int64_t n, const int32_t* n_
     for (int p = 0; p < passes; ++p) {
         const int shift = p * kRadixBits;
         sort_hist_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, n, n_dev, shift, hist, L.nblocks_sort);
-        sort_scan_kernel<<<1, 1024, 0, st>>>(hist, L.nblocks_sort);
+        sort_scan_kernel<<<1, 1024, 0, st>>>(hist, L.nblocks_sort, n, n_dev);
         sort_scatter_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, vin, n, n_dev, shift, hist, L.nblocks_sort, kout, vout);
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
     // kin now holds the sorted keys, vin == occ_sorted
     heads_count_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles);
-    scan_single_cta_kernel<<<1, 1024, 0, st>>>(tiles, L.nblocks_scan);
-    heads_emit_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles, uniq_ids, seg_start, n_unique);
+    scan_single_cta_kernel<<<1, 1024, 0, st>>>(tiles, L.nblocks_scan, n, n_dev);
+    heads_emit_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles, uniq_ids, seg_start, n_unique, pos_seg);
     return check_launch("map_dedup_ids");
 }
+
+/* 1 = the single-launch pipeline is selected (MAP_B200_DEDUP != "multi"): launch accounting of the host side */
+extern "C" int map_dedup_single_launch(void) { return mapb::dedup_use_persistent() ? 1 : 0; }
 
 extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_t* uniq_ids, int32_t* seg_start,
                              int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,
                              map_stream_t stream) {
-    return map_dedup_ids_ex(ids, n, nullptr, key_bits, 0, uniq_ids, seg_start, occ_sorted, n_unique, workspace, workspace_bytes, stream);
+    return map_dedup_ids_ex(ids, n, nullptr, key_bits, 0, uniq_ids, seg_start, occ_sorted, n_unique, nullptr, workspace, workspace_bytes,
+                            stream);
 }
 
 extern "C" int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
                                           const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
-                                          int64_t n_ids, const int32_t* n_dev, const int32_t* occ_map,
+                                          const int32_t* pos_seg, int64_t n_ids, const int32_t* n_dev, const int32_t* occ_map,
                                           const float* const* row_ptrs, int n_peers, int64_t rows_per_peer, float* grad_compact,
                                           float* scalar_out, map_stream_t stream) {
     using namespace mapb;
@@ -610,18 +945,18 @@ extern "C" int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, in
     const unsigned blocks = (unsigned)ceil_div(tiles, 256 / lanes);
     if (vec)
         segment_reduce_kernel<4><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids,
-                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer);
+                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer, pos_seg);
     else
         segment_reduce_kernel<1><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids,
-                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer);
+                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer, pos_seg);
     return check_launch("map_segment_reduce_rows");
 }
 
 extern "C" int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
                                        const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
                                        int64_t n_ids, float* grad_compact, float* scalar_out, map_stream_t stream) {
-    return map_segment_reduce_rows_ex(rows, ld_rows, D, scale, group, occ_sorted, seg_start, n_unique, n_ids, nullptr, nullptr, nullptr,
-                                      0, 0, grad_compact, scalar_out, stream);
+    return map_segment_reduce_rows_ex(rows, ld_rows, D, scale, group, occ_sorted, seg_start, n_unique, nullptr, n_ids, nullptr, nullptr,
+                                      nullptr, 0, 0, grad_compact, scalar_out, stream);
 }
 
 extern "C" int map_scatter_rows(const float* grad_compact, const int64_t* uniq_ids, const int32_t* n_unique,

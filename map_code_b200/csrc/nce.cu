@@ -207,7 +207,31 @@ __global__ void __launch_bounds__(256) scatter_add_slices_kernel(const float* __
     }
 }
 
+// ids[n, 0] = target[n], ids[n, 1 + k] = noise[n, k]: the id list of the NCE tables' gradient (what nce_fwd also emits as ids_out),
+// available as soon as the noise is drawn so that its sort can start before the forward pass
+__global__ void __launch_bounds__(256) nce_ids_concat_kernel(const int64_t* __restrict__ target, const int64_t* __restrict__ noise,
+                                                             int64_t N, int K, int64_t* __restrict__ ids) {
+    const int K1 = K + 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * K1; e += stride) {
+        const int64_t n = e / K1;
+        const int j = (int)(e - n * K1);
+        ids[e] = (j == 0) ? __ldg(target + n) : __ldg(noise + n * K + (j - 1));
+    }
+}
+
 }  // namespace mapb
+
+extern "C" int map_nce_ids_concat(const int64_t* target, const int64_t* noise, int64_t N, int K, int64_t* ids_out,
+                                  map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(target && noise && ids_out && N >= 0 && K >= 1, "map_nce_ids_concat: bad argument");
+    if (N == 0) return MAP_OK;
+    int64_t blocks = ceil_div(N * (K + 1), 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    nce_ids_concat_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(target, noise, N, K, ids_out);
+    return check_launch("map_nce_ids_concat");
+}
 
 static int nce_fwd_launch(const float* input, int64_t N, int P, int K, const int64_t* target, const int64_t* noise,
                           const mapb::PeerTable& emb_t, const mapb::PeerTable& bias_t, int R, const float* logprob_noise,

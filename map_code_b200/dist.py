@@ -319,6 +319,9 @@ class ShardedFusedStep(FusedStep):
     `batch_size` is the per-rank batch; the global batch is batch_size * world.  Philox counters are indexed by the global
     row, so the R-rank run reproduces the single-GPU run on the concatenated batch."""
 
+    # barrier sites of one step: ids sorted everywhere / NCE values complete / embedding values complete / end of step
+    BAR_KEYS, BAR_NCE, BAR_EMBED, BAR_END, N_BARRIER_SITES = 0, 1, 2, 3, 4
+
     def __init__(self, model, *, world: int, rank: int, group=None, **kw):
         self.world, self.rank, self.group = world, rank, group
         if world > 8:
@@ -330,13 +333,20 @@ class ShardedFusedStep(FusedStep):
         self.pm = PeerMemory(world, rank, next(model.parameters()).device, group)
         self._full_shapes: Dict[str, int] = {}
         super().__init__(model, **kw)
+        # Barriers: a one-warp kernel over peer-memory flags (map_p2p_barrier; one flag set per barrier site of the schedule, so
+        # barriers on different streams may overlap).  MAP_B200_BARRIER=nccl keeps the earlier 4-byte all-reduce on its own
+        # communicator (collectives of ONE communicator execute in issue order, and the barriers must not queue behind the
+        # 23 MB dense all-reduce that overlaps the embedding merge).
+        import os
+        self.barrier_kind = os.environ.get("MAP_B200_BARRIER", "p2p")
+        self.bar_flags = self.pm.alloc((self.N_BARRIER_SITES * 8,), torch.int32)
+        self.bar_epochs = torch.zeros(self.N_BARRIER_SITES, dtype=torch.int32, device=self.dev)
+        self.bar_error = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        # barriers travel on their own communicator: collectives of ONE communicator execute in issue order, and the barriers
-        # must not queue behind the 23 MB dense all-reduce that overlaps the embedding merge
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
         self.bar_group = dist.new_group(ranks=ranks, backend="nccl")
         if self.multi_stream:
-            for k in ("nce", "comm"):
+            for k in ("keys", "nce", "comm"):
                 self.streams[k] = torch.cuda.Stream(device=self.dev, priority=-1)
 
     # -- setup: shards, peer-visible compact gradients, merge plans
@@ -421,34 +431,57 @@ class ShardedFusedStep(FusedStep):
         self.tables[te.name], self.tables[tb.name] = te, tb
 
     # -- exchange primitives
-    def _barrier(self):
-        """stream-ordered barrier over the ranks (a 4-byte all-reduce): everything every rank issued before it on the calling
-        stream is complete and visible to peer loads after it"""
-        dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.bar_group)
-        _lib.mark("nccl_barrier")
-
-    def _merge(self, tables):
-        """tables share one id stream (plan + merge): pull the owned entries of all ranks and reduce them per local row"""
+    def _barrier(self, site: int):
+        """stream-ordered barrier over the ranks: everything every rank issued before it on the calling stream is complete and
+        visible to peer loads after it"""
         from . import ops
-        t0 = tables[0]
-        m, plan = t0.merge, t0.plan
+        if self.barrier_kind == "nccl":
+            dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.bar_group)
+            _lib.mark("nccl_barrier")
+        else:
+            ops.p2p_barrier(self.bar_flags.ptrs, self.world, self.rank, site, self.N_BARRIER_SITES, self.bar_epochs, self.bar_error)
+
+    def _merge_keys(self, table):
+        """KEY side of the owner-side merge (needs only ids): pull the owned entries of all ranks' unique-id lists and sort them
+        by (local row, source rank)"""
+        from . import ops
+        m, plan = table.merge, table.plan
         ops.owned_compact(plan.uniq_buf.ptrs, plan.n_unique_buf.ptrs, self.world, self.rank, m.cap, m.keys, m.src, m.n_owned)
         m.plan.run(m.keys)
+
+    def _merge_values(self, tables):
+        """VALUE side: tables share one id stream (plan + merge); reduce the ranks' compact gradient rows per local row"""
+        m = tables[0].merge
         for t in tables:
             m.plan.reduce_peer_rows(t.gbuf.ptrs, self.world, m.cap, t.D, m.src, out=t.grad_owned)
 
     # -- hooks of FusedStep
     def _embed_lookup(self, ids):
+        """Everything of the exchange that depends only on ids runs NOW on the 'keys' stream, under the forward GEMMs: the local
+        sorts of both id streams, one barrier, the owners' pulls and their sorts.  What is left for the backward are the value
+        reductions (local segment sums -> barrier -> owner-side sums over peer rows)."""
         from . import ops
         t = self.tables["embed.embedding.weight"]
+        mfp = self.mode == "MFP"
         self._fork("tab")
         with self._on("tab"):
             self._draw_noise()
-            t.plan.run(ids.view(-1))
+            if mfp:
+                ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
+            self._fork("keys")
+            with self._on("keys"):
+                te = self.tables["mfp_criterion.emb.weight"] if mfp else None
+                t.plan.run(ids.view(-1))
+                if mfp:
+                    te.plan.run(self.ids_all.view(-1))
+                self._barrier(self.BAR_KEYS)      # every rank's unique-id lists are complete
+                self._merge_keys(t)
+                if mfp:
+                    self._merge_keys(te)
         ops.emb_gather_sharded(t.shard.ptrs, self.world, t.V_full, self.D, ids, out=self.X0)
 
     def _embed_backward(self):
-        self._join("tab")
+        self._join("keys")
         t = self.tables["embed.embedding.weight"]
         t.plan.reduce_rows(self.dE, self.D, out=t.grad)
         if self.has_fm:
@@ -463,18 +496,18 @@ class ShardedFusedStep(FusedStep):
         self.acc_count.zero_()
         n_global = self.global_batch * L
         ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, None, None, crit.logprob_noise, self.norm_term, self.loss_type,
-                    grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all, loss_pos=self.loss_pos, dz=self.dz,
+                    grad_scale=1.0 / n_global, logits=self.logits, want_ids=False, loss_pos=self.loss_pos, dz=self.dz,
                     d_input=self.d_sel, acc_count=self.acc_count, shards=(te.shard.ptrs, tb.shard.ptrs, self.world))
-        # the NCE table-gradient chain has its own stream: the embedding backward (which joins 'tab') must not wait for it
+        # the NCE table-gradient chain has its own stream: the embedding backward must not wait for it
         self._fork("nce")
         with self._on("nce"):
             ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
-            te.plan.run(self.ids_all.view(-1))
+            self._join("keys")
             te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad.view(-1))
             # every rank has finished reading the NCE tables (its nce_fwd precedes this point) and its compact gradients are
             # complete: owners pull now, off the critical path of the backward pass
-            self._barrier()
-            self._merge([te, tb])
+            self._barrier(self.BAR_NCE)
+            self._merge_values([te, tb])
 
     def _join_streams(self):
         for name in self.streams:   # the NCE merge chain keeps running; the optimizer joins it
@@ -487,8 +520,8 @@ class ShardedFusedStep(FusedStep):
         with self._on("comm"):
             dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
             _lib.mark("nccl_all_reduce", ("bytes", self.grad_flat.numel() * 4))
-        self._barrier()          # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
-        self._merge([self.tables[n] for n in ("embed.embedding.weight", "lr_layer.embed_w.weight") if n in self.tables])
+        self._barrier(self.BAR_EMBED)   # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
+        self._merge_values([self.tables[n] for n in ("embed.embedding.weight", "lr_layer.embed_w.weight") if n in self.tables])
 
     def optimizer_step(self):
         from . import ops
@@ -502,7 +535,7 @@ class ShardedFusedStep(FusedStep):
                 ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
         # end-of-step barrier: every rank's pulls are complete (compact gradients may be overwritten) and every shard is
         # up to date (the next step's gathers may read it)
-        self._barrier()
+        self._barrier(self.BAR_END)
         self._join("comm")
         ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
 

@@ -381,7 +381,16 @@ class FusedStep:
             if self._early:      # every Philox consumer of this step has been issued: the step counter may advance
                 self._hyper_step()
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
+            self._nce_keys()
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
+
+    def _nce_keys(self):
+        """ids of the NCE tables' gradient = [labels | noise] (what nce_fwd consumes): known as soon as the noise is drawn, so
+        their sort (K2a) runs under the forward GEMMs instead of after the NCE kernel"""
+        if self.mode != "MFP":
+            return
+        ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
+        self.tables["mfp_criterion.emb.weight"].plan.run(self.ids_all.view(-1))
 
     def _draw_noise(self):
         if self.mode != "MFP":
@@ -500,14 +509,13 @@ class FusedStep:
         self.acc_count.zero_()
         n_global = self.global_batch * L
         ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
-                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
+                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, want_ids=False,
                     loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
-        # table gradients on the 'tab' stream: sort the (N, K+1) ids, reduce dz * input rows per unique id
+        # table gradients on the 'tab' stream: reduce dz * input rows per unique id (the ids were sorted at the start of the step)
         te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
         self._fork("tab")
         with self._on("tab"):
             ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
-            te.plan.run(self.ids_all.view(-1))
             te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
             if self._early and self.optimizer_mode == "sparse":
                 # nothing reads the two NCE tables again in this step: their row-wise AdamW runs here, under the backward GEMMs

@@ -63,6 +63,11 @@ def emb_gather_sharded(shard_ptrs, R: int, V: int, D: int, ids: torch.Tensor, ou
     return out
 
 
+def p2p_barrier(flag_ptrs, R: int, rank: int, site: int, n_sites: int, epochs: torch.Tensor, error_word: Optional[torch.Tensor] = None):
+    """stream-ordered barrier over the ranks through peer-memory flags (map_p2p_barrier)"""
+    call("map_p2p_barrier", flag_ptrs, R, rank, site, n_sites, epochs.data_ptr(), _ptr(error_word), _stream())
+
+
 def owned_compact(uniq_ptrs, n_unique_ptrs, R: int, rank: int, cap: int, keys: torch.Tensor, src: torch.Tensor, n_out: torch.Tensor):
     call("map_owned_compact", uniq_ptrs, n_unique_ptrs, R, rank, cap, keys.data_ptr(), src.data_ptr(), n_out.data_ptr(), _stream())
 
@@ -82,6 +87,7 @@ class DedupPlan:
         self.seg_start = torch.empty(self.n + 1, dtype=torch.int32, device=device)
         self.occ_sorted = torch.empty(self.n, dtype=torch.int32, device=device)
         self.n_unique = mk((1,), torch.int32)
+        self.pos_seg = torch.empty(self.n, dtype=torch.int32, device=device)   # sorted position -> segment index
         self.ws_bytes = int(_lib.load().map_dedup_workspace_bytes(self.n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
 
@@ -89,7 +95,8 @@ class DedupPlan:
         _check(ids, torch.int64, "ids")
         assert ids.numel() == self.n
         call("map_dedup_ids_ex", ids.data_ptr(), self.n, _ptr(self.n_dev), self.key_bits, self.seg_shift, self.uniq.data_ptr(),
-             self.seg_start.data_ptr(), self.occ_sorted.data_ptr(), self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws_bytes, _stream())
+             self.seg_start.data_ptr(), self.occ_sorted.data_ptr(), self.n_unique.data_ptr(), self.pos_seg.data_ptr(), self.ws.data_ptr(),
+             self.ws_bytes, _stream())
         return self
 
     def reduce_peer_rows(self, row_ptrs, n_peers: int, rows_per_peer: int, D: int, occ_map: torch.Tensor, out: torch.Tensor):
@@ -98,8 +105,8 @@ class DedupPlan:
         if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
             _lib.CURRENT_TAG = ("segred_peer", self.n, D)
         call("map_segment_reduce_rows_ex", None, D, D, None, 1, self.occ_sorted.data_ptr(), self.seg_start.data_ptr(),
-             self.n_unique.data_ptr(), self.n, _ptr(self.n_dev), occ_map.data_ptr(), row_ptrs, n_peers, rows_per_peer, out.data_ptr(),
-             None, _stream())
+             self.n_unique.data_ptr(), self.pos_seg.data_ptr(), self.n, _ptr(self.n_dev), occ_map.data_ptr(), row_ptrs, n_peers, rows_per_peer,
+             out.data_ptr(), None, _stream())
         return out
 
     def reduce_rows(self, rows: torch.Tensor, D: int, ld_rows: Optional[int] = None, scale: Optional[torch.Tensor] = None,
@@ -109,8 +116,8 @@ class DedupPlan:
         if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
             _lib.CURRENT_TAG = ("segred", self.n, D)
         call("map_segment_reduce_rows_ex", rows.data_ptr(), ld_rows if ld_rows is not None else D, D, _ptr(scale), group,
-             self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.n, _ptr(self.n_dev), None, None, 0, 0,
-             out.data_ptr(), _ptr(scalar_out), _stream())
+             self.occ_sorted.data_ptr(), self.seg_start.data_ptr(), self.n_unique.data_ptr(), self.pos_seg.data_ptr(), self.n, _ptr(self.n_dev),
+             None, None, 0, 0, out.data_ptr(), _ptr(scalar_out), _stream())
         return out
 
     def scatter_dense(self, grad_compact: torch.Tensor, D: int, dense: torch.Tensor):
@@ -268,6 +275,17 @@ def nce_fwd(inp, target, noise, emb, bias, logq, norm_term: float, loss_type: st
          logq.data_ptr(), emb.shape[0], float(norm_term), _lib.NCE_LOSS[loss_type], float(grad_scale), logits.data_ptr(),
          _ptr(ids_out), loss_pos.data_ptr(), dz.data_ptr(), _ptr(d_input), _ptr(acc_count), _stream())
     return logits, ids_out, loss_pos, dz, d_input
+
+
+def nce_ids_concat(target: torch.Tensor, noise: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[target | noise] -> ids [N, K+1] (index_linear.py:79-83), the id list of the NCE tables' gradient"""
+    _check(target, torch.int64, "target")
+    _check(noise, torch.int64, "noise")
+    N, K = noise.shape
+    if out is None:
+        out = torch.empty(N, K + 1, dtype=torch.int64, device=noise.device)
+    call("map_nce_ids_concat", target.data_ptr(), noise.data_ptr(), N, K, out.data_ptr(), _stream())
+    return out
 
 
 def gather_slices(enc: torch.Tensor, masked_index: torch.Tensor, F: int, P: int, out=None) -> torch.Tensor:
