@@ -245,6 +245,11 @@ def _lib_mod():
     return _lib
 
 
+if os.environ.get("MAP_B200_BENCH_VERBOSE"):   # where is the host when a run stalls?  (stack of every thread after 45 s)
+    import faulthandler
+    faulthandler.dump_traceback_later(45, exit=False, file=sys.stderr)
+
+
 def _stage(msg):
     if os.environ.get("MAP_B200_BENCH_VERBOSE"):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)

@@ -78,12 +78,11 @@ int map_segment_reduce_rows(const float* rows, int64_t ld_rows, int D, const flo
  *              (peer memory mapped with map_p2p_open; the loads travel over NVLink);
  *   pos_seg    (may be NULL) int32 [n_ids]: map_dedup_ids_ex writes the segment index of every sorted position; given to
  *              map_segment_reduce_rows_ex it replaces the per-tile binary search over seg_start.
- * map_dedup_ids_ex runs the whole pipeline as ONE launch of persistent CTAs with grid barriers (one barrier per radix pass);
- * the environment variable MAP_B200_DEDUP=multi selects the multi-launch pipeline (histogram / scan / scatter per pass). */
+ * map_dedup_ids(_ex) run the whole pipeline as ONE launch of persistent CTAs with grid barriers (one barrier per radix pass). */
 int map_dedup_ids_ex(const int64_t* ids, int64_t n_ids, const int32_t* n_dev, int key_bits, int seg_shift, int64_t* uniq_ids,
                      int32_t* seg_start, int32_t* occ_sorted, int32_t* n_unique, int32_t* pos_seg, void* workspace,
                      size_t workspace_bytes, map_stream_t stream);
-int map_dedup_single_launch(void);
+size_t map_dedup_debug_offset(int64_t n_ids); /* tuning aid: offset of the single-launch kernel's phase timestamps in the workspace */
 int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, int D, const float* scale, int group,
                                const int32_t* occ_sorted, const int32_t* seg_start, const int32_t* n_unique,
                                const int32_t* pos_seg, int64_t n_ids, const int32_t* n_dev, const int32_t* occ_map,

@@ -59,7 +59,7 @@ PROTOTYPES = {
     "map_dedup_ids": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "map_segment_reduce_rows": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _l, _p, _p, _p]),
     "map_dedup_ids_ex": (_i, [_p, _l, _p, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "map_dedup_single_launch": (_i, []),
+    "map_dedup_debug_offset": (_sz, [_l]),
     "map_segment_reduce_rows_ex": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p, _l, _p, _p, _p, _i, _l, _p, _p, _p]),
     "map_scatter_rows": (_i, [_p, _p, _p, _l, _i, _p, _p]),
     "map_adamw_hyper_step": (_i, [_p, _p, _d, _d, _d, _d, _i, _l, _l, _p]),
@@ -143,9 +143,6 @@ def last_error() -> str:
 
 # number of kernels one entry point launches (for the `gpu_launches` figure of bench.py)
 KERNELS_PER_CALL = {
-    # single launch (persistent CTAs) by default; MAP_B200_DEDUP=multi: prep + (hist, scan, scatter) per pass + heads (3)
-    "map_dedup_ids": lambda args: 1 if load().map_dedup_single_launch() else 1 + 3 * ((int(args[2]) + 7) // 8) + 3,
-    "map_dedup_ids_ex": lambda args: 1 if load().map_dedup_single_launch() else 1 + 3 * ((int(args[3]) + 7) // 8) + 3,
     "map_segment_reduce_rows_ex": 2, "map_p2p_alloc": 0, "map_p2p_open": 0, "map_p2p_close": 0, "map_p2p_free": 0,
     "map_segment_reduce_rows": 2, "map_reduce_sum_f32": 2, "map_bce_logits_fwd": 2, "map_colsum_f32": 2,
     "map_alias_build": 0,
@@ -155,7 +152,7 @@ CURRENT_TAG = None    # free-form shape tag set by ops.* just before a call (e.g
 LAUNCHES = None       # set to a dict: name -> number of kernels launched
 RECORD = None         # set to a list: (name, args, tag) of every call (arguments kept alive), for replaying one kernel class alone
 TIMELINE = None       # set to dict(buf=<device int64 tensor>, ops=[]): a timestamp marker follows every call on its stream
-HOST_FUNCS = {"map_alias_build", "map_dedup_single_launch", "map_gemm_set_trace", "map_p2p_alloc", "map_p2p_open", "map_p2p_close", "map_p2p_free"}
+HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace", "map_p2p_alloc", "map_p2p_open", "map_p2p_close", "map_p2p_free"}
 
 
 def mark(name: str, tag=None, stream: int = None):

@@ -2,9 +2,6 @@
 //   radix sort (id, occurrence)  ->  unique ids + segment starts  ->  segmented row sums.
 // Replaces aten::embedding_dense_backward (thrust sort + dense [V,D] grad) behind code/layers.py:98 and the dense
 // index_add behind code/nce/index_linear.py:99-100.  Everything is integer / HBM-L2 bound; no tensor cores.
-#include <stdlib.h>
-#include <string.h>
-
 #include "common.cuh"
 
 namespace mapb {
@@ -15,9 +12,6 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per CTA
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
 
 // The number of keys may live on the device (n_dev != nullptr: the owner-side merge of the row-sharded tables compacts a
 // data-dependent number of entries): grids are sized for the capacity n, every kernel clamps to min(n, *n_dev).
@@ -28,319 +22,103 @@ __device__ __forceinline__ int64_t eff_n(int64_t n, const int32_t* n_dev) {
 }
 
 // ---------------------------------------------------------------------------------------------- sort
-__global__ void __launch_bounds__(256) sort_prep_kernel(const int64_t* __restrict__ ids, int64_t n, const int32_t* n_dev,
-                                                        uint32_t* keys, uint32_t* vals) {
-    n = eff_n(n, n_dev);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        keys[i] = (uint32_t)ids[i];
-        vals[i] = (uint32_t)i;
-    }
-}
-
-// hist[block * 256 + bin] = #keys of this CTA's tile whose digit == bin
-__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, const int32_t* n_dev,
-                                                                 int shift, uint32_t* __restrict__ hist, int nblocks) {
-    __shared__ uint32_t sh[kRadixBins];
-    n = eff_n(n, n_dev);
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll
-    for (int it = 0; it < kSortItems; ++it) {
-        const int64_t i = base + it * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadixBins - 1)], 1u);
-    }
-    __syncthreads();
-    hist[(int64_t)blockIdx.x * kRadixBins + threadIdx.x] = sh[threadIdx.x];
-}
-
-// Exclusive scan of the digit histogram in (bin-major, block-minor) order, computed on the block-major array:
-// out[block][bin] = #keys with a smaller digit + #keys with this digit in earlier blocks.
-// One CTA of 1024 threads = 4 groups x 256 bins; each group walks a quarter of the blocks with 8 independent loads in
-// flight per thread (the old single-CTA linear scan was a 20 us latency chain per pass).
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* __restrict__ hist, int nblocks, int64_t n, const int32_t* n_dev) {
-    __shared__ uint32_t tot[4][kRadixBins];
-    {   // with a device-side count only the tiles that hold keys are scanned (the grids are sized for the capacity)
-        const int64_t live = (eff_n(n, n_dev) + kSortTile - 1) / kSortTile;
-        if (live < nblocks) nblocks = live > 0 ? (int)live : 1;
-    }
-    __shared__ uint32_t bin_excl[kRadixBins];
-    __shared__ uint32_t warp_tot[8];
-    const int bin = threadIdx.x & (kRadixBins - 1);
-    const int grp = threadIdx.x >> 8;
-    const int per = (nblocks + 3) >> 2;
-    const int b0 = grp * per;
-    const int b1 = (b0 + per < nblocks) ? b0 + per : nblocks;
-    uint32_t sum = 0;
-    int b = b0;
-    for (; b + 8 <= b1; b += 8) {
-        uint32_t c[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = hist[(int64_t)(b + k) * kRadixBins + bin];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sum += c[k];
-    }
-    for (; b < b1; ++b) sum += hist[(int64_t)b * kRadixBins + bin];
-    tot[grp][bin] = sum;
-    __syncthreads();
-    if (threadIdx.x < kRadixBins) {  // exclusive scan of the 256 bin totals
-        const uint32_t t = tot[0][bin] + tot[1][bin] + tot[2][bin] + tot[3][bin];
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        uint32_t incl = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) warp_tot[w] = incl;
-        bin_excl[bin] = incl - t;
-    }
-    __syncthreads();
-    if (threadIdx.x < kRadixBins) {
-        uint32_t off = 0;
-        for (int w = 0; w < (threadIdx.x >> 5); ++w) off += warp_tot[w];
-        bin_excl[bin] += off;
-    }
-    __syncthreads();
-    uint32_t run = bin_excl[bin];
-    for (int g = 0; g < grp; ++g) run += tot[g][bin];
-    b = b0;
-    for (; b + 8 <= b1; b += 8) {
-        uint32_t c[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = hist[(int64_t)(b + k) * kRadixBins + bin];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            hist[(int64_t)(b + k) * kRadixBins + bin] = run;
-            run += c[k];
-        }
-    }
-    for (; b < b1; ++b) {
-        const uint32_t c = hist[(int64_t)b * kRadixBins + bin];
-        hist[(int64_t)b * kRadixBins + bin] = run;
-        run += c;
-    }
-}
-
-// In-place exclusive scan of `data[0..len)` by ONE CTA of 1024 threads (len <= a few million: bins*nblocks).
-__global__ void __launch_bounds__(1024) scan_single_cta_kernel(uint32_t* data, int64_t len, int64_t n, const int32_t* n_dev) {
-    __shared__ uint32_t warp_tot[32];
-    {
-        const int64_t live = (eff_n(n, n_dev) + kScanTile - 1) / kScanTile;
-        if (live < len) len = live > 0 ? live : 1;
-    }
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
+// exclusive scan of one value per thread over the 256 threads of the CTA (warp_tot: scratch); returns the exclusive prefix,
+// *total = sum over the CTA
+__device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t t, uint32_t* warp_tot, uint32_t* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // each thread owns 4 consecutive elements per chunk of 4096
-    for (int64_t chunk = 0; chunk < len; chunk += 4096) {
-        const int64_t i0 = chunk + (int64_t)threadIdx.x * 4;
-        uint32_t x[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = (i0 + k < len) ? data[i0 + k] : 0u;
-        const uint32_t tsum = x[0] + x[1] + x[2] + x[3];
-        uint32_t incl = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_tot[lane];
-            uint32_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += y;
-            }
-            warp_tot[lane] = wi - w;  // exclusive warp offsets
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_tot[warp] + (incl - tsum);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < len) data[i0 + k] = excl;
-            excl += x[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl;  // total so far (thread 1023 owns the chunk's last elements)
-        __syncthreads();
-    }
-}
-
-// Stable scatter of one digit.  Order inside a tile is (item round, thread) == ascending index.  Ranks are computed per warp
-// with match.any and combined across warps / rounds through shared-memory counters; the tile is then REORDERED IN SHARED
-// MEMORY by digit so that the global writes of one digit are contiguous (coalesced runs instead of 32 scattered 4-byte
-// stores per warp instruction).
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                    const uint32_t* __restrict__ vals_in, int64_t n,
-                                                                    const int32_t* n_dev, int shift,
-                                                                    const uint32_t* __restrict__ hist_scanned,
-                                                                    int nblocks, uint32_t* __restrict__ keys_out,
-                                                                    uint32_t* __restrict__ vals_out) {
-    __shared__ uint32_t warp_cnt[kSortWarps][kRadixBins];  // per-round per-warp digit counts -> exclusive prefixes
-    __shared__ uint32_t tile_run[kRadixBins];              // running count of each digit over the rounds done so far
-    __shared__ uint32_t tile_excl[kRadixBins];             // exclusive scan over digits of the tile histogram
-    __shared__ uint32_t gbase[kRadixBins];                 // global start of (digit, this tile)
-    __shared__ uint32_t warp_tot[kSortWarps];
-    __shared__ uint32_t keys_s[kSortTile];
-    __shared__ uint32_t vals_s[kSortTile];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    n = eff_n(n, n_dev);
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-    if (base >= n) return;  // (uniform) tile beyond a device-side count
-    const int tile_n = (int)((n - base < kSortTile) ? (n - base) : kSortTile);
-    gbase[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * kRadixBins + threadIdx.x];
-    tile_run[threadIdx.x] = 0;
-    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
-    // ---- pass A: load, and rank every key among the keys of the same digit that precede it in the tile
-    for (int it = 0; it < kSortItems; ++it) {
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) warp_cnt[w][threadIdx.x] = 0;
-        __syncthreads();
-        const int li = it * kSortThreads + threadIdx.x;
-        const bool valid = li < tile_n;
-        key[it] = valid ? keys_in[base + li] : 0u;
-        val[it] = valid ? vals_in[base + li] : 0u;
-        const uint32_t digit = valid ? ((key[it] >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank_in_warp == 0) warp_cnt[warp][digit] = __popc(peers);
-        __syncthreads();
-        {   // thread d: exclusive prefix of digit d over the warps of this round, on top of the rounds before
-            uint32_t run = tile_run[threadIdx.x];
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
-                const uint32_t c = warp_cnt[w][threadIdx.x];
-                warp_cnt[w][threadIdx.x] = run;
-                run += c;
-            }
-            tile_run[threadIdx.x] = run;
-        }
-        __syncthreads();
-        rank[it] = valid ? warp_cnt[warp][digit] + rank_in_warp : 0u;
-        __syncthreads();
-    }
-    // ---- exclusive scan of the tile histogram (tile_run now holds the per-digit totals)
-    {
-        const uint32_t t = tile_run[threadIdx.x];
-        uint32_t incl = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t off = 0;
-        for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        tile_excl[threadIdx.x] = off + incl - t;
-    }
-    __syncthreads();
-    // ---- pass B: reorder the tile by digit in shared memory (stable)
-#pragma unroll
-    for (int it = 0; it < kSortItems; ++it) {
-        const int li = it * kSortThreads + threadIdx.x;
-        if (li < tile_n) {
-            const uint32_t digit = (key[it] >> shift) & (kRadixBins - 1);
-            const uint32_t lp = tile_excl[digit] + rank[it];
-            keys_s[lp] = key[it];
-            vals_s[lp] = val[it];
-        }
-    }
-    __syncthreads();
-    // ---- pass C: position i of the reordered tile goes to gbase[digit] + (i - tile_excl[digit])
-    for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
-        const uint32_t k = keys_s[i];
-        const uint32_t digit = (k >> shift) & (kRadixBins - 1);
-        const uint32_t pos = gbase[digit] + ((uint32_t)i - tile_excl[digit]);
-        keys_out[pos] = k;
-        vals_out[pos] = vals_s[i];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- unique / segments
-// keys that agree above `seg_shift` belong to one segment (the low bits order the occurrences of a row deterministically,
-// e.g. by source rank in the sharded merge)
-__device__ __forceinline__ uint32_t head_flag(const uint32_t* keys, int64_t i, int seg_shift) {
-    return (i == 0 || (keys[i] >> seg_shift) != (keys[i - 1] >> seg_shift)) ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(kScanThreads) heads_count_kernel(const uint32_t* __restrict__ keys, int64_t n,
-                                                                   const int32_t* n_dev, int seg_shift,
-                                                                   uint32_t* __restrict__ tile_sums) {
-    __shared__ uint32_t sh[kScanThreads / 32];
-    n = eff_n(n, n_dev);
-    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    uint32_t c = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
-        if (base + k < n) c += head_flag(keys, base + k, seg_shift);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kScanThreads / 32; ++w) t += sh[w];
-        tile_sums[blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(kScanThreads) heads_emit_kernel(const uint32_t* __restrict__ keys, int64_t n,
-                                                                  const int32_t* n_dev, int seg_shift,
-                                                                  const uint32_t* __restrict__ tile_offsets,
-                                                                  int64_t* __restrict__ uniq_ids,
-                                                                  int32_t* __restrict__ seg_start,
-                                                                  int32_t* __restrict__ n_unique,
-                                                                  int32_t* __restrict__ pos_seg) {
-    __shared__ uint32_t warp_tot[kScanThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    n = eff_n(n, n_dev);
-    if (n == 0) {  // empty list (possible with a device-side count)
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            seg_start[0] = 0;
-            *n_unique = 0;
-        }
-        return;
-    }
-    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    uint32_t f[kScanItems];
-    uint32_t tsum = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        f[k] = (base + k < n) ? head_flag(keys, base + k, seg_shift) : 0u;
-        tsum += f[k];
-    }
-    uint32_t incl = tsum;
+    uint32_t incl = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
     }
+    __syncthreads();   // warp_tot may still be read by the previous use
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
-    uint32_t u = tile_offsets[blockIdx.x] + woff + (incl - tsum);
+    uint32_t off = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        if (f[k]) {
-            uniq_ids[u] = (int64_t)(keys[base + k] >> seg_shift);
-            seg_start[u] = (int32_t)(base + k);
-            ++u;
-        }
-        if (pos_seg != nullptr && base + k < n) pos_seg[base + k] = (int32_t)u - 1;
-        if (base + k == n - 1) {  // the last element closes the list
-            seg_start[u] = (int32_t)n;
-            *n_unique = (int32_t)u;
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t x = warp_tot[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    if (total != nullptr) *total = tot;
+    return off + incl - t;
+}
+
+// one shared-memory atomic per distinct digit of the warp (the <mask> row alone is 8 % of the embedding ids: per-key atomics on
+// one counter serialise)
+__device__ __forceinline__ void warp_hist_add(uint32_t* sh, uint32_t digit, bool valid) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 0xFFFFFFFFu);
+    if (valid && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&sh[digit], (uint32_t)__popc(peers));
+}
+
+// Shared-memory state of one 2048-key tile
+struct TileSmem {
+    uint32_t warp_cnt[kSortWarps][kRadixBins];  // per-warp digit counts -> exclusive prefixes over the warps
+    uint32_t tile_run[kRadixBins];              // digit counts of the tile
+    uint32_t tile_excl[kRadixBins];             // their exclusive scan
+    uint32_t gbase[kRadixBins];                 // global start of (digit, this tile)
+    uint32_t warp_tot[kSortWarps];
+    uint32_t keys_s[kSortTile];
+    uint32_t vals_s[kSortTile];
+};
+
+// Loads a tile, ranks every key among the keys of the same digit that precede it, and reorders the tile by digit in shared
+// memory (stable) so that the global writes of one digit are contiguous runs.  Element order inside the tile is
+// (warp, round, lane) == ascending index: warp w owns the contiguous keys [256 w, 256 w + 256) and ranks them against its OWN
+// histogram row with match.any — no CTA-wide synchronisation inside the 8 rounds (the earlier version met at 3 barriers per
+// round) — then one pass over the 8 rows turns them into exclusive prefixes over the warps.
+// On return: tile_run[d] = #keys of digit d, tile_excl[d] = exclusive scan, keys_s / vals_s = the tile sorted by digit.
+template <typename LoadKey, typename LoadVal>
+__device__ __forceinline__ void tile_rank_reorder(TileSmem& sm, int tile_n, int shift, LoadKey load_key, LoadVal load_val) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) sm.warp_cnt[w][tid] = 0;
+    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+#pragma unroll
+    for (int it = 0; it < kSortItems; ++it) {
+        const int li = warp * (kSortItems * 32) + it * 32 + lane;
+        const bool valid = li < tile_n;
+        key[it] = valid ? load_key(li) : 0u;
+        val[it] = valid ? load_val(li) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; ++it) {
+        const int li = warp * (kSortItems * 32) + it * 32 + lane;
+        const bool valid = li < tile_n;
+        const uint32_t digit = valid ? ((key[it] >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t before = valid ? sm.warp_cnt[warp][digit] : 0u;
+        __syncwarp();
+        if (valid && rank_in_warp == 0) sm.warp_cnt[warp][digit] = before + __popc(peers);
+        __syncwarp();
+        rank[it] = before + rank_in_warp;
+    }
+    __syncthreads();
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = sm.warp_cnt[w][tid];
+        sm.warp_cnt[w][tid] = run;
+        run += c;
+    }
+    sm.tile_run[tid] = run;
+    sm.tile_excl[tid] = cta_excl_scan_256(run, sm.warp_tot, nullptr);
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSortItems; ++it) {
+        const int li = warp * (kSortItems * 32) + it * 32 + lane;
+        if (li < tile_n) {
+            const uint32_t digit = (key[it] >> shift) & (kRadixBins - 1);
+            const uint32_t lp = sm.tile_excl[digit] + sm.warp_cnt[warp][digit] + rank[it];
+            sm.keys_s[lp] = key[it];
+            sm.vals_s[lp] = val[it];
         }
     }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------- segmented row sums
@@ -528,12 +306,13 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------- single-launch pipeline
 // The whole of K2a (key extraction, every radix pass, head flags, unique ids / segment starts / position -> segment map) as
-// ONE launch of persistent CTAs that meet at grid barriers.  At the step's sizes (n = 1.6e5 .. 3.2e5 keys) the multi-launch
-// pipeline above is a chain of 13 dependent launches of a few microseconds each — launch/drain latency, not bandwidth; here a
-// pass costs one barrier:
+// ONE launch of persistent CTAs that meet at grid barriers.  At the step's sizes (n = 1.6e5 .. 3.2e5 keys) a pipeline of
+// separate launches (prep, {histogram, scan, scatter} per pass, head count, scan, emit: 13 dependent launches of a few
+// microseconds each, what this file did until r01e: 89 us for 1.6e5 keys) is launch/drain latency, not bandwidth; here a pass
+// costs one barrier (41 us for the same keys):
 //   H   CTA g builds the digit-0 histogram of its contiguous key range                              -> hist[0][g][256]
 //   S_p thread b sums column b of hist[p] (all G rows: totals; rows < g: its own prefix), the CTA scans the 256 totals, then
-//       ranks / reorders / scatters its tiles exactly like sort_scatter_kernel; while writing key k to position `pos` it also
+//       ranks / reorders / scatters its tiles (tile_rank_reorder); while writing key k to position `pos` it also
 //       counts k's NEXT digit into hist[p+1][owner CTA of pos] (global reductions), so pass p+1 needs no histogram sweep
 //   U   head flags of the sorted keys: per-CTA counts -> barrier -> every CTA emits its range at its prefix
 // G <= 2 CTAs per SM (256 threads, < 32 KB shared memory), so all CTAs are co-resident on an otherwise idle GPU; beside other
@@ -570,56 +349,42 @@ __device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned target, in
     return *ok_s != 0;
 }
 
-struct PersistSmem {
-    uint32_t warp_cnt[kSortWarps][kRadixBins];
-    uint32_t tile_run[kRadixBins];
-    uint32_t tile_excl[kRadixBins];
-    uint32_t gbase[kRadixBins];
-    uint32_t warp_tot[kSortWarps];
-    uint32_t keys_s[kSortTile];
-    uint32_t vals_s[kSortTile];
+struct PersistSmem : TileSmem {
     uint32_t carry;
     int ok;
 };
 
-// exclusive scan of one value per thread over the 256 threads of the CTA (warp_tot: scratch); returns the exclusive prefix,
-// *total = sum over the CTA
-__device__ __forceinline__ uint32_t cta_excl_scan_256(uint32_t t, uint32_t* warp_tot, uint32_t* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = t;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-    }
-    __syncthreads();   // warp_tot may still be read by the previous use
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t x = warp_tot[w];
-        if (w < warp) off += x;
-        tot += x;
-    }
-    if (total != nullptr) *total = tot;
-    return off + incl - t;
-}
-
-__global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
+__global__ void __launch_bounds__(kSortThreads, 3) dedup_persistent_kernel(
     const int64_t* __restrict__ ids, int64_t n_cap, const int32_t* __restrict__ n_dev, int passes, int seg_shift, uint32_t* keys_a,
     uint32_t* keys_b, uint32_t* vals_a, uint32_t* occ, uint32_t* hist, uint32_t* cnt, unsigned* sync, int64_t* __restrict__ uniq_ids,
     int32_t* __restrict__ seg_start, int32_t* __restrict__ n_unique, int32_t* __restrict__ pos_seg) {
     __shared__ PersistSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, g = blockIdx.x;
+    const int g = blockIdx.x;
     const int64_t n = eff_n(n_cap, n_dev);
     const int64_t ntiles = (n + kSortTile - 1) / kSortTile;
-    int64_t tpc = (ntiles + G - 1) / G;
+    // with a device-side count (owner-side merge: the grid is sized for the capacity R * cap) only as many CTAs as there are
+    // tiles take part: the others leave at once and the barriers / column sums span G rows only
+    const int G = ((int64_t)gridDim.x < ntiles) ? (int)gridDim.x : (ntiles > 0 ? (int)ntiles : 1);
+    if (g >= G) return;
+    uint32_t tpc = (uint32_t)((ntiles + G - 1) / G);   // tiles per CTA
     if (tpc < 1) tpc = 1;
     const int64_t tile0 = (int64_t)g * tpc;
     const int64_t tile1 = (tile0 + tpc < ntiles) ? tile0 + tpc : ntiles;   // (tile0 >= tile1: this CTA only attends the barriers)
     unsigned epoch = 0;
+    // phase timestamps of CTA 0 (globaltimer ns) behind the two sync words: start, H, barrier, then per pass (column sums,
+    // tiles, barrier), head count, barrier, emit — read back through map_dedup_debug_offset (tuning aid, one store per phase)
+    unsigned long long* stamps = reinterpret_cast<unsigned long long*>(sync + 16);
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (g == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            stamps[n_stamp] = t;
+        }
+        ++n_stamp;
+    };
+    stamp();
 
     // ---- H: digit-0 histogram of the own range (keys come straight from the int64 ids); rows of the later passes start at 0
     sm.tile_run[tid] = 0;
@@ -630,12 +395,15 @@ __global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
 #pragma unroll
         for (int it = 0; it < kSortItems; ++it) {
             const int64_t i = base + it * kSortThreads + tid;
-            if (i < n) atomicAdd(&sm.tile_run[(uint32_t)ids[i] & (kRadixBins - 1)], 1u);
+            const bool valid = i < n;
+            warp_hist_add(sm.tile_run, valid ? ((uint32_t)ids[i] & (kRadixBins - 1)) : 0u, valid);
         }
     }
     __syncthreads();
     hist[(size_t)g * kRadixBins + tid] = sm.tile_run[tid];
+    stamp();
     if (!grid_barrier(sync, (++epoch) * G, &sm.ok)) return;
+    stamp();
 
     // ---- S_p
     for (int p = 0; p < passes; ++p) {
@@ -650,94 +418,66 @@ __global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
             const uint32_t* h = hist + (size_t)p * G * kRadixBins + tid;
             uint32_t tot = 0, pre = 0;
             int r = 0;
-            for (; r + 8 <= G; r += 8) {
-                uint32_t c[8];
+            for (; r + 32 <= G; r += 32) {   // 32 independent L2 loads in flight per thread: the walk is latency-bound
+                uint32_t c[32];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) c[k] = __ldcg(h + (size_t)(r + k) * kRadixBins);
+                for (int k = 0; k < 32; ++k) c[k] = __ldcg(h + (size_t)(r + k) * kRadixBins);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 32; ++k) {
                     tot += c[k];
                     if (r + k < g) pre += c[k];
                 }
             }
-            for (; r < G; ++r) {
-                const uint32_t c = __ldcg(h + (size_t)r * kRadixBins);
-                tot += c;
-                if (r < g) pre += c;
+            {   // tail: the same batch with a row guard
+                uint32_t c[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) c[k] = (r + k < G) ? __ldcg(h + (size_t)(r + k) * kRadixBins) : 0u;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    tot += c[k];
+                    if (r + k < g) pre += c[k];
+                }
             }
             const uint32_t excl = cta_excl_scan_256(tot, sm.warp_tot, nullptr);
             sm.gbase[tid] = excl + pre;
         }
         __syncthreads();
+        stamp();
         for (int64_t t = tile0; t < tile1; ++t) {
             const int64_t base = t * kSortTile;
             const int tile_n = (int)((n - base < kSortTile) ? (n - base) : kSortTile);
-            sm.tile_run[tid] = 0;
-            uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
-            // pass A: load, rank every key among the keys of the same digit that precede it in the tile
-            for (int it = 0; it < kSortItems; ++it) {
-#pragma unroll
-                for (int w = 0; w < kSortWarps; ++w) sm.warp_cnt[w][tid] = 0;
-                __syncthreads();
-                const int li = it * kSortThreads + tid;
-                const bool valid = li < tile_n;
-                if (p == 0) {
-                    key[it] = valid ? (uint32_t)ids[base + li] : 0u;
-                    val[it] = (uint32_t)(base + li);
-                } else {
-                    key[it] = valid ? __ldcg(kin + base + li) : 0u;
-                    val[it] = valid ? __ldcg(vin + base + li) : 0u;
+            if (p == 0)
+                tile_rank_reorder(sm, tile_n, shift, [&](int li) { return (uint32_t)ids[base + li]; },
+                                  [&](int li) { return (uint32_t)(base + li); });
+            else
+                tile_rank_reorder(sm, tile_n, shift, [&](int li) { return __ldcg(kin + base + li); },
+                                  [&](int li) { return __ldcg(vin + base + li); });
+            // coalesced runs to global memory + the next pass's histogram of the destination range (one reduction per distinct
+            // (owner CTA, next digit) of the warp: hot keys would otherwise serialise on one L2 address)
+            for (int i0 = 0; i0 < tile_n; i0 += kSortThreads) {
+                const int i = i0 + tid;
+                const bool valid = i < tile_n;
+                uint32_t code = 0xFFFFFFFFu;
+                if (valid) {
+                    const uint32_t k = sm.keys_s[i];
+                    const uint32_t digit = (k >> shift) & (kRadixBins - 1);
+                    const uint32_t pos = sm.gbase[digit] + ((uint32_t)i - sm.tile_excl[digit]);
+                    kout[pos] = k;
+                    vout[pos] = sm.vals_s[i];
+                    code = (uint32_t)((pos / kSortTile) / tpc) * kRadixBins + ((k >> (shift + kRadixBits)) & (kRadixBins - 1));
                 }
-                const uint32_t digit = valid ? ((key[it] >> shift) & (kRadixBins - 1)) : 0xFFFFFFFFu;
-                const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-                const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-                if (valid && rank_in_warp == 0) sm.warp_cnt[warp][digit] = __popc(peers);
-                __syncthreads();
-                {
-                    uint32_t run = sm.tile_run[tid];
-#pragma unroll
-                    for (int w = 0; w < kSortWarps; ++w) {
-                        const uint32_t c = sm.warp_cnt[w][tid];
-                        sm.warp_cnt[w][tid] = run;
-                        run += c;
-                    }
-                    sm.tile_run[tid] = run;
-                }
-                __syncthreads();
-                rank[it] = valid ? sm.warp_cnt[warp][digit] + rank_in_warp : 0u;
-                __syncthreads();
-            }
-            sm.tile_excl[tid] = cta_excl_scan_256(sm.tile_run[tid], sm.warp_tot, nullptr);
-            __syncthreads();
-            // pass B: stable reorder by digit in shared memory
-#pragma unroll
-            for (int it = 0; it < kSortItems; ++it) {
-                const int li = it * kSortThreads + tid;
-                if (li < tile_n) {
-                    const uint32_t digit = (key[it] >> shift) & (kRadixBins - 1);
-                    const uint32_t lp = sm.tile_excl[digit] + rank[it];
-                    sm.keys_s[lp] = key[it];
-                    sm.vals_s[lp] = val[it];
-                }
-            }
-            __syncthreads();
-            // pass C: coalesced runs to global memory + the next pass's histogram of the destination range
-            for (int i = tid; i < tile_n; i += kSortThreads) {
-                const uint32_t k = sm.keys_s[i];
-                const uint32_t digit = (k >> shift) & (kRadixBins - 1);
-                const uint32_t pos = sm.gbase[digit] + ((uint32_t)i - sm.tile_excl[digit]);
-                kout[pos] = k;
-                vout[pos] = sm.vals_s[i];
                 if (!last) {
-                    const uint32_t owner = (uint32_t)((pos / kSortTile) / tpc);
-                    atomicAdd(hnext + (size_t)owner * kRadixBins + ((k >> (shift + kRadixBits)) & (kRadixBins - 1)), 1u);
+                    const uint32_t peers = __match_any_sync(0xffffffffu, code);
+                    if (valid && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(hnext + code, (uint32_t)__popc(peers));
                 }
             }
             __syncthreads();
             sm.gbase[tid] += sm.tile_run[tid];
             __syncthreads();
         }
+        stamp();
         if (!grid_barrier(sync, (++epoch) * G, &sm.ok)) return;
+        stamp();
     }
 
     // ---- U: head flags.  sorted keys are in the buffer the last pass wrote
@@ -760,7 +500,9 @@ __global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
         (void)cta_excl_scan_256(my_heads, sm.warp_tot, &total);
         if (tid == 0) cnt[g] = total;
     }
+    stamp();
     if (!grid_barrier(sync, (++epoch) * G, &sm.ok)) return;
+    stamp();
     {
         uint32_t part = 0;
         for (int r = tid; r < g; r += kSortThreads) part += __ldcg(cnt + r);
@@ -808,6 +550,7 @@ __global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
         if (tid == 0) sm.carry += tile_total;
         __syncthreads();
     }
+    stamp();
     if (n == 0 && g == 0 && tid == 0) {  // empty list (possible with a device-side count)
         seg_start[0] = 0;
         *n_unique = 0;
@@ -815,35 +558,23 @@ __global__ void __launch_bounds__(kSortThreads) dedup_persistent_kernel(
 }
 
 struct DedupLayout {
-    size_t keys_a, keys_b, vals_a, hist, tiles, phist, pcnt, psync, total;
-    int nblocks_sort, nblocks_scan, persist_ctas;
+    size_t keys_a, keys_b, vals_a, phist, pcnt, psync, total;
+    int persist_ctas;
 };
 static DedupLayout dedup_layout(int64_t n) {
     DedupLayout L;
-    L.nblocks_sort = (int)ceil_div(n > 0 ? n : 1, kSortTile);
-    L.nblocks_scan = (int)ceil_div(n > 0 ? n : 1, kScanTile);
-    L.persist_ctas = L.nblocks_sort < kPersistMaxCtas ? L.nblocks_sort : kPersistMaxCtas;
+    const int64_t ntiles = ceil_div(n > 0 ? n : 1, kSortTile);
+    L.persist_ctas = ntiles < kPersistMaxCtas ? (int)ntiles : kPersistMaxCtas;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     L.keys_a = off; off += align((size_t)n * 4);
     L.keys_b = off; off += align((size_t)n * 4);
     L.vals_a = off; off += align((size_t)n * 4);
-    L.hist = off; off += align((size_t)kRadixBins * L.nblocks_sort * 4);
-    L.tiles = off; off += align((size_t)(L.nblocks_scan + 1) * 4);
     L.phist = off; off += align((size_t)4 * L.persist_ctas * kRadixBins * 4);   // one histogram per pass (key_bits <= 32)
     L.pcnt = off; off += align((size_t)L.persist_ctas * 4);
-    L.psync = off; off += 256;
+    L.psync = off; off += 512;   // 2 sync words, then (at +64) up to 32 phase timestamps
     L.total = off;
     return L;
-}
-
-// MAP_B200_DEDUP=multi selects the multi-launch pipeline (A/B measurements, fallback); default: the single-launch kernel
-static bool dedup_use_persistent() {
-    static const int mode = [] {
-        const char* e = getenv("MAP_B200_DEDUP");
-        return (e != nullptr && strcmp(e, "multi") == 0) ? 0 : 1;
-    }();
-    return mode != 0;
 }
 
 }  // namespace mapb
@@ -865,47 +596,22 @@ extern "C" int map_dedup_ids_ex(const int64_t* ids, int64_t n, const int32_t* n_
     }
     cudaStream_t st = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
-    uint32_t* keys_a = reinterpret_cast<uint32_t*>(ws + L.keys_a);
-    uint32_t* keys_b = reinterpret_cast<uint32_t*>(ws + L.keys_b);
-    uint32_t* vals_a = reinterpret_cast<uint32_t*>(ws + L.vals_a);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + L.hist);
-    uint32_t* tiles = reinterpret_cast<uint32_t*>(ws + L.tiles);
-    uint32_t* occ = reinterpret_cast<uint32_t*>(occ_sorted);
     const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
-    if (dedup_use_persistent()) {
-        unsigned* sync = reinterpret_cast<unsigned*>(ws + L.psync);
-        if (cudaMemsetAsync(sync, 0, 8, st) != cudaSuccess) {
-            set_error("map_dedup_ids: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return MAP_ECUDA;
-        }
-        dedup_persistent_kernel<<<L.persist_ctas, kSortThreads, 0, st>>>(
-            ids, n, n_dev, passes, seg_shift, keys_a, keys_b, vals_a, occ, reinterpret_cast<uint32_t*>(ws + L.phist),
-            reinterpret_cast<uint32_t*>(ws + L.pcnt), sync, uniq_ids, seg_start, n_unique, pos_seg);
-        return check_launch("map_dedup_ids");
+    unsigned* sync = reinterpret_cast<unsigned*>(ws + L.psync);
+    if (cudaMemsetAsync(sync, 0, 8, st) != cudaSuccess) {   // arrival counter + error word of the grid barriers
+        set_error("map_dedup_ids: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MAP_ECUDA;
     }
-    // ping-pong so that the final values land in occ_sorted
-    uint32_t* vin = (passes % 2 == 0) ? occ : vals_a;
-    uint32_t* vout = (passes % 2 == 0) ? vals_a : occ;
-    uint32_t* kin = keys_a;
-    uint32_t* kout = keys_b;
-    sort_prep_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ids, n, n_dev, kin, vin);
-    for (int p = 0; p < passes; ++p) {
-        const int shift = p * kRadixBits;
-        sort_hist_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, n, n_dev, shift, hist, L.nblocks_sort);
-        sort_scan_kernel<<<1, 1024, 0, st>>>(hist, L.nblocks_sort, n, n_dev);
-        sort_scatter_kernel<<<L.nblocks_sort, kSortThreads, 0, st>>>(kin, vin, n, n_dev, shift, hist, L.nblocks_sort, kout, vout);
-        uint32_t* t = kin; kin = kout; kout = t;
-        t = vin; vin = vout; vout = t;
-    }
-    // kin now holds the sorted keys, vin == occ_sorted
-    heads_count_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles);
-    scan_single_cta_kernel<<<1, 1024, 0, st>>>(tiles, L.nblocks_scan, n, n_dev);
-    heads_emit_kernel<<<L.nblocks_scan, kScanThreads, 0, st>>>(kin, n, n_dev, seg_shift, tiles, uniq_ids, seg_start, n_unique, pos_seg);
+    dedup_persistent_kernel<<<L.persist_ctas, kSortThreads, 0, st>>>(
+        ids, n, n_dev, passes, seg_shift, reinterpret_cast<uint32_t*>(ws + L.keys_a), reinterpret_cast<uint32_t*>(ws + L.keys_b),
+        reinterpret_cast<uint32_t*>(ws + L.vals_a), reinterpret_cast<uint32_t*>(occ_sorted), reinterpret_cast<uint32_t*>(ws + L.phist),
+        reinterpret_cast<uint32_t*>(ws + L.pcnt), sync, uniq_ids, seg_start, n_unique, pos_seg);
     return check_launch("map_dedup_ids");
 }
 
-/* 1 = the single-launch pipeline is selected (MAP_B200_DEDUP != "multi"): launch accounting of the host side */
-extern "C" int map_dedup_single_launch(void) { return mapb::dedup_use_persistent() ? 1 : 0; }
+/* byte offset, inside the workspace of map_dedup_ids for n_ids keys, of the uint64 phase timestamps the kernel's CTA 0 leaves
+ * (globaltimer ns: start, histogram, barrier, per pass {column sums, tiles, barrier}, head count, barrier, emit) */
+extern "C" size_t map_dedup_debug_offset(int64_t n_ids) { return mapb::dedup_layout(n_ids).psync + 64; }
 
 extern "C" int map_dedup_ids(const int64_t* ids, int64_t n, int key_bits, int64_t* uniq_ids, int32_t* seg_start,
                              int32_t* occ_sorted, int32_t* n_unique, void* workspace, size_t workspace_bytes,

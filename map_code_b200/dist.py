@@ -342,6 +342,7 @@ class ShardedFusedStep(FusedStep):
         self.bar_flags = self.pm.alloc((self.N_BARRIER_SITES * 8,), torch.int32)
         self.bar_epochs = torch.zeros(self.N_BARRIER_SITES, dtype=torch.int32, device=self.dev)
         self.bar_error = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._xr_event = None
         self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
         self.bar_group = dist.new_group(ranks=ranks, backend="nccl")
@@ -431,15 +432,34 @@ class ShardedFusedStep(FusedStep):
         self.tables[te.name], self.tables[tb.name] = te, tb
 
     # -- exchange primitives
+    def _cross_rank(self):
+        """Context for every operation that WAITS FOR OTHER RANKS inside a kernel (peer-flag barriers, NCCL collectives): each one
+        starts after the previous one of the step has finished, on every rank in the same program order.  Without this chain two
+        such kernels can be in flight at once on different streams; a captured graph may map their branches to one hardware
+        queue in a different order on different ranks (A: barrier ahead of all-reduce, B: all-reduce ahead of barrier) and the
+        ranks then wait for each other for ever (seen at N=2 with the gradient buckets next to the NCE barrier)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if self._xr_event is not None:
+                torch.cuda.current_stream().wait_event(self._xr_event)
+            yield
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._xr_event = ev
+        return cm()
+
     def _barrier(self, site: int):
         """stream-ordered barrier over the ranks: everything every rank issued before it on the calling stream is complete and
         visible to peer loads after it"""
         from . import ops
-        if self.barrier_kind == "nccl":
-            dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.bar_group)
-            _lib.mark("nccl_barrier")
-        else:
-            ops.p2p_barrier(self.bar_flags.ptrs, self.world, self.rank, site, self.N_BARRIER_SITES, self.bar_epochs, self.bar_error)
+        with self._cross_rank():
+            if self.barrier_kind == "nccl":
+                dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.bar_group)
+                _lib.mark("nccl_barrier")
+            else:
+                ops.p2p_barrier(self.bar_flags.ptrs, self.world, self.rank, site, self.N_BARRIER_SITES, self.bar_epochs, self.bar_error)
 
     def _merge_keys(self, table):
         """KEY side of the owner-side merge (needs only ids): pull the owned entries of all ranks' unique-id lists and sort them
@@ -510,16 +530,61 @@ class ShardedFusedStep(FusedStep):
             self._merge_values([te, tb])
 
     def _join_streams(self):
-        for name in self.streams:   # the NCE merge chain keeps running; the optimizer joins it
-            if name != "nce":
+        for name in self.streams:   # the NCE merge chain and the gradient buckets keep running; the optimizer joins them
+            if name not in ("nce", "comm"):
                 self._join(name)
 
-    def reduce_gradients(self):
-        # dense gradients: one all-reduce on the 'comm' stream, overlapping the embedding merge below
+    # -- dense gradients: bucketed all-reduce under the backward pass.  grad_flat is laid out so that the weight gradients the
+    # backward has finished form a SUFFIX of the buffer (engine._alloc); after every grouped launch that completes weight
+    # gradients, the newly finished part of the suffix goes out on the 'comm' stream once it is worth a collective.  What is left
+    # for the end of the step are the biases and the first tower layers (~4 MB of the 23 MB at C2).
+    BUCKET_MIN_FLOATS = 1 << 19   # 2 MB
+
+    def forward_backward(self):
+        self._ar_hi = self.grad_flat.numel()      # [_ar_hi, end) has been handed to NCCL
+        self._ar_done = set()
+        self._xr_event = None                     # the chain of cross-rank operations restarts with every step
+        super().forward_backward()
+
+    def _all_reduce_range(self, lo: int, hi: int):
         self._fork("comm")
-        with self._on("comm"):
-            dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
-            _lib.mark("nccl_all_reduce", ("bytes", self.grad_flat.numel() * 4))
+        with self._on("comm"), self._cross_rank():
+            dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            _lib.mark("nccl_all_reduce", ("bytes", (hi - lo) * 4))
+
+    def _gemm_group(self, problems):
+        super()._gemm_group(problems)
+        if not self.multi_stream or not hasattr(self, "_ar_hi"):
+            return
+        base, new = self.grad_flat.data_ptr(), False
+        for pr in problems:
+            if pr is None:
+                continue
+            off = (pr["C_out"].data_ptr() - base) // 4
+            if 0 <= off < self.grad_flat.numel():
+                for name, (lo, hi) in self.grad_offsets.items():
+                    if lo <= off < hi:
+                        self._ar_done.add(name)
+                        new = True
+        if not new:
+            return
+        # longest suffix of the layout (below what was already sent) whose gradients are all complete
+        lo_ok = self._ar_hi
+        for name, (lo, hi) in sorted(self.grad_offsets.items(), key=lambda kv: -kv[1][0]):
+            if lo >= self._ar_hi:
+                continue
+            if name not in self._ar_done or self.dense[name].dim() == 1:
+                break
+            lo_ok = lo
+        if self._ar_hi - lo_ok >= self.BUCKET_MIN_FLOATS:
+            self._all_reduce_range(lo_ok, self._ar_hi)
+            self._ar_hi = lo_ok
+
+    def reduce_gradients(self):
+        # the rest of the dense gradients (biases, first layers) on the 'comm' stream, overlapping the embedding merge below;
+        # every side stream that produced gradients was joined into the current stream by forward_backward()
+        self._all_reduce_range(0, self._ar_hi)
+        self._ar_hi = 0
         self._barrier(self.BAR_EMBED)   # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
         self._merge_values([self.tables[n] for n in ("embed.embedding.weight", "lr_layer.embed_w.weight") if n in self.tables])
 

@@ -189,7 +189,10 @@ class FusedStep:
         # one flat gradient buffer (a single all-reduce in data-parallel runs); per-parameter views keep 16-byte alignment
         # 1-D parameters (biases) come first: their gradients are accumulated by fused column sums in GEMM epilogues
         # (fp32 reductions), so that prefix is zeroed with one small memset at the start of every step.
-        self.dense = dict(sorted(self.dense.items(), key=lambda kv: 0 if kv[1].dim() == 1 else 1))
+        # The 2-D weights follow in the REVERSE of the order in which the backward pass completes their gradients (layer 0 of
+        # the towers first, the head last): at any point of the backward the finished gradients are a suffix of the buffer, which
+        # the data-parallel step all-reduces in a few buckets under the remaining GEMMs (dist.ShardedFusedStep).
+        self.dense = dict(sorted(self.dense.items(), key=lambda kv: (0, 0) if kv[1].dim() == 1 else (1, self._layer_depth(kv[0]))))
         offs, tot, padded, n_bias_floats = {}, 0, {}, 0
         for n, p in self.dense.items():
             offs[n] = tot
@@ -203,6 +206,7 @@ class FusedStep:
             if p.dim() == 1:
                 n_bias_floats = tot
         self.grad_flat = torch.zeros(tot, **f32)
+        self.grad_offsets = {n: (offs[n], offs[n] + (padded[n] + 3) // 4 * 4) for n in self.dense}   # float ranges in grad_flat
         self.bias_grad_flat = self.grad_flat[:n_bias_floats]
         self.grads, self.grads_padded, self.opt_param = {}, {}, {}
         for n, p in self.dense.items():
@@ -296,6 +300,15 @@ class FusedStep:
         self.tables[te.name], self.tables[tb.name] = te, tb
 
     # ------------------------------------------------------------------------------------------------ helpers
+    @staticmethod
+    def _layer_depth(name: str) -> int:
+        """position of a weight's gradient in the backward pass, counted from the END (tower layer i -> i; heads -> 99)"""
+        parts = name.split(".")
+        for prefix, div in (("cross_net.cross_layers.", 1), ("parallel_dnn.dnn.", 3), ("dnn.dnn.", 3)):
+            if name.startswith(prefix):
+                return int(parts[prefix.count(".")]) // div
+        return 99
+
     def _gemm(self, *a, **k):
         return ops.gemm(*a, backend=self.gemm_backend, **k)
 
@@ -381,16 +394,7 @@ class FusedStep:
             if self._early:      # every Philox consumer of this step has been issued: the step counter may advance
                 self._hyper_step()
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
-            self._nce_keys()
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
-
-    def _nce_keys(self):
-        """ids of the NCE tables' gradient = [labels | noise] (what nce_fwd consumes): known as soon as the noise is drawn, so
-        their sort (K2a) runs under the forward GEMMs instead of after the NCE kernel"""
-        if self.mode != "MFP":
-            return
-        ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
-        self.tables["mfp_criterion.emb.weight"].plan.run(self.ids_all.view(-1))
 
     def _draw_noise(self):
         if self.mode != "MFP":
@@ -509,13 +513,16 @@ class FusedStep:
         self.acc_count.zero_()
         n_global = self.global_batch * L
         ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
-                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, want_ids=False,
+                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
                     loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
-        # table gradients on the 'tab' stream: reduce dz * input rows per unique id (the ids were sorted at the start of the step)
+        # table gradients on the 'tab' stream: sort the (N, K+1) ids, reduce dz * input rows per unique id.  (On one GPU the sort
+        # stays HERE, under the backward GEMMs: the SMs are saturated either way, and sorting under the forward pass instead
+        # delayed the NCE kernel — r01f timeline.  The sharded step sorts early because its owners' pulls hang on the keys.)
         te, tb = self.tables["mfp_criterion.emb.weight"], self.tables["mfp_criterion.bias.weight"]
         self._fork("tab")
         with self._on("tab"):
             ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
+            te.plan.run(self.ids_all.view(-1))
             te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
             if self._early and self.optimizer_mode == "sparse":
                 # nothing reads the two NCE tables again in this step: their row-wise AdamW runs here, under the backward GEMMs
