@@ -208,7 +208,25 @@ def algorithmic(tag):
     if kind == "sparse_adamw":
         _, n, d = tag
         return n * (8 + 7 * 4 * d), 0.0
+    if kind == "dedup":   # ids read once + (key, value) read and written per 8-bit radix pass
+        _, n, bits = tag
+        return n * (8 + 4 * 4 * ((bits + 7) // 8)), 0.0
     return 0.0, 0.0
+
+
+def measured_traffic(kernel_class: str, workload: str, task: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json, written by scripts/ncu_summary.py); None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        for e in json.load(open(path)):
+            if e["kernel_class"] == kernel_class and e["workload"] == workload and e["task"] == task:
+                return e["avg_dram_bytes_per_launch"]
+    except (ValueError, KeyError):
+        pass
+    return None
 
 
 def replay_kernel_class(records, reps=20):
@@ -502,7 +520,8 @@ def main_ours(args):
                 sec, n_l = sum(agg[k]["ms"] for k in agg if "gemm_tf32" in k) * 1e-3 / args.profile_steps, len(gemm_recs)
             ach = fl / sec / 1e12
             roof = {"kernel": "map_gemm_tf32_group + map_gemm_tf32_tcgen05 (tcgen05 TF32 GEMM)", "bound": "tensor", "achieved": ach,
-                    "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"], "traffic": None,
+                    "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
+                    "traffic": measured_traffic("gemm_tf32", WORKLOAD, args.task) if world == 1 else None,
                     "launches_per_step": n_l, "us_per_launch": 1e6 * sec / max(n_l, 1), "flops_per_step": fl,
                     "note": f"TF32 operands (nominal rate = half of bf16); peak = {pk['src']} sustained bf16 cuBLAS; achieved = algorithmic "
                             "flops of all tcgen05 GEMM launches of one step / their device time, launches replayed back to back in a CUDA graph on one stream"}

@@ -581,17 +581,18 @@ class ShardedFusedStep(FusedStep):
             self._ar_hi = lo_ok
 
     def reduce_gradients(self):
-        # the rest of the dense gradients (biases, first layers) on the 'comm' stream, overlapping the embedding merge below;
         # every side stream that produced gradients was joined into the current stream by forward_backward()
+        self._hyper_step()              # every Philox consumer of the step has been issued: the step counter may advance
+        self._barrier(self.BAR_EMBED)   # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
+        # the rest of the dense gradients (biases, first layers) on the 'comm' stream, beside the embedding merge below
         self._all_reduce_range(0, self._ar_hi)
         self._ar_hi = 0
-        self._barrier(self.BAR_EMBED)   # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
         self._merge_values([self.tables[n] for n in ("embed.embedding.weight", "lr_layer.embed_w.weight") if n in self.tables])
 
     def optimizer_step(self):
         from . import ops
-        b1, b2 = self.betas
-        ops.adamw_hyper_step(self.hyper, self.step_counter, self.lr, b1, b2, self.eps, self.sched, self.warmup_steps, self.total_steps)
+        with self._on("comm"):          # dense AdamW behind the last gradient bucket, beside the table updates
+            ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
         self._join("nce")
         for t in self.tables.values():
             if self.optimizer_mode == "sparse":
@@ -602,7 +603,6 @@ class ShardedFusedStep(FusedStep):
         # up to date (the next step's gathers may read it)
         self._barrier(self.BAR_END)
         self._join("comm")
-        ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
 
     def dense_table_grad(self, name: str) -> torch.Tensor:
         """[shard_rows, D] dense view of the merged gradient of this rank's shard"""

@@ -94,6 +94,8 @@ class DedupPlan:
     def run(self, ids: torch.Tensor):
         _check(ids, torch.int64, "ids")
         assert ids.numel() == self.n
+        if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
+            _lib.CURRENT_TAG = ("dedup", self.n, self.key_bits)
         call("map_dedup_ids_ex", ids.data_ptr(), self.n, _ptr(self.n_dev), self.key_bits, self.seg_shift, self.uniq.data_ptr(),
              self.seg_start.data_ptr(), self.occ_sorted.data_ptr(), self.n_unique.data_ptr(), self.pos_seg.data_ptr(), self.ws.data_ptr(),
              self.ws_bytes, _stream())
