@@ -154,7 +154,7 @@ struct RowVec<1> {
 // occurrences) are first merged ACROSS THE GROUPS OF THE CTA through shared memory — every group deposits at most a
 // "head" and a "tail" partial — and only the per-CTA result goes to global memory: a plain store when the segment lies
 // inside the CTA's range, otherwise one atomic per CTA (instead of one per 8 occurrences).
-template <int VEC>
+template <int VEC, bool HAS_MAP>
 __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __restrict__ rows, int64_t ld_rows, int lanes,
                                                              const float* __restrict__ scale, int group,
                                                              const int32_t* __restrict__ occ_sorted,
@@ -185,20 +185,39 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
         slot_seg[2 * g + 1] = -1;
     }
     if (active) {
-        // segment containing t0: read from the position -> segment map when the dedup produced one, else the largest s
-        // with seg_start[s] <= t0 (a 20-step chain of dependent loads per group at 1e6 unique rows)
-        int s;
-        if (pos_seg != nullptr) {
-            s = __ldg(pos_seg + t0);
+        // segment index of every position of the tile, of the position before it and of the position after it (-1 = outside
+        // the list).  With the position -> segment map of the dedup these are 10 independent loads issued together with the
+        // occurrence loads; without it (plain map_segment_reduce_rows) they come from a binary search over seg_start and a
+        // walk of dependent loads (a 20-step chain per group at 1e6 unique rows, and one more round trip per segment).
+        int sg[kSegTile + 1];
+        int sg_prev = -1;
+        if (HAS_MAP) {
+#pragma unroll
+            for (int k = 0; k <= kSegTile; ++k) sg[k] = (t0 + k < n) ? __ldg(pos_seg + t0 + k) : -1;
+            if (t0 > 0) sg_prev = __ldg(pos_seg + t0 - 1);
         } else {
             int lo = 0, hi = U - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
                 if ((int64_t)seg_start[mid] <= t0) lo = mid; else hi = mid - 1;
             }
-            s = lo;
+            int cur = lo;
+            int64_t cur_end = seg_start[cur + 1];
+            if ((int64_t)seg_start[cur] < t0) sg_prev = cur;
+            else if (t0 > 0) sg_prev = cur - 1;
+#pragma unroll
+            for (int k = 0; k <= kSegTile; ++k) {
+                if (t0 + k < n) {
+                    if (t0 + k >= cur_end) {
+                        ++cur;
+                        cur_end = seg_start[cur + 1];
+                    }
+                    sg[k] = cur;
+                } else {
+                    sg[k] = -1;
+                }
+            }
         }
-        int64_t s_end = seg_start[s + 1];
         RowVec<VEC> r[kSegTile];
         float sc[kSegTile];
 #pragma unroll
@@ -220,21 +239,21 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
         RowVec<VEC> acc;
         acc.zero();
         float sacc = 0.f;
-        int64_t seg_first_pos = (int64_t)seg_start[s];
+        bool started_here = sg_prev != sg[0];   // does the segment being accumulated begin inside this tile?
 #pragma unroll
         for (int k = 0; k < kSegTile; ++k) {
             const int64_t pos = t0 + k;
             if (pos < t1) {
+                const int s = sg[k];
                 acc.fma(r[k], sc[k]);
                 sacc += sc[k];
-                if (pos + 1 == s_end || pos + 1 == t1) {  // flush
-                    const bool starts_here = seg_first_pos >= t0;
-                    const bool ends_here = s_end <= t1;
-                    if (starts_here && ends_here) {       // interior segment of this tile
+                const bool ends_here = sg[k + 1] != s;   // (also true at the end of the list: sg = -1 there)
+                if (ends_here || pos + 1 == t1) {        // flush
+                    if (started_here && ends_here) {      // interior segment of this tile
                         acc.store(grad + (int64_t)s * D + lane * VEC);
                         if (scalar_out != nullptr && lane == 0) scalar_out[s] = sacc;
                     } else {                              // straddles: head slot if it began before the tile, else tail slot
-                        const int slot = starts_here ? 2 * g + 1 : 2 * g;
+                        const int slot = started_here ? 2 * g + 1 : 2 * g;
                         acc.store(slot_vec + slot * rowlen + lane * VEC);
                         if (lane == 0) {
                             slot_seg[slot] = s;
@@ -243,11 +262,7 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
                     }
                     acc.zero();
                     sacc = 0.f;
-                    if (pos + 1 == s_end && pos + 1 < t1) {
-                        ++s;
-                        seg_first_pos = s_end;
-                        s_end = seg_start[s + 1];
-                    }
+                    started_here = true;                  // whatever follows begins inside the tile
                 }
             }
         }
@@ -274,7 +289,14 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
             acc.fma(o, 1.f);
             sacc += slot_sc[k];
         }
-        const bool whole = ((int64_t)seg_start[s] >= blk_t0) && ((int64_t)seg_start[s + 1] <= blk_t1);
+        bool whole;   // does the segment lie entirely inside this CTA's range of positions?
+        if (HAS_MAP) {
+            const bool cut_front = blk_t0 > 0 && __ldg(pos_seg + blk_t0) == s && __ldg(pos_seg + blk_t0 - 1) == s;
+            const bool cut_back = blk_t1 < n && __ldg(pos_seg + blk_t1 - 1) == s && __ldg(pos_seg + blk_t1) == s;
+            whole = !cut_front && !cut_back;
+        } else {
+            whole = ((int64_t)seg_start[s] >= blk_t0) && ((int64_t)seg_start[s + 1] <= blk_t1);
+        }
         float* dst = grad + (int64_t)s * D + lane * VEC;
         if (whole) acc.store(dst); else acc.atomic_add(dst);
         if (scalar_out != nullptr && lane == 0) {
@@ -649,12 +671,14 @@ extern "C" int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, in
     MAP_REQUIRE(lanes <= 256, "map_segment_reduce_rows: D=%d too wide for one CTA", D);
     const int64_t tiles = ceil_div(n_ids, kSegTile);
     const unsigned blocks = (unsigned)ceil_div(tiles, 256 / lanes);
-    if (vec)
-        segment_reduce_kernel<4><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids,
-                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer, pos_seg);
-    else
-        segment_reduce_kernel<1><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids,
-                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer, pos_seg);
+#define LAUNCH_SEGRED(V, M)                                                                                                     \
+    segment_reduce_kernel<V, M><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids, \
+                                                        grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer, pos_seg)
+    if (vec && pos_seg != nullptr) LAUNCH_SEGRED(4, true);
+    else if (vec) LAUNCH_SEGRED(4, false);
+    else if (pos_seg != nullptr) LAUNCH_SEGRED(1, true);
+    else LAUNCH_SEGRED(1, false);
+#undef LAUNCH_SEGRED
     return check_launch("map_segment_reduce_rows");
 }
 

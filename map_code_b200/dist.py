@@ -346,6 +346,12 @@ class ShardedFusedStep(FusedStep):
         self._bar = torch.zeros(1, dtype=torch.float32, device=self.dev)
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
         self.bar_group = dist.new_group(ranks=ranks, backend="nccl")
+        # the gradient buckets run under the backward GEMMs: on a normal-priority stream NCCL's CTAs queue behind every GEMM wave
+        # (r01f 8-GPU timeline: ~100 us per 5.5 MB bucket), so the buckets get a communicator with a high-priority stream
+        self.grad_group = group
+        if os.environ.get("MAP_B200_NCCL_PRIO", "1") == "1":
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            self.grad_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
         if self.multi_stream:
             for k in ("keys", "nce", "comm"):
                 self.streams[k] = torch.cuda.Stream(device=self.dev, priority=-1)
@@ -549,7 +555,7 @@ class ShardedFusedStep(FusedStep):
     def _all_reduce_range(self, lo: int, hi: int):
         self._fork("comm")
         with self._on("comm"), self._cross_rank():
-            dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.grad_group)
             _lib.mark("nccl_all_reduce", ("bytes", (hi - lo) * 4))
 
     def _gemm_group(self, problems):

@@ -99,6 +99,25 @@ def test_segment_reduce_matches_index_add(ops, D):
     torch.testing.assert_close(dense.cpu().double(), ref, rtol=1e-5, atol=1e-4)
 
 
+def test_segment_reduce_plain_abi_without_position_map(ops):
+    """map_segment_reduce_rows (no pos_seg): segment boundaries come from the binary search / seg_start walk"""
+    from map_code_b200 import _lib
+    g = torch.Generator().manual_seed(7)
+    n, V, D = 30_000, 5000, 16
+    ids = torch.randint(0, V, (n,), generator=g)
+    ids[1000:9000] = 3
+    rows = dev(torch.randn(n, D, generator=g))
+    plan = ops.DedupPlan(n, V, "cuda").run(dev(ids))
+    G = torch.zeros(n, D, device="cuda")
+    _lib.call("map_segment_reduce_rows", rows.data_ptr(), D, D, None, 1, plan.occ_sorted.data_ptr(), plan.seg_start.data_ptr(),
+              plan.n_unique.data_ptr(), n, G.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
+    G2 = plan.reduce_rows(rows, D)
+    U = plan.n_unique.item()
+    ref = torch.zeros(V, D, dtype=torch.float64).index_add_(0, ids, rows.cpu().double())
+    torch.testing.assert_close(G[:U].cpu().double(), ref[plan.uniq[:U].cpu()], rtol=1e-5, atol=1e-4)
+    assert torch.equal(G[:U], G2[:U])   # same summation order with and without the map
+
+
 def test_segment_reduce_scaled_grouped(ops):
     """NCE form: occurrence o = n*(K+1)+j contributes dz[o] * input[n, :] to row ids[o] and dz[o] to its bias."""
     g = torch.Generator().manual_seed(1)
