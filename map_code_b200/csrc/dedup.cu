@@ -315,6 +315,25 @@ __global__ void __launch_bounds__(256) zero_unique_rows_kernel(float* grad, floa
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += stride) scalar_out[i] = 0.f;
 }
 
+// With the position -> segment map only the rows of segments that a CTA border of segment_reduce_kernel cuts can receive
+// atomics: one warp per border zeroes that one row (zeroing all U rows first cost U * D * 4 bytes of HBM writes, half as much
+// again as the reduce itself reads at C5).
+__global__ void __launch_bounds__(256) zero_cut_rows_kernel(float* grad, float* scalar_out, int D, const int32_t* __restrict__ pos_seg,
+                                                            int64_t n, const int32_t* __restrict__ n_dev, int64_t per_cta,
+                                                            int64_t n_borders) {
+    n = eff_n(n, n_dev);
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + 1; b <= n_borders; b += warps) {
+        const int64_t p = b * per_cta;   // first position of CTA b
+        if (p >= n) break;
+        const int s = __ldg(pos_seg + p);
+        if (__ldg(pos_seg + p - 1) != s) continue;
+        for (int d = lane; d < D; d += 32) grad[(int64_t)s * D + d] = 0.f;
+        if (scalar_out != nullptr && lane == 0) scalar_out[s] = 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ grad, const int64_t* __restrict__ uniq,
                                                            const int32_t* __restrict__ n_unique, int D,
                                                            float* __restrict__ dense) {
@@ -662,15 +681,21 @@ extern "C" int map_segment_reduce_rows_ex(const float* rows, int64_t ld_rows, in
     // peer buffers come from map_p2p_alloc (256-byte aligned), so only the local pointers need the alignment check
     const bool vec = (D % 4 == 0) && (ld_rows % 4 == 0) && ((uintptr_t)rows % 16 == 0) && ((uintptr_t)grad_compact % 16 == 0);
     const int lanes = vec ? D / 4 : D;
-    const int64_t max_elems = n_ids * D;
-    {
-        int64_t blocks = ceil_div(max_elems, 256);
-        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-        zero_unique_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad_compact, scalar_out, D, n_unique, max_elems);
-    }
     MAP_REQUIRE(lanes <= 256, "map_segment_reduce_rows: D=%d too wide for one CTA", D);
-    const int64_t tiles = ceil_div(n_ids, kSegTile);
-    const unsigned blocks = (unsigned)ceil_div(tiles, 256 / lanes);
+    const int64_t per_cta = (int64_t)(256 / lanes) * kSegTile;   // sorted positions per CTA of segment_reduce_kernel
+    const unsigned blocks = (unsigned)ceil_div(n_ids, per_cta);
+    if (pos_seg != nullptr) {
+        if (blocks > 1) {
+            int64_t zb = ceil_div((int64_t)(blocks - 1) * 32, 256);
+            if (zb > kNumSMs * 8) zb = kNumSMs * 8;
+            zero_cut_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(grad_compact, scalar_out, D, pos_seg, n_ids, n_dev, per_cta, (int64_t)blocks - 1);
+        }
+    } else {
+        const int64_t max_elems = n_ids * D;
+        int64_t zb = ceil_div(max_elems, 256);
+        if (zb > kNumSMs * 8) zb = kNumSMs * 8;
+        zero_unique_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(grad_compact, scalar_out, D, n_unique, max_elems);
+    }
 #define LAUNCH_SEGRED(V, M)                                                                                                     \
     segment_reduce_kernel<V, M><<<blocks, 256, 0, st>>>(rows, ld_rows, lanes, scale, group, occ_sorted, seg_start, n_unique, n_ids, \
                                                         grad_compact, scalar_out, D, n_dev, occ_map, row_tab, rows_per_peer, pos_seg)

@@ -115,7 +115,7 @@ def test_segment_reduce_plain_abi_without_position_map(ops):
     U = plan.n_unique.item()
     ref = torch.zeros(V, D, dtype=torch.float64).index_add_(0, ids, rows.cpu().double())
     torch.testing.assert_close(G[:U].cpu().double(), ref[plan.uniq[:U].cpu()], rtol=1e-5, atol=1e-4)
-    assert torch.equal(G[:U], G2[:U])   # same summation order with and without the map
+    torch.testing.assert_close(G[:U], G2[:U], rtol=1e-5, atol=1e-4)   # (the hot row is merged with atomics: not bit-stable)
 
 
 def test_segment_reduce_scaled_grouped(ops):
