@@ -223,6 +223,20 @@ class CollectiveShardedFusedStep(FusedStep):
 
 
 # ------------------------------------------------------------------------------------------------ owner-side merge (layout)
+def finished_suffix(grad_offsets: Dict[str, tuple], biases: set, done: set, hi: int) -> int:
+    """Start of the longest suffix of the flat gradient buffer below `hi` whose weight gradients are all complete.
+    grad_offsets: name -> (lo, hi) float range in grad_flat, laid out [biases | weights in reverse backward order]
+    (engine.FusedStep._alloc); biases never join a bucket (their column sums finish on side streams: they go out last)."""
+    lo_ok = hi
+    for name, (lo, _) in sorted(grad_offsets.items(), key=lambda kv: -kv[1][0]):
+        if lo >= hi:
+            continue
+        if name not in done or name in biases:
+            break
+        lo_ok = lo
+    return lo_ok
+
+
 def merge_key_layout(world: int, n_shard_rows: int):
     """(shift, key_bits) of the merge keys  ((id // R) << shift) | source_rank  built by map_owned_compact: the source rank
     sits in the low `shift` bits so that a stable sort orders the contributions of one row by source rank."""
@@ -314,8 +328,8 @@ class ShardedFusedStep(FusedStep):
     backward  every rank reduces its own occurrences to a compact (unique id, gradient row) list exactly like the single-GPU
               step; after a barrier the OWNER of each row pulls the entries it owns from all R lists, sums them in source-rank
               order (deterministic) and applies row-wise AdamW to its shard;
-    dense     parameters are replicated; ONE all-reduce of the flat gradient buffer, issued after the table updates so that
-              its completion also tells every rank that all shards are up to date for the next step's gathers.
+    dense     parameters are replicated; the flat gradient buffer is all-reduced in buckets under the backward pass (finished
+              weight gradients form a suffix of the buffer), the rest beside the embedding merge.
     `batch_size` is the per-rank batch; the global batch is batch_size * world.  Philox counters are indexed by the global
     row, so the R-rank run reproduces the single-GPU run on the concatenated batch."""
 
@@ -574,14 +588,7 @@ class ShardedFusedStep(FusedStep):
                         new = True
         if not new:
             return
-        # longest suffix of the layout (below what was already sent) whose gradients are all complete
-        lo_ok = self._ar_hi
-        for name, (lo, hi) in sorted(self.grad_offsets.items(), key=lambda kv: -kv[1][0]):
-            if lo >= self._ar_hi:
-                continue
-            if name not in self._ar_done or self.dense[name].dim() == 1:
-                break
-            lo_ok = lo
+        lo_ok = finished_suffix(self.grad_offsets, {n for n, p in self.dense.items() if p.dim() == 1}, self._ar_done, self._ar_hi)
         if self._ar_hi - lo_ok >= self.BUCKET_MIN_FLOATS:
             self._all_reduce_range(lo_ok, self._ar_hi)
             self._ar_hi = lo_ok

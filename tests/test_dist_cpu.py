@@ -223,3 +223,35 @@ def test_peer_memory_merge_world2():
 
 def test_peer_memory_merge_world3_uneven():
     run2(_peer_merge_case, world=3)
+
+
+def test_gradient_bucket_suffix_logic():
+    """dist.finished_suffix: which part of the flat gradient buffer may go to NCCL after each level of the backward pass
+    (layout of engine.FusedStep._alloc for DCNv2-MFP: biases first, then weights in reverse backward order)."""
+    from map_code_b200.dist import finished_suffix
+    from map_code_b200.engine import FusedStep
+    names = ["cross_net.cross_layers.0.bias", "parallel_dnn.dnn.0.bias", "feat_encoder.bias",
+             "cross_net.cross_layers.0.weight", "parallel_dnn.dnn.0.weight", "cross_net.cross_layers.1.weight", "parallel_dnn.dnn.3.weight",
+             "cross_net.cross_layers.2.weight", "parallel_dnn.dnn.6.weight", "feat_encoder.weight"]
+    # the sort key of the engine puts them in exactly this order
+    depth = [FusedStep._layer_depth(n) for n in names[3:]]
+    assert depth == sorted(depth) and depth[-1] == 99
+    offs, o = {}, 0
+    for i, n in enumerate(names):
+        offs[n] = (o, o + 100 * (i + 1))
+        o += 100 * (i + 1)
+    biases = set(names[:3])
+    hi = o
+    done = set()
+    assert finished_suffix(offs, biases, done, hi) == hi                          # nothing finished yet
+    done.add("feat_encoder.weight")
+    hi1 = finished_suffix(offs, biases, done, hi)
+    assert hi1 == offs["feat_encoder.weight"][0]
+    done.add("parallel_dnn.dnn.6.weight")                                          # cross layer 2 still missing: no progress past dnn.6
+    assert finished_suffix(offs, biases, done, hi1) == offs["parallel_dnn.dnn.6.weight"][0]
+    done.add("cross_net.cross_layers.1.weight")                                    # out of order: a hole below dnn.6 -> no further progress
+    assert finished_suffix(offs, biases, done, hi1) == offs["parallel_dnn.dnn.6.weight"][0]
+    done.update(names[3:])
+    assert finished_suffix(offs, biases, done, hi1) == offs["cross_net.cross_layers.0.weight"][0]   # stops at the biases
+    done.update(names)
+    assert finished_suffix(offs, biases, done, hi1) == offs["cross_net.cross_layers.0.weight"][0]
