@@ -417,6 +417,7 @@ def main_ours(args):
         dist.barrier()
         ms = float(t.item())
     loss_after = float(eng.outputs()[0])
+    eng.check_health()   # a device-side wait that gave up (sort grid barrier, peer barrier) voids the run: fail loudly
     value = Bg * args.steps / (ms / 1e3)
 
     _stage('timed region done')

@@ -701,6 +701,21 @@ class FusedStep:
         self.steps_done += 1
         return self.loss if self.mode == "MFP" else self.stats[0:1]
 
+    def check_health(self):
+        """Raises if any kernel of the steps so far gave up on a device-side wait (grid barrier of a sort, peer-flag barrier of
+        the sharded step) instead of completing.  Synchronises; call it outside the hot loop (the Trainer does at logging steps)."""
+        plans = {id(t.plan): (t.name, t.plan) for t in self.tables.values() if t.plan is not None}
+        for t in self.tables.values():
+            m = getattr(t, "merge", None)
+            if m is not None:
+                plans[id(m.plan)] = (t.name + " (owner-side merge)", m.plan)
+        for name, plan in plans.values():
+            if plan.error_word():
+                raise _lib.MapB200Error(f"sort of the ids of {name}: a grid barrier was not met (CTAs not co-resident?)")
+        bar = getattr(self, "bar_error", None)
+        if bar is not None and int(bar.item()):
+            raise _lib.MapB200Error("sharded step: a rank did not arrive at a peer-memory barrier")
+
     def outputs(self):
         """Reference-style output tuple of the last step (device tensors; reading them synchronises)."""
         if self.mode == "MFP":

@@ -101,6 +101,12 @@ class DedupPlan:
              self.ws_bytes, _stream())
         return self
 
+    def error_word(self) -> int:
+        """1 if a grid barrier of the last sort was not met within its spin bound (the kernel then gave up instead of hanging
+        the GPU and its outputs are garbage).  Synchronises: call it outside the step (FusedStep.check_health)."""
+        off = int(_lib.load().map_dedup_debug_offset(self.n)) - 64 + 4
+        return int(self.ws[off:off + 4].view(torch.int32).item())
+
     def reduce_peer_rows(self, row_ptrs, n_peers: int, rows_per_peer: int, D: int, occ_map: torch.Tensor, out: torch.Tensor):
         """segment sums over rows that live in the R ranks' compact gradients (row_ptrs: ctypes array of R device pointers,
         peer memory): row code = occ_map[occurrence] = peer * rows_per_peer + row."""

@@ -303,6 +303,8 @@ class Trainer:
                 win_acc += (outputs[2].detach().float().view(1) / outputs[1]) if kind == "MFP" else outputs[2].detach().view(1)
                 win_n += 1
                 if self.global_step % a.logging_steps == 0:
+                    if self._fused is not None:
+                        self._fused.check_health()
                     _log = {f"window_{kind.lower()}_loss": win_loss.item() / win_n, f"window_{kind.lower()}_acc": win_acc.item() / win_n,
                             "time_cost": time.time() - start_time}
                     logger.info(f"step = {self.global_step}, {str(_log)}")
@@ -389,6 +391,8 @@ class Trainer:
                 win_loss += outputs[0].detach().view(1)
                 win_n += 1
                 if self.global_step % a.logging_steps == 0:
+                    if self._fused is not None:
+                        self._fused.check_health()
                     logger.info(f"step = {self.global_step}, {{'window_loss': {win_loss.item() / win_n}}}")
                     win_loss.zero_(); win_n = 0
             self.eval()

@@ -119,3 +119,21 @@ def test_train_step_async_matches_train_step(pt_type, tmp_path):
         assert tr.global_step == 8
     assert np.allclose(losses["sync"], losses["async"], rtol=1e-4), losses
     assert losses["sync"][-1] < losses["sync"][0]
+
+
+def test_check_health_reports_a_failed_device_wait(tmp_path):
+    """FusedStep.check_health: clean after normal steps; raises when a sort's error word is set (what the kernel does when a
+    grid barrier is not met within its spin bound)"""
+    from map_code_b200 import _lib
+    from map_code_b200.trainer import Trainer
+    model, cfg, args, train, valid = make("MFP", True, "DCNv2", tmp_path)
+    model.cuda()
+    tr = Trainer(model, cfg, args, train, valid)
+    eng = tr.fused_step(100, 0)
+    tr.train_step(torch.from_numpy(train.X[:256]).cuda())
+    eng.check_health()
+    plan = eng.tables["embed.embedding.weight"].plan
+    off = int(_lib.load().map_dedup_debug_offset(plan.n)) - 64 + 4
+    plan.ws[off:off + 4].view(torch.int32).fill_(1)
+    with pytest.raises(_lib.MapB200Error):
+        eng.check_health()
