@@ -196,6 +196,15 @@ size_t map_reduce_workspace_bytes(int64_t n);
 int map_bce_logits_fwd(const float* logits, const float* labels, int64_t n, float* stats_out, float* dlogits,
                        void* workspace, size_t workspace_bytes, map_stream_t stream);
 
+/* On-device ROC AUC for Trainer.eval (replaces sklearn.metrics.roc_auc_score on host copies, code/trainer.py:183-197):
+ * keys[i] = order-preserving 32-bit image of scores[i] (as int64, the id type of map_dedup_ids; key_bits = 32); after
+ * map_dedup_ids(keys) and map_segment_reduce_rows(labels as [n,1] rows) -> pos_count[u] positives in tie group u,
+ * map_auc_rank_sum leaves out2 = {sum of the average 1-based ranks of the positives, number of positives P} (fp64), so that
+ * AUC = (out2[0] - P(P+1)/2) / (P (n - P)). */
+int map_float_sort_keys(const float* scores, int64_t n, int64_t* keys, map_stream_t stream);
+int map_auc_rank_sum(const int32_t* seg_start, const float* pos_count, const int32_t* n_unique, int64_t max_unique, double* out2,
+                     map_stream_t stream);
+
 /* ------------------------------------------------------------------ K11  FM second-order + LR term (DeepFM)
  * replaces LR.forward (code/models.py:137-143) + InnerProductLayer product_sum (code/layers.py:125-131):
  * out[b] = sum_f w[ids[b,f]] + lr_bias + 0.5 * sum_d ((sum_f e[b,f,d])^2 - sum_f e[b,f,d]^2)

@@ -78,6 +78,8 @@ PROTOTYPES = {
     "map_reduce_sum_f32": (_i, [_p, _l, _f, _p, _p, _sz, _p]),
     "map_reduce_workspace_bytes": (_sz, [_l]),
     "map_bce_logits_fwd": (_i, [_p, _p, _l, _p, _p, _p, _sz, _p]),
+    "map_float_sort_keys": (_i, [_p, _l, _p, _p]),
+    "map_auc_rank_sum": (_i, [_p, _p, _p, _l, _p, _p]),
     "map_fm_lr_fwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _l, _p]),
     "map_fm_lr_bwd": (_i, [_p, _p, _l, _l, _i, _i, _i, _p, _p, _p]),
     "map_gemm_f32_simt": (_i, [C.POINTER(GemmArgs), _p]),

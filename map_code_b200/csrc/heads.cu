@@ -375,3 +375,81 @@ extern "C" int map_gather_rows_i64(const int64_t* X, int64_t n_rows, int F, cons
     gather_rows_i64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, F, idx, n, out);
     return check_launch("map_gather_rows_i64");
 }
+
+// ------------------------------------------------------------------------------------------------ on-device AUC (Trainer.eval)
+// ROC AUC of n scores = (sum of the average ranks of the positives - P(P+1)/2) / (P * (n - P)), ties sharing their average
+// rank — what sklearn.metrics.roc_auc_score computes (code/trainer.py:196) — as a composition of the K2 kernels: scores ->
+// order-preserving 32-bit keys -> map_dedup_ids (sorted tie groups: unique keys, segment starts) -> map_segment_reduce_rows
+// with the labels as 1-float rows (positives per tie group) -> the rank sum below.
+namespace mapb {
+
+__global__ void __launch_bounds__(256) float_sort_keys_kernel(const float* __restrict__ x, int64_t n, int64_t* __restrict__ keys) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t b = __float_as_uint(x[i] + 0.0f);                 // (-0.0 + 0.0 = +0.0: the two zeros tie)
+        b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);           // ascending float order == ascending unsigned order
+        keys[i] = (int64_t)b;
+    }
+}
+
+// out[0] += sum_u pos[u] * (seg_start[u] + seg_start[u+1] + 1) / 2   (average 1-based rank of tie group u), out[1] += sum_u pos[u]
+__global__ void __launch_bounds__(256) auc_rank_sum_kernel(const int32_t* __restrict__ seg_start, const float* __restrict__ pos,
+                                                           const int32_t* __restrict__ n_unique, double* __restrict__ out) {
+    __shared__ double sh[2][8];
+    const int64_t U = *n_unique;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double r = 0.0, p = 0.0;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U; u += stride) {
+        const double c = (double)pos[u];
+        if (c != 0.0) {
+            r += c * (0.5 * ((double)seg_start[u] + (double)seg_start[u + 1] + 1.0));
+            p += c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+        p += __shfl_xor_sync(0xffffffffu, p, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh[0][warp] = r;
+        sh[1][warp] = p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double rs = 0.0, ps = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            rs += sh[0][w];
+            ps += sh[1][w];
+        }
+        if (rs != 0.0) atomicAdd(out, rs);
+        if (ps != 0.0) atomicAdd(out + 1, ps);
+    }
+}
+
+}  // namespace mapb
+
+extern "C" int map_float_sort_keys(const float* x, int64_t n, int64_t* keys, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(x && keys && n > 0, "map_float_sort_keys: bad argument");
+    int64_t blocks = ceil_div(n, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    float_sort_keys_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, n, keys);
+    return check_launch("map_float_sort_keys");
+}
+
+extern "C" int map_auc_rank_sum(const int32_t* seg_start, const float* pos_count, const int32_t* n_unique, int64_t max_unique,
+                                double* out2, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(seg_start && pos_count && n_unique && out2 && max_unique > 0, "map_auc_rank_sum: bad argument");
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(out2, 0, 2 * sizeof(double), st) != cudaSuccess) {
+        set_error("map_auc_rank_sum: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MAP_ECUDA;
+    }
+    int64_t blocks = ceil_div(max_unique, 256);
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    auc_rank_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(seg_start, pos_count, n_unique, out2);
+    return check_launch("map_auc_rank_sum");
+}

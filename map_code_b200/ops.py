@@ -344,6 +344,26 @@ def bce_logits(logits: torch.Tensor, labels: torch.Tensor, stats=None, dlogits=N
     return stats, dlogits
 
 
+def auc_logloss(logits: torch.Tensor, labels: torch.Tensor):
+    """ROC AUC (ties share their average rank, like sklearn.metrics.roc_auc_score) and mean BCE-with-logits of n scores, on
+    the device: scores -> sortable keys -> sort-dedup (K2a) -> positives per tie group (K2b) -> rank sum.  Returns two 0-d
+    float64 device tensors; nothing synchronises.  (trainer.py:183-197 copies logits to the host and calls sklearn.)"""
+    logits = logits.reshape(-1).contiguous().float()
+    labels = labels.reshape(-1).contiguous().float()
+    n = logits.numel()
+    dev = logits.device
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    call("map_float_sort_keys", logits.data_ptr(), n, keys.data_ptr(), _stream())
+    plan = DedupPlan(n, 1 << 32, dev).run(keys)
+    pos = plan.reduce_rows(labels.view(n, 1), 1)
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    call("map_auc_rank_sum", plan.seg_start.data_ptr(), pos.data_ptr(), plan.n_unique.data_ptr(), n, out.data_ptr(), _stream())
+    P = out[1]
+    auc = (out[0] - P * (P + 1) / 2) / (P * (n - P))
+    stats, _ = bce_logits(logits, labels, want_grad=False)
+    return auc, stats[0].double()
+
+
 def fm_lr_fwd(feat_embed, ids, lr_w, lr_bias, out=None, ld_out: int = 1):
     B, F, D = feat_embed.shape
     if out is None:

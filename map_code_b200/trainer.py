@@ -400,8 +400,10 @@ class Trainer:
                 break
 
     def eval(self, eval_dataset=None, test_eval=False):
-        """trainer.py:163-215: AUC / logloss over the eval split (sklearn on the host, like the reference)."""
-        from sklearn.metrics import log_loss, roc_auc_score
+        """trainer.py:163-215: AUC / logloss over the eval split.  The reference copies every batch's logits to the host and calls
+        sklearn (roc_auc_score, log_loss); here the logits stay on the device and both metrics come from ops.auc_logloss (sort of
+        the scores with the K2 kernels, ties share their average rank like sklearn) — one host read at the end."""
+        from . import ops
         loader = self.get_dataloader(self.eval_dataset if eval_dataset is None else eval_dataset, is_training=False)
         logger.info("***** running %s *****", "TEST" if test_eval else "eval")
         self.model.eval()
@@ -411,13 +413,16 @@ class Trainer:
                 outputs = self.model(input_ids=X, labels=Y)
                 logits_all.append(outputs[1].view(-1))
                 labels_all.append(Y.view(-1))
-        logits = torch.cat(logits_all).double().cpu().numpy()
-        labels = torch.cat(labels_all).cpu().numpy()
-        probs = 1.0 / (1.0 + np.exp(-logits))
-        auc = roc_auc_score(y_true=labels, y_score=probs)
-        ll = log_loss(y_true=labels, y_pred=probs)
+            logits = torch.cat(logits_all).float()
+            labels = torch.cat(labels_all).float()
+            n_pos = int(labels.sum().item())
+            if n_pos == 0 or n_pos == labels.numel():   # sklearn.metrics.roc_auc_score raises the same way
+                raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+            auc_t, ll_t = ops.auc_logloss(logits, labels)
+            probs_mean = torch.sigmoid(logits.double()).mean()
+            auc, ll, avg_logits, avg_probs = (float(v) for v in torch.stack([auc_t, ll_t, logits.double().mean(), probs_mean]).cpu())
         self.eval_metrics.append([auc, ll])
-        logger.info(str({"eval_auc": auc, "eval_loss": ll, "avg_logits": logits.mean(), "avg_probs": probs.mean()}))
+        logger.info(str({"eval_auc": auc, "eval_loss": ll, "avg_logits": avg_logits, "avg_probs": avg_probs}))
         if not test_eval:
             if auc > self.best_eval_auc:
                 self.best_eval_auc, self.best_eval_step, self._patience = auc, self.global_step, 0

@@ -136,6 +136,23 @@ def test_segment_reduce_scaled_grouped(ops):
     torch.testing.assert_close(sc[:U].cpu().double(), refb[u], rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("n,decimals", [(1000, 1), (100_000, 2), (300_000, 6), (5000, 0)])
+def test_auc_logloss_matches_sklearn(ops, n, decimals):
+    """on-device ROC AUC / logloss (Trainer.eval) against sklearn on the host (what the reference calls, trainer.py:196-197);
+    rounded scores give large tie groups, which must share their average rank"""
+    from sklearn.metrics import log_loss, roc_auc_score
+    g = torch.Generator().manual_seed(n)
+    z = torch.randn(n, generator=g) * 2
+    z = torch.round(z * 10 ** decimals) / 10 ** decimals
+    z[::97] = 0.0
+    z[1::97] = -0.0
+    y = (torch.rand(n, generator=g) < torch.sigmoid(z)).float()
+    auc, ll = ops.auc_logloss(dev(z), dev(y))
+    probs = torch.sigmoid(z.double()).numpy()
+    assert abs(float(auc) - roc_auc_score(y.numpy(), z.double().numpy())) < 1e-9
+    assert abs(float(ll) - log_loss(y.numpy(), probs)) < 2e-5 * max(1.0, log_loss(y.numpy(), probs))
+
+
 # ------------------------------------------------------------------------------------------------ AdamW
 def test_adamw_hyper_schedule(ops):
     hyper = torch.zeros(8, device="cuda")
