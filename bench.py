@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2: DCNv2 Criteo shape (BASELINE configs[1]/[2], the headline); c4: DeepFM on the Avazu shape (configs[3]); "
                          "c5: DCNv2, ~1e8-row vocabulary x dim 64, batch 65536 (configs[4])")
+    ap.add_argument("--mask-ratio", type=float, default=0.1, help="0.1 = the headline configs (L = int(F * ratio) = 3 at 39 fields); "
+                                                                  "0.3 (L = 11) is what the reference's own run scripts use (SURVEY §8d secondary point)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=5)
@@ -63,12 +65,12 @@ WORKLOAD = "c2"
 def workload_name(task, batch, n):
     if WORKLOAD == "c4":
         return (f"DeepFM {task} pretraining, synthetic Avazu shape (24 fields, V=1334055), embed 16, hidden 1000x3, proj 32, K=25, "
-                f"mask_ratio 0.1 (L=2), batch {batch}/GPU x {n} GPU")
+                f"mask_ratio {MASK_RATIO:g} (L={int(24 * MASK_RATIO)}), batch {batch}/GPU x {n} GPU")
     if WORKLOAD == "c5":
         return (f"DCNv2 {task} pretraining, scaled Criteo shape (39 fields, V=99999992), embed 64, hidden 1000x3, cross 3, proj 32, K=25, "
-                f"mask_ratio 0.1 (L=3), batch {batch}/GPU x {n} GPU")
+                f"mask_ratio {MASK_RATIO:g} (L={int(39 * MASK_RATIO)}), batch {batch}/GPU x {n} GPU")
     return (f"DCNv2 {task} pretraining, synthetic Criteo shape (39 fields, V=1085271), embed 16, hidden 1000x3, cross 3, proj 32, "
-            f"K=25, mask_ratio 0.1 (L=3), batch {batch}/GPU x {n} GPU")
+            f"K=25, mask_ratio {MASK_RATIO:g} (L={int(39 * MASK_RATIO)}), batch {batch}/GPU x {n} GPU")
 
 
 def config_dict(task):
@@ -566,6 +568,7 @@ def main_ours(args):
 if __name__ == "__main__":
     a = parse()
     WORKLOAD = a.workload
+    MASK_RATIO = a.mask_ratio
     if a.batch is None:
         a.batch = 65536 if WORKLOAD == "c5" else B_PER_GPU
     if a.impl == "reference":
