@@ -90,10 +90,17 @@ class FusedStep:
         # Independent branches of the step (MLP tower vs CrossNet, weight gradients vs the dgrad chain, table sorts vs
         # GEMMs) are issued on side streams; under capture they become parallel branches of the CUDA graph.
         self.multi_stream = multi_stream
-        # the table streams run many tiny integer kernels (sort passes): high priority lets their CTAs slip in between GEMM
-        # waves instead of queueing behind every GEMM launch (r01e timeline: the NCE sort took 300 us of wall time for 85 us of work)
-        self.streams = ({k: torch.cuda.Stream(device=self.dev, priority=(-1 if k == "tab" else 0)) for k in ("tab", "mlp", "dw")}
+        # The table stream ('tab') has NORMAL priority.  While the sort was 13 tiny launches, high priority let them slip in
+        # between GEMM waves; with the single-launch sort (persistent CTAs that spin at grid barriers) high priority takes SM
+        # slots from the GEMMs for the whole sort.  Measured (r01f, C2 MFP, ms/step, two runs each): normal 0.6209 / 0.6204,
+        # high 0.6604 / 0.6607; sorting the NCE ids under the forward pass instead (MAP_B200_NCE_SORT=early): 0.632 / 0.638.
+        import os
+        tab_prio = int(os.environ.get("MAP_B200_TAB_PRIO", "0"))
+        self.streams = ({k: torch.cuda.Stream(device=self.dev, priority=(tab_prio if k == "tab" else 0)) for k in ("tab", "mlp", "dw")}
                         if multi_stream else {})
+        # where the sort of the NCE ids runs on one GPU: "late" = after the NCE kernel, under the backward GEMMs; "early" = right
+        # after the embedding sort, under the forward GEMMs (the ids = [labels | noise] are known once the noise is drawn)
+        self.nce_sort_early = os.environ.get("MAP_B200_NCE_SORT", "late") == "early"
         self._forked = set()
         self._early = False          # set by _step_body: optimizer work may start inside the backward
         self._tables_done = set()    # tables whose AdamW already ran inside the step
@@ -394,6 +401,9 @@ class FusedStep:
             if self._early:      # every Philox consumer of this step has been issued: the step counter may advance
                 self._hyper_step()
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
+            if self.nce_sort_early and self.mode == "MFP":
+                ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
+                self.tables["mfp_criterion.emb.weight"].plan.run(self.ids_all.view(-1))
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
 
     def _draw_noise(self):
@@ -513,7 +523,8 @@ class FusedStep:
         self.acc_count.zero_()
         n_global = self.global_batch * L
         ops.nce_fwd(self.sel, self.labels.view(-1), self.noise, crit.emb.weight.data, crit.bias.weight.data.view(-1), crit.logprob_noise,
-                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits, ids_out=self.ids_all,
+                    self.norm_term, self.loss_type, grad_scale=1.0 / n_global, logits=self.logits,
+                    ids_out=None if self.nce_sort_early else self.ids_all, want_ids=False,
                     loss_pos=self.loss_pos, dz=self.dz, d_input=self.d_sel, acc_count=self.acc_count)
         # table gradients on the 'tab' stream: sort the (N, K+1) ids, reduce dz * input rows per unique id.  (On one GPU the sort
         # stays HERE, under the backward GEMMs: the SMs are saturated either way, and sorting under the forward pass instead
@@ -522,7 +533,8 @@ class FusedStep:
         self._fork("tab")
         with self._on("tab"):
             ops.reduce_sum(self.loss_pos, 1.0 / n_global, out=self.loss, ws=self.red_ws)
-            te.plan.run(self.ids_all.view(-1))
+            if not self.nce_sort_early:
+                te.plan.run(self.ids_all.view(-1))
             te.plan.reduce_rows(self.sel, P, scale=self.dz.view(-1), group=K + 1, out=te.grad, scalar_out=tb.grad)
             if self._early and self.optimizer_mode == "sparse":
                 # nothing reads the two NCE tables again in this step: their row-wise AdamW runs here, under the backward GEMMs
