@@ -367,7 +367,9 @@ class ShardedFusedStep(FusedStep):
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             self.grad_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
         if self.multi_stream:
-            for k in ("keys", "nce", "comm"):
+            # all table-side streams of the sharded step are high-priority (the configuration the N > 1 numbers were measured in;
+            # the 1-GPU step runs its 'tab' stream at normal priority, see engine.py)
+            for k in ("tab", "keys", "nce", "comm"):
                 self.streams[k] = torch.cuda.Stream(device=self.dev, priority=-1)
 
     # -- setup: shards, peer-visible compact gradients, merge plans
