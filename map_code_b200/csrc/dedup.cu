@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) dedup_persistent_kernel(
     uint32_t* keys_b, uint32_t* vals_a, uint32_t* occ, uint32_t* hist, uint32_t* cnt, unsigned* sync, int64_t* __restrict__ uniq_ids,
     int32_t* __restrict__ seg_start, int32_t* __restrict__ n_unique, int32_t* __restrict__ pos_seg) {
     __shared__ PersistSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int g = blockIdx.x;
     const int64_t n = eff_n(n_cap, n_dev);
     const int64_t ntiles = (n + kSortTile - 1) / kSortTile;
