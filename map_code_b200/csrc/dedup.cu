@@ -360,31 +360,43 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
 // kernels the late CTAs simply arrive late (nothing they wait for depends on this kernel).  Cross-CTA data is read with
 // ld.global.cg (L2): the buffers are rewritten between passes, so the non-coherent / L1 paths must not be used for them.
 constexpr int kPersistMaxCtas = 2 * kNumSMs;
-constexpr unsigned kSpinLimit = 1u << 22;   // ~ seconds; a barrier that is not met sets the error word instead of hanging
+constexpr unsigned long long kBarrierTimeoutNs = 5000000000ull;   // wall-clock bound of one grid-barrier wait (%globaltimer)
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long dedup_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
-// sync[0] = arrival counter (zeroed by the host before the launch), sync[1] = error word
+// sync[0] = arrival counter (zeroed by the host before the launch), sync[1] = error word.
+// A barrier that is not met within kBarrierTimeoutNs of WALL time (not a poll count: the bound does not depend on clocks,
+// time-slicing or co-running kernels) is FATAL: the error word is set for the host and the kernel traps, so the launch fails
+// through the normal CUDA error path and nothing downstream (segment sums, AdamW) ever consumes a partial sort.
 __device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned target, int* ok_s) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(sync, 1u);
-        int ok = 1;
         unsigned spins = 0;
+        unsigned long long t0 = 0;
         while (ld_acquire_u32(sync) < target) {
-            if (++spins > kSpinLimit || ld_acquire_u32(sync + 1) != 0u) {
-                atomicExch(sync + 1, 1u);
-                ok = 0;
-                break;
+            if ((++spins & 0x3FFu) == 0u) {
+                const unsigned long long now = dedup_globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > kBarrierTimeoutNs || ld_acquire_u32(sync + 1) != 0u) {
+                    atomicExch(sync + 1, 1u);
+                    __threadfence_system();
+                    __trap();
+                }
             }
         }
         __threadfence();
-        *ok_s = ok;
+        *ok_s = 1;
     }
     __syncthreads();
     return *ok_s != 0;

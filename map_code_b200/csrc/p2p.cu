@@ -134,11 +134,20 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(const PeerTable flags, 
         st_release_sys_u32(static_cast<unsigned*>(const_cast<void*>(flags.p[s])) + site * kMaxPeers + rank, e);
         const unsigned* mine = static_cast<const unsigned*>(flags.p[rank]) + site * kMaxPeers + s;
         unsigned spins = 0;
+        unsigned long long t0 = 0;
         // (epochs only grow; the signed difference keeps the comparison valid across a wrap)
+        // A rank that does not arrive within 30 s of wall time is FATAL (error word for the host, then trap): continuing would
+        // let the owner-side sums and AdamW run on unsynchronised peer data.
         while ((int)(ld_acquire_sys_u32(mine) - e) < 0) {
-            if (++spins > (1u << 24)) {   // seconds: a rank that never arrives must not hang the GPU
-                if (error_word != nullptr) atomicExch(error_word, 1u);
-                break;
+            if ((++spins & 0x3FFu) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                if (now - t0 > 30000000000ull) {
+                    if (error_word != nullptr) atomicExch(error_word, 1u);
+                    __threadfence_system();
+                    __trap();
+                }
             }
         }
         __threadfence_system();

@@ -30,11 +30,12 @@ def is_no_decay(name: str) -> bool:
 class _Table:
     """One [V, D] table with AdamW state and the dedup plan of its per-step id stream."""
 
-    def __init__(self, name, param, n_ids, weight_decay, device):
+    def __init__(self, name, param, n_ids, weight_decay, device, share: Optional["_Table"] = None):
         self.name, self.p = name, param
         self.V, self.D = param.shape
-        self.m = torch.zeros_like(param.data)
-        self.v = torch.zeros_like(param.data)
+        # `share`: the same table inside another FusedStep over the same model (ragged last batch): ONE optimizer state
+        self.m = torch.zeros_like(param.data) if share is None else share.m
+        self.v = torch.zeros_like(param.data) if share is None else share.v
         self.wd = weight_decay
         self.n_ids = n_ids
         self.plan: Optional[ops.DedupPlan] = None  # may be shared between tables fed by the same id stream
@@ -47,8 +48,16 @@ class FusedStep:
                  warmup_steps: int = 0, total_steps: int = 1000, seed: int = 42, optimizer_mode: str = "sparse",
                  x_train: Optional[torch.Tensor] = None, idx_low=None, idx_high=None, use_graph: bool = True,
                  row0: int = 0, global_batch: Optional[int] = None, gemm_backend: Optional[str] = None,
-                 multi_stream: bool = True):
+                 multi_stream: bool = True, share_state_with: Optional["FusedStep"] = None):
+        """share_state_with: another FusedStep over the SAME model with a different batch size (the Trainer's ragged last batch,
+        reference trainer.py:51-58 has drop_last=False).  Parameters, padded parameter storage, AdamW moments of every dense
+        parameter and table, the step counter and the schedule state are the other engine's tensors; only the activations, the
+        id plans and the captured graph are this engine's own — one optimizer and one scheduler for every batch, like the
+        reference."""
         cfg = model.config
+        self._share = share_state_with
+        if share_state_with is not None and share_state_with.model is not model:
+            raise ValueError("share_state_with: engines must wrap the same model")
         self.model, self.cfg = model, cfg
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -138,8 +147,9 @@ class FusedStep:
         E = lambda *s: torch.empty(*s, **f32)
         self.in_ids = torch.zeros(B, F, **i64)            # static graph inputs
         self.in_labels = torch.zeros(B, **f32)            # CTR labels
-        self.step_counter = torch.zeros(1, **i64)
-        self.hyper = torch.zeros(8, **f32)
+        sh = self._share
+        self.step_counter = torch.zeros(1, **i64) if sh is None else sh.step_counter
+        self.hyper = torch.zeros(8, **f32) if sh is None else sh.hyper
         self.loss = torch.zeros(1, **f32)
         self.acc_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(4, **f32)
@@ -169,12 +179,15 @@ class FusedStep:
         if self.mode == "RFD":
             l2 = getattr(self.model.pred_rfd, "2")
             self.Fp = (F + 3) // 4 * 4
-            self.W2p = torch.zeros(self.Fp, l2.weight.shape[1], **f32)
-            self.W2p[:F].copy_(l2.weight.data)
-            l2.weight.data = self.W2p[:F]
-            self.b2p = torch.zeros(self.Fp, **f32)
-            self.b2p[:F].copy_(l2.bias.data)
-            l2.bias.data = self.b2p[:F]
+            if sh is not None:      # the parameters already live in the other engine's padded storage
+                self.W2p, self.b2p = sh.W2p, sh.b2p
+            else:
+                self.W2p = torch.zeros(self.Fp, l2.weight.shape[1], **f32)
+                self.W2p[:F].copy_(l2.weight.data)
+                l2.weight.data = self.W2p[:F]
+                self.b2p = torch.zeros(self.Fp, **f32)
+                self.b2p[:F].copy_(l2.bias.data)
+                l2.bias.data = self.b2p[:F]
             self._pad_rows = {"pred_rfd.2.weight": self.Fp, "pred_rfd.2.bias": self.Fp}
         # DeepFM pretraining: final_dim = hidden + 1 = 1001 (models.py:211) is not a multiple of 4 floats.  The first head
         # layer's weight [n_out, 1001] is re-pointed at a strided view of zero-padded storage [n_out, 1004] (the padding
@@ -184,9 +197,12 @@ class FusedStep:
         if cfg.pretrain and self.ld_final != self.final_dim:
             wname = self.head0_name + ".weight"
             mod = self.model.feat_encoder if cfg.pt_type == "MFP" else getattr(self.model.pred_rfd, "0")
-            Wp = torch.zeros(mod.weight.shape[0], self.ld_final, **f32)
-            Wp[:, :self.final_dim].copy_(mod.weight.data)
-            mod.weight.data = Wp[:, :self.final_dim]
+            if sh is not None:
+                Wp = sh._pad_cols[wname]
+            else:
+                Wp = torch.zeros(mod.weight.shape[0], self.ld_final, **f32)
+                Wp[:, :self.final_dim].copy_(mod.weight.data)
+                mod.weight.data = Wp[:, :self.final_dim]
             self._pad_cols[wname] = Wp
         # dense parameter gradients + AdamW state
         self.dense: Dict[str, torch.nn.Parameter] = {}
@@ -227,8 +243,8 @@ class FusedStep:
                     self.grads_padded[n] = flat.view(self._pad_rows[n], -1)
                 self.grads[n] = flat[:p.numel()].view_as(p.data)
                 self.opt_param[n] = p.data
-        self.exp_avg = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense}
-        self.exp_avg_sq = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense}
+        self.exp_avg = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense} if sh is None else sh.exp_avg
+        self.exp_avg_sq = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense} if sh is None else sh.exp_avg_sq
         entries = [(self.opt_param[n], self.grad_flat[offs[n]:offs[n] + self.opt_param[n].numel()].view_as(self.opt_param[n]),
                     self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None) for n in self.dense]
         self.adam_table, self.adam_n, self.adam_max = ops.make_adamw_tensor_list(entries, dev)
@@ -286,14 +302,17 @@ class FusedStep:
 
     def _make_embed_table(self):
         name = "embed.embedding.weight"
-        t = _Table(name, self.embed_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev)
+        t = _Table(name, self.embed_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev, self._shared_table(name))
         t.plan = ops.DedupPlan(self.B * self.F, self.V, self.dev)
         self.tables[name] = t
+
+    def _shared_table(self, name):
+        return None if self._share is None else self._share.tables[name]
 
     def _make_lr_table(self):
         """DeepFM's first-order table lr_layer.embed_w [V,1] is fed by the same id stream as the embedding: it shares its plan."""
         name = "lr_layer.embed_w.weight"
-        t = _Table(name, self.lr_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev)
+        t = _Table(name, self.lr_w, self.B * self.F, 0.0 if is_no_decay(name) else self.wd, self.dev, self._shared_table(name))
         t.plan = self.tables["embed.embedding.weight"].plan
         self.tables[name] = t
 
@@ -301,8 +320,10 @@ class FusedStep:
         crit = self.model.mfp_criterion
         n_occ = max(self.N, 1) * (self.K + 1)
         plan = ops.DedupPlan(n_occ, self.V, self.dev)
-        te = _Table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.emb.weight") else self.wd, self.dev)
-        tb = _Table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.bias.weight") else self.wd, self.dev)
+        te = _Table("mfp_criterion.emb.weight", crit.emb.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.emb.weight") else self.wd, self.dev,
+                    self._shared_table("mfp_criterion.emb.weight"))
+        tb = _Table("mfp_criterion.bias.weight", crit.bias.weight, n_occ, 0.0 if is_no_decay("mfp_criterion.bias.weight") else self.wd, self.dev,
+                    self._shared_table("mfp_criterion.bias.weight"))
         te.plan = tb.plan = plan
         self.tables[te.name], self.tables[tb.name] = te, tb
 

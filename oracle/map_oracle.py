@@ -540,7 +540,15 @@ class OracleTrainer:
 
     def __init__(self, cfg, params: Dict[str, torch.Tensor], alias_prob=None, alias_alias=None, x_train=None,
                  lr=1e-3, weight_decay=5e-2, betas=(0.9, 0.999), eps=1e-8, mask_ratio=0.1, sampling_method="randint",
-                 seed=42, lr_lambda=None, idx_low=None, idx_high=None):
+                 seed=42, lr_lambda=None, idx_low=None, idx_high=None, table_update: str = "dense"):
+        """table_update="dense" is the reference (transformers.AdamW sweeps every row of every [V, .] table, trainer.py:140).
+        table_update="touched_rows" restates the PRODUCT's documented `optimizer_mode="sparse"` semantics for its parity tests
+        (DESIGN.md §5.1): a table row takes part in the optimizer step only when its id occurs in this step's batch
+        (embedding / first-order tables: the masked input ids; NCE tables: targets + noise); the update rule is unchanged."""
+        if table_update not in ("dense", "touched_rows"):
+            raise ValueError(table_update)
+        self.table_update = table_update
+        self._touched = {}
         self.cfg = cfg
         self.buffers = {k: v for k, v in params.items() if k in TRAINABLE_EXCLUDE}
         self.params = {k: v.clone().requires_grad_(True) for k, v in params.items() if k not in TRAINABLE_EXCLUDE}
@@ -582,6 +590,17 @@ class OracleTrainer:
         else:
             outs = model_forward(self.cfg, all_p, batch["input_ids"], batch["labels"])
         outs[0].backward()
+        if self.table_update == "touched_rows":
+            V = self.cfg.input_size
+            t_in = torch.zeros(V, dtype=torch.bool)
+            t_in[batch["input_ids"].reshape(-1)] = True
+            self._touched = {"embed.embedding.weight": t_in, "lr_layer.embed_w.weight": t_in}
+            if self.cfg.pretrain and self.cfg.pt_type == "MFP":
+                t_nce = torch.zeros(V, dtype=torch.bool)
+                t_nce[batch["labels"].reshape(-1)] = True
+                t_nce[batch["noise"].reshape(-1)] = True
+                self._touched["mfp_criterion.emb.weight"] = t_nce
+                self._touched["mfp_criterion.bias.weight"] = t_nce
         return outs
 
     def optimizer_step(self):
@@ -592,6 +611,13 @@ class OracleTrainer:
                 if p.grad is None:
                     continue
                 m, v = self.state[k]
+                rows = self._touched.get(k) if self.table_update == "touched_rows" else None
+                if rows is not None:
+                    pr, mr, vr = p[rows], m[rows], v[rows]
+                    hf_adamw_update(pr, p.grad[rows], mr, vr, self.global_step, lr, self.betas[0], self.betas[1], self.eps,
+                                    0.0 if is_no_decay(k) else self.wd)
+                    p[rows], m[rows], v[rows] = pr, mr, vr
+                    continue
                 hf_adamw_update(p, p.grad, m, v, self.global_step, lr, self.betas[0], self.betas[1], self.eps,
                                 0.0 if is_no_decay(k) else self.wd)
 
