@@ -116,7 +116,9 @@ typedef struct {
     int64_t n;       /* element count */
     int32_t rows, cols; /* only used when p_t != NULL (n == rows*cols) */
     float weight_decay;
-    int32_t pad_;
+    int32_t n_planes;        /* 0, or 1..3: the update also rewrites the parameter's bf16 planes (operand format of map_gemm_bf16s_group) */
+    uint16_t* planes;        /* plane i at planes + i * plane_stride, same flat layout as p (n % 4 == 0 required) */
+    int64_t plane_stride;
 } map_adamw_tensor;
 /* one launch over a device-resident list of tensors (dense parameters) */
 int map_adamw_multi_tensor(const map_adamw_tensor* tensors_dev, int n_tensors, int64_t max_elems_per_tensor,
@@ -267,6 +269,30 @@ int map_gemm_tf32_tcgen05(const map_gemm_args* args, map_stream_t stream);
 int map_gemm_tf32_group(const map_gemm_args* args, int count, map_stream_t stream);
 /* 1 if map_gemm_tf32_tcgen05 accepts these arguments (shape / alignment), else 0 */
 int map_gemm_tf32_supported(const map_gemm_args* args);
+/* ---- split-bf16 tensor-core GEMM (the default backend of the step; gemm_bf16s.cu).
+ * Every fp32 operand x is carried as bf16 planes hi = bf16(x), lo = bf16(x - hi), lo2 = bf16(x - hi - lo) in the SAME storage
+ * layout as x (plane i at base + i * plane_stride elements, row stride `ld` elements; 16-byte aligned, strides % 8 == 0).
+ * terms = 3: hi*hi + hi*lo + lo*hi into one fp32 accumulator (~2^-17 per product; needs 2 planes of A and B);
+ * terms = 6: + lo*lo + hi*lo2 + lo2*hi (~2^-24, fp32-level; needs 3 planes) — used for the forward GEMMs whose output feeds a
+ * ReLU: d(loss)/d(weights) is discontinuous in those pre-activations.  g.A / g.B are ignored; g carries the
+ * shapes, trans flags, epilogue and fp32 outputs exactly as for map_gemm_tf32_tcgen05.  Optional c_planes: the epilogue also
+ * writes C as c_nplanes bf16 planes (the operand format of the GEMMs that consume C next).
+ * One call = up to 4 INDEPENDENT problems in one persistent launch of CTA pairs (cta_group::2) with two TMEM accumulators. */
+typedef struct {
+    map_gemm_args g;
+    const uint16_t* a_planes; int64_t a_ld; int64_t a_plane_stride; int32_t a_nplanes; int32_t terms;
+    const uint16_t* b_planes; int64_t b_ld; int64_t b_plane_stride; int32_t b_nplanes; int32_t reserved0_;
+    uint16_t* c_planes; int64_t c_ld; int64_t c_plane_stride; int32_t c_nplanes; int32_t reserved1_;
+} map_gemm_split_args;
+int map_gemm_bf16s_group(const map_gemm_split_args* args, int count, map_stream_t stream);
+/* Tuning aid (scripts/trace_gemm_bf16s.py): while dev_buf != NULL every CTA of the following map_gemm_bf16s_group launches writes a
+ * 64 x uint64 record (entry / exit times, and per tile: first TMA issue, accumulator granted, first stage landed, last MMA issued,
+ * accumulator complete, epilogue end) to dev_buf[64 * cta ...] if capacity_u64 covers the grid.  NULL switches it off. */
+int map_gemm_bf16s_set_trace(unsigned long long* dev_buf, int64_t capacity_u64);
+/* fp32 [rows, cols] (row stride ld) -> n_planes (1..3) bf16 planes [rows, ld_p]; for operands no kernel of ours produces
+ * (parameters after load_state_dict, test inputs).  cols, ld, ld_p, plane_stride multiples of 4 elements. */
+int map_split_bf16(const float* src, int64_t ld, int64_t rows, int64_t cols, uint16_t* planes, int64_t ld_p, int64_t plane_stride,
+                   int n_planes, map_stream_t stream);
 /* Tuning aid (scripts/trace_gemm.py): while dev_buf != NULL every CTA of the following tcgen05 GEMM launches (grids of at
  * most capacity_records CTAs) writes 8 uint64 phase timestamps to dev_buf[8 * linear_cta_id ...].  NULL switches it off. */
 int map_gemm_set_trace(unsigned long long* dev_buf, int64_t capacity_records);

@@ -42,7 +42,17 @@ class GemmArgs(C.Structure):
 class AdamwTensor(C.Structure):
     _fields_ = [
         ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_t", C.c_void_p),
-        ("n", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("weight_decay", C.c_float), ("pad_", C.c_int32),
+        ("n", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("weight_decay", C.c_float), ("n_planes", C.c_int32),
+        ("planes", C.c_void_p), ("plane_stride", C.c_int64),
+    ]
+
+
+class GemmSplitArgs(C.Structure):
+    _fields_ = [
+        ("g", GemmArgs),
+        ("a_planes", C.c_void_p), ("a_ld", C.c_int64), ("a_plane_stride", C.c_int64), ("a_nplanes", C.c_int32), ("terms", C.c_int32),
+        ("b_planes", C.c_void_p), ("b_ld", C.c_int64), ("b_plane_stride", C.c_int64), ("b_nplanes", C.c_int32), ("reserved0_", C.c_int32),
+        ("c_planes", C.c_void_p), ("c_ld", C.c_int64), ("c_plane_stride", C.c_int64), ("c_nplanes", C.c_int32), ("reserved1_", C.c_int32),
     ]
 
 
@@ -86,6 +96,9 @@ PROTOTYPES = {
     "map_gemm_tf32_tcgen05": (_i, [C.POINTER(GemmArgs), _p]),
     "map_gemm_tf32_group": (_i, [C.POINTER(GemmArgs), _i, _p]),
     "map_gemm_tf32_supported": (_i, [C.POINTER(GemmArgs)]),
+    "map_gemm_bf16s_group": (_i, [C.POINTER(GemmSplitArgs), _i, _p]),
+    "map_gemm_bf16s_set_trace": (_i, [_p, _l]),
+    "map_split_bf16": (_i, [_p, _l, _l, _l, _p, _l, _l, _i, _p]),
     "map_gemm_set_trace": (_i, [_p, _l]),
     "map_emb_gather_owned_f32": (_i, [_p, _l, _i, _p, _l, _i, _i, _p, _p]),
     "map_owned_keys": (_i, [_p, _l, _i, _i, _l, _p, _p]),
@@ -154,7 +167,7 @@ CURRENT_TAG = None    # free-form shape tag set by ops.* just before a call (e.g
 LAUNCHES = None       # set to a dict: name -> number of kernels launched
 RECORD = None         # set to a list: (name, args, tag) of every call (arguments kept alive), for replaying one kernel class alone
 TIMELINE = None       # set to dict(buf=<device int64 tensor>, ops=[]): a timestamp marker follows every call on its stream
-HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace", "map_p2p_alloc", "map_p2p_open", "map_p2p_close", "map_p2p_free"}
+HOST_FUNCS = {"map_alias_build", "map_gemm_set_trace", "map_gemm_bf16s_set_trace", "map_p2p_alloc", "map_p2p_open", "map_p2p_close", "map_p2p_free"}
 
 
 def mark(name: str, tag=None, stream: int = None):

@@ -3,6 +3,8 @@
 // Hyper-parameters live in device memory so a captured CUDA graph sees the scheduled learning rate of every replay.
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mapb {
@@ -88,6 +90,19 @@ __global__ void __launch_bounds__(256) adamw_multi_tensor_kernel(const map_adamw
             *reinterpret_cast<float4*>(t.p + i) = p;
             *reinterpret_cast<float4*>(t.m + i) = m;
             *reinterpret_cast<float4*>(t.v + i) = v;
+            if (t.n_planes > 0) {   // refresh the bf16 planes the split-bf16 GEMMs read: hi = bf16(p), lo = bf16(p - hi), ...
+                float r0 = p.x, r1 = p.y, r2 = p.z, r3 = p.w;
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(t.planes) + i;
+                for (int pl = 0; pl < t.n_planes; ++pl) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1), h2 = __float2bfloat16_rn(r2), h3 = __float2bfloat16_rn(r3);
+                    r0 -= __bfloat162float(h0); r1 -= __bfloat162float(h1); r2 -= __bfloat162float(h2); r3 -= __bfloat162float(h3);
+                    uint2 pk;
+                    pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+                    *reinterpret_cast<uint2*>(dst) = pk;
+                    dst += t.plane_stride;
+                }
+            }
             if (t.p_t != nullptr) {
                 const float pv[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll

@@ -1,0 +1,647 @@
+// K3 / K4 (default backend): split-bf16 tensor-core GEMM for sm_100a with fp32-level accuracy.
+//
+// Why not TF32: tcgen05 kind::tf32 truncates operands to 10 mantissa bits.  On this path the forward pre-activations feed
+// ReLUs, and d(loss)/d(weights) is a DISCONTINUOUS function of them: a pre-activation whose sign differs from the reference's
+// switches a whole unit's gradient on or off.  Measured at the benchmarked shape (B=4096, H=1000; profiles/r02a_parity_*):
+// TF32 -> 3e-2 Frobenius error on the MLP weight gradients (north_star asks for 1e-3), exact fp32 with another summation
+// order -> 2e-4..8e-4 (the reference's own reproducibility floor).  Every fp32 operand is therefore carried as bf16 PLANES
+//     x = hi + lo (+ lo2),  hi = bf16(x), lo = bf16(x - hi), lo2 = bf16(x - hi - lo)
+// written once by whoever produces the tensor (GEMM epilogues, the gather, AdamW), and a GEMM sums several bf16 MMAs into one
+// fp32 TMEM accumulator:
+//     terms = 3:  hi*hi + hi*lo + lo*hi                      (relative error ~2^-17 per product; all linear uses)
+//     terms = 6:  + lo*lo + hi*lo2 + lo2*hi                  (~2^-24: the forward GEMMs whose outputs feed a ReLU)
+// The tensor core's fp32 accumulator rounds toward zero: measured on B200, every MMA that lands in an accumulator costs ~2e-8 of its
+// magnitude, systematically (terms = 6, K = 1624: 624 MMAs -> 1.1e-5, WORSE than terms = 3).  With terms = 6 the five small
+// correction products therefore go to a SECOND TMEM accumulator (its rounding is relative to a 2^-8 times smaller sum) and only
+// the K/16 hi*hi MMAs touch the main one; the epilogue adds the two in fp32.
+// bf16 keeps fp32's exponent range, so there is no scaling and no overflow mode.  Per k-block of 64 elements a CTA stages 2-3
+// planes of A and of its half of B (TMA, 128B swizzle) and the pair's leader issues terms x 4 MMAs (kind::f16, K = 16).
+//
+// Shape of the kernel (one launch = up to 4 INDEPENDENT problems = one level of the step's dependency graph):
+//   * persistent: one CTA PAIR (cta_group::2, 256 x BLOCK_N tile, each CTA stages its 128 rows of A and half of B) per pair
+//     of SMs walks the concatenated tile list of all problems;
+//   * warp-specialised: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (leader CTA), warps 2-5 epilogue;
+//   * two TMEM accumulators (2 x 256 columns): the epilogue of tile i (TMEM -> registers -> smem transpose -> fused
+//     bias / ReLU / CrossNet / ReLU-mask / residual -> global fp32 + bf16 planes for the next GEMM) overlaps the MMAs of tile i+1;
+//   * operands in both majors straight from row-major storage: K-major tiles are {64 k, rows} boxes, MN-major tiles are
+//     {64 mn, 64 k} boxes (dgrad reads W [N,K] as B^T, wgrad reads dY and X transposed), no transposed copies anywhere.
+// Replaces the cuBLAS sgemm behind every nn.Linear of the step (code/layers.py:179-200, code/models.py:116-123), fwd + bwd.
+#define MAP_GEMM_TWO_ACCUMULATORS 1
+#include "gemm_common.cuh"
+
+namespace mapb {
+
+constexpr int kSBlockK = 64;               // bf16 elements per k-block = 128 bytes = one swizzle span
+constexpr int kSUmmaK = 16;                // kind::f16: 32 bytes of K per tcgen05.mma
+constexpr int kSPlaneA = kBlockM * 128;    // 16 KiB: one plane of a CTA's A tile
+constexpr int kSChunk = 64 * 128;          // 8 KiB: one {64 mn, 64 k} box of an MN-major tile
+constexpr int kSMaxStages = 6;
+constexpr int kSMaxGroup = 4;
+constexpr int kSAccCols = 256;             // TMEM columns per accumulator
+constexpr int kSTmemCols = 2 * kSAccCols;
+constexpr int kSStagingBytes = 4 * 32 * kStageLd * 4;   // per-warp transpose tiles of the 4 epilogue warps
+constexpr int kSSmemBudget = 227 * 1024 - 2048;
+
+struct SProblem {
+    GemmParams p;          // b_tile_bytes = bytes of ONE plane of this CTA's half of the B tile
+    int pa, pb, terms;     // planes staged of A / B; MMAs per k-step (3 or 6; 6 = two accumulators, see above)
+    int half_n;            // B columns staged by one CTA (block_n / 2)
+    int n_tiles, m_pairs;  // tile grid (pair tiles)
+    int tile_end;          // exclusive prefix sum of pair tiles (x split_k) over the problems of the launch
+};
+
+struct SGroupArgs {
+    CUtensorMap tmap[2 * kSMaxGroup];   // A, B of problem i at [2i], [2i+1]; 3-D {inner, rows, plane}
+    SProblem pr[kSMaxGroup];
+    int count, total_tiles;
+    int stages, stage_bytes;            // one ring geometry for the whole launch (the largest problem's planes)
+    unsigned long long* trace;          // optional per-CTA timeline (map_gemm_bf16s_set_trace), nullptr in production
+};
+
+// trace record of one CTA: 64 x u64 = {globaltimer at entry, clock after setup, globaltimer at exit, smid | tiles << 32,
+// then for each of its first 10 tiles: clock of the first TMA issue (producer), clock when the MMA issuer got the accumulator
+// buffer, clock when the first stage had landed, clock when the last MMA was issued, clock when the accumulator was complete
+// (epilogue warp 2), clock at the end of warp 2's epilogue}
+constexpr int kSTraceWords = 64;
+constexpr int kSTraceTiles = 10;
+
+struct TileInfo {
+    int gi, m_pair, n_tile, ks;
+    int block_n, half_n, trans_a, trans_b, pa, pb, terms, nkb, kb0, b_plane_bytes;
+};
+
+// TMEM accumulator buffers: a single-accumulator tile takes ONE of the two 256-column buffers (alternating, so its epilogue
+// overlaps the next tile's MMAs), a two-accumulator tile takes BOTH (main in buffer 0, corrections in buffer 1).  MMA issuer and
+// epilogue warps run the same bookkeeping: uses[b] = tiles that have used buffer b so far (its parity drives the barriers).
+struct AccState {
+    uint32_t uses[2];
+    uint32_t next;
+};
+__device__ __forceinline__ uint32_t acc_pick(AccState& st, bool dual) {
+    if (dual) { st.next = 0; return 0; }
+    const uint32_t b = st.next;
+    st.next ^= 1u;
+    return b;
+}
+
+__device__ __forceinline__ TileInfo decode_tile(const SGroupArgs& g, int t) {
+    TileInfo ti;
+    int gi = 0, start = 0;
+#pragma unroll
+    for (int i = 0; i < kSMaxGroup - 1; ++i)
+        if (t >= g.pr[i].tile_end) {
+            gi = i + 1;
+            start = g.pr[i].tile_end;
+        }
+    int nt, mp, nkb_split, kbt;
+#define MAP_LOAD_PR(i)                                                                                              \
+    {                                                                                                               \
+        ti.block_n = g.pr[i].p.block_n; ti.half_n = g.pr[i].half_n; ti.trans_a = g.pr[i].p.trans_a;                 \
+        ti.trans_b = g.pr[i].p.trans_b; ti.pa = g.pr[i].pa; ti.pb = g.pr[i].pb; ti.terms = g.pr[i].terms;          \
+        ti.b_plane_bytes = g.pr[i].p.b_tile_bytes; nt = g.pr[i].n_tiles; mp = g.pr[i].m_pairs;                      \
+        nkb_split = g.pr[i].p.num_k_blocks; kbt = g.pr[i].p.k_blocks_total;                                         \
+    }
+    if (gi == 0) MAP_LOAD_PR(0) else if (gi == 1) MAP_LOAD_PR(1) else if (gi == 2) MAP_LOAD_PR(2) else MAP_LOAD_PR(3)
+#undef MAP_LOAD_PR
+    const int local = t - start;
+    ti.gi = gi;
+    ti.m_pair = local % mp;          // m fastest: the pairs that run side by side share one B (weight) tile
+    const int r = local / mp;
+    ti.n_tile = r % nt;
+    ti.ks = r / nt;
+    ti.kb0 = ti.ks * nkb_split;
+    int nkb = kbt - ti.kb0;
+    if (nkb > nkb_split) nkb = nkb_split;
+    ti.nkb = nkb;
+    return ti;
+}
+
+template <int E0, int E1, int E2, int E3>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __grid_constant__ SGroupArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t full_bar[kSMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kSMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1);
+    const int n_clusters = (int)(gridDim.x >> 1);
+    const int stages = g.stages;
+    const uint32_t stage_bytes = (uint32_t)g.stage_bytes;
+    const int total = g.total_tiles;
+    unsigned long long* trace = g.trace != nullptr ? g.trace + (size_t)kSTraceWords * blockIdx.x : nullptr;
+    if (trace != nullptr && threadIdx.x == 0) trace[0] = globaltimer_ns();
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 2 * g.count; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmap[i]) : "memory");
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[b]), 8);   // 4 epilogue warps of each CTA of the pair (leader's barrier is used)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // warp-collective in BOTH CTAs: the same columns are reserved on both SMs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)kSTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything of this CTA can arrive on them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    if (trace != nullptr && threadIdx.x == 0) trace[1] = (unsigned long long)clock64();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===================== TMA producer (each CTA: its A rows, its half of B) =====================
+            int s = 0;
+            uint32_t ph = 0;
+            int tj = 0;
+            for (int t = cluster_id; t < total; t += n_clusters, ++tj) {
+                const TileInfo ti = decode_tile(g, t);
+                const CUtensorMap* tmap_a = &g.tmap[2 * ti.gi];
+                const CUtensorMap* tmap_b = tmap_a + 1;
+                const int m0 = (ti.m_pair * 2 + (int)cta_rank) * kBlockM;
+                const int nb = ti.n_tile * ti.block_n + (int)cta_rank * ti.half_n;
+                const uint32_t tx_bytes = (uint32_t)(ti.pa * kSPlaneA + ti.pb * ti.b_plane_bytes);
+                const int b_chunks = ti.half_n >> 6;
+                for (int i = 0; i < ti.nkb; ++i) {
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    if (trace != nullptr && i == 0 && tj < kSTraceTiles) trace[4 + 6 * tj] = (unsigned long long)clock64();
+                    // both CTAs' loads complete on the LEADER's full barrier (its MMA reads both shared memories)
+                    if (cta_rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * tx_bytes);
+                    const uint32_t fb = mapa_cta0(smem_u32(&full_bar[s]));
+                    const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t b_dst = a_dst + (uint32_t)(ti.pa * kSPlaneA);
+                    const int k0 = (ti.kb0 + i) * kSBlockK;
+                    for (int pl = 0; pl < ti.pa; ++pl) {
+                        if (!ti.trans_a) {
+                            tma_load_3d_pair(a_dst + pl * kSPlaneA, tmap_a, fb, k0, m0, pl);                      // box {64 k, 128 m}
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kBlockM / 64; ++c)
+                                tma_load_3d_pair(a_dst + pl * kSPlaneA + c * kSChunk, tmap_a, fb, m0 + c * 64, k0, pl);   // box {64 m, 64 k}
+                        }
+                    }
+                    for (int pl = 0; pl < ti.pb; ++pl) {
+                        if (!ti.trans_b) {
+                            tma_load_3d_pair(b_dst + pl * ti.b_plane_bytes, tmap_b, fb, k0, nb, pl);              // box {64 k, half_n n}
+                        } else {
+                            for (int c = 0; c < b_chunks; ++c)
+                                tma_load_3d_pair(b_dst + pl * ti.b_plane_bytes + c * kSChunk, tmap_b, fb, nb + c * 64, k0, pl);  // box {64 n, 64 k}
+                        }
+                    }
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && cta_rank == 0) {  // ===================== MMA issuer (the pair's leader) =====================
+            int s = 0;
+            uint32_t ph = 0;
+            AccState acc{{0u, 0u}, 0u};
+            int tj = 0;
+            for (int t = cluster_id; t < total; t += n_clusters, ++tj) {
+                const TileInfo ti = decode_tile(g, t);
+                const bool dual = ti.terms == 6;
+                const uint32_t buf = acc_pick(acc, dual);
+                // the epilogue of the tile that last used this accumulator has drained it
+                mbar_wait(smem_u32(&tmem_empty_bar[buf]), (acc.uses[buf] & 1u) ^ 1u);
+                if (dual) mbar_wait(smem_u32(&tmem_empty_bar[1]), (acc.uses[1] & 1u) ^ 1u);
+                tcgen05_fence_after();
+                if (trace != nullptr && tj < kSTraceTiles) trace[5 + 6 * tj] = (unsigned long long)clock64();
+                const uint32_t idesc = make_idesc_bf16(ti.block_n, ti.trans_a, ti.trans_b, 2 * kBlockM);
+                // K-major  (SWIZZLE_128B): 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of every row -> +32 B per K step
+                // MN-major (SWIZZLE_128B): 64-element chunks 8192 B apart (LBO); 8-k-row groups 1024 B apart (SBO); one MMA
+                //                          consumes 16 k-rows -> +2048 B per K step
+                const uint32_t a_lbo = ti.trans_a ? (uint32_t)kSChunk : 16u, a_adv = ti.trans_a ? 2048u : 32u;
+                const uint32_t b_lbo = ti.trans_b ? (uint32_t)kSChunk : 16u, b_adv = ti.trans_b ? 2048u : 32u;
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)kSAccCols;
+                const uint32_t d_corr = tmem_base + (uint32_t)kSAccCols;   // two-accumulator tiles: corrections in buffer 1
+                const uint32_t a_planes_bytes = (uint32_t)(ti.pa * kSPlaneA);
+                for (int i = 0; i < ti.nkb; ++i) {
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    tcgen05_fence_after();
+                    if (trace != nullptr && i == 0 && tj < kSTraceTiles) trace[6 + 6 * tj] = (unsigned long long)clock64();
+                    const uint32_t a_src = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t b_src = a_src + a_planes_bytes;
+                    // products ordered (a plane, b plane): (0,0) (0,1) (1,0) | (1,1) (0,2) (2,0)
+                    for (int term = 0; term < ti.terms; ++term) {
+                        const int ia = (term == 2 || term == 3) ? 1 : (term == 5 ? 2 : 0);
+                        const int ib = (term == 1 || term == 3) ? 1 : (term == 4 ? 2 : 0);
+                        const uint32_t a_pl = a_src + (uint32_t)(ia * kSPlaneA);
+                        const uint32_t b_pl = b_src + (uint32_t)(ib * ti.b_plane_bytes);
+#pragma unroll
+                        for (int k = 0; k < kSBlockK / kSUmmaK; ++k) {
+                            const uint64_t da = make_smem_desc(a_pl + k * a_adv, a_lbo, 1024u, 2u);
+                            const uint64_t db = make_smem_desc(b_pl + k * b_adv, b_lbo, 1024u, 2u);
+                            if (dual && term > 0) umma_bf16_pair(d_corr, da, db, idesc, (i | (term - 1) | k) != 0 ? 1u : 0u);
+                            else umma_bf16_pair(d_tmem, da, db, idesc, (i | term | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tcgen05_commit_pair(smem_u32(&empty_bar[s]));   // frees the stage in both CTAs when these MMAs have read it
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+                tcgen05_commit_pair(smem_u32(&tmem_full_bar[buf]));  // accumulator complete (both CTAs' epilogues)
+                if (trace != nullptr && tj < kSTraceTiles) trace[7 + 6 * tj] = (unsigned long long)clock64();
+                ++acc.uses[buf];
+                if (dual) {
+                    tcgen05_commit_pair(smem_u32(&tmem_full_bar[1]));
+                    ++acc.uses[1];
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs): TMEM -> registers -> smem transpose -> fused epilogue -> global =====
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stages * stage_bytes) + q * (32 * kStageLd);
+        AccState acc{{0u, 0u}, 0u};
+        int tj = 0;
+        for (int t = cluster_id; t < total; t += n_clusters, ++tj) {
+            const TileInfo ti = decode_tile(g, t);
+            const bool dual = ti.terms == 6;
+            const uint32_t buf = acc_pick(acc, dual);
+            unsigned long long* ttr = (trace != nullptr && tj < kSTraceTiles) ? trace + 4 + 6 * tj : nullptr;   // epi_tile stamps [5], [6]
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kSAccCols;
+            const int m0 = (ti.m_pair * 2 + (int)cta_rank) * kBlockM;
+            const int n0 = ti.n_tile * ti.block_n;
+            const int row_base = m0 + q * 32;
+            const uint32_t fb = smem_u32(&tmem_full_bar[buf]);
+            const uint32_t par = acc.uses[buf] & 1u;
+            if (dual) {   // the corrections' barrier completes with the same commit sequence: consume its phase too
+                mbar_wait(smem_u32(&tmem_full_bar[1]), acc.uses[1] & 1u);
+            }
+            // (epi_tile stamps ttr[5] when the accumulator is complete and ttr[6] at its end: words 8 and 9 (+6 per tile) of the record
+            //  are written through the pointer shifted by -1 so that they land on [4 + 6 tj + 4] and [+5])
+            unsigned long long* tt = ttr != nullptr ? ttr - 1 : nullptr;
+            if (ti.gi == 0) epi_slot<E0>(g.pr[0].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
+            else if (ti.gi == 1) epi_slot<E1>(g.pr[1].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
+            else if (ti.gi == 2) epi_slot<E2>(g.pr[2].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
+            else epi_slot<E3>(g.pr[3].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
+            // this warp has read its quarter of the accumulator: hand the buffer back to the MMA issuer (leader CTA's barrier)
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cta0(smem_u32(&tmem_empty_bar[buf]));
+                if (dual) mbar_arrive_cta0(smem_u32(&tmem_empty_bar[1]));
+            }
+            ++acc.uses[buf];
+            if (dual) ++acc.uses[1];
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        int my_tiles = 0;
+        for (int t = cluster_id; t < total; t += n_clusters) ++my_tiles;
+        trace[2] = globaltimer_ns();
+        trace[3] = (unsigned long long)smid | ((unsigned long long)my_tiles << 32);
+    }
+    cluster_sync_all();  // neither CTA retires (shared memory, barriers, TMEM) while the other may still reference it
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kSTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ split kernel
+// fp32 [rows, cols] (row stride ld) -> n_planes bf16 planes [rows, ld_p]: hi, lo, lo2 (see the header of this file)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols4,
+                                                         __nv_bfloat16* __restrict__ planes, int64_t ld_p, int64_t plane_stride, int n_planes) {
+    const int64_t total = rows * cols4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / cols4;
+        const int64_t c = (i - r * cols4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
+        float r0 = v.x, r1 = v.y, r2 = v.z, r3 = v.w;
+        __nv_bfloat16* dst = planes + r * ld_p + c;
+        for (int pl = 0; pl < n_planes; ++pl) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1), h2 = __float2bfloat16_rn(r2), h3 = __float2bfloat16_rn(r3);
+            r0 -= __bfloat162float(h0); r1 -= __bfloat162float(h1); r2 -= __bfloat162float(h2); r3 -= __bfloat162float(h3);
+            uint2 pk;
+            pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            *reinterpret_cast<uint2*>(dst) = pk;
+            dst += plane_stride;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFnS)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFnS get_encode_fn_s() {
+    static EncodeTiledFnS fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFnS>(sym);
+    }
+    return fn;
+}
+
+// 3-D bf16 tensor map over the planes of one operand: {inner (contiguous), outer rows, plane}; box = {64, box_rows, 1}
+static int make_tmap_planes(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int64_t plane_stride,
+                            int n_planes, int box_rows) {
+    EncodeTiledFnS enc = get_encode_fn_s();
+    if (enc == nullptr) {
+        set_error("map_gemm_bf16s: cuTensorMapEncodeTiled is not available from the driver");
+        return MAP_ECUDA;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)n_planes};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ld * 2u, (cuuint64_t)plane_stride * 2u};
+    const cuuint32_t box[3] = {(cuuint32_t)kSBlockK, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("map_gemm_bf16s: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld planes=%d box_rows=%d", (int)r,
+                  (long long)inner, (long long)outer, (long long)ld, n_planes, box_rows);
+        return MAP_ECUDA;
+    }
+    return MAP_OK;
+}
+
+static bool aligned16s(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static int bf16s_check(const map_gemm_split_args* a) {
+    const map_gemm_args* g = &a->g;
+    MAP_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "map_gemm_bf16s: bad shape M=%d N=%d K=%d", g->M, g->N, g->K);
+    MAP_REQUIRE(g->N % 4 == 0, "map_gemm_bf16s: N=%d must be a multiple of 4", g->N);
+    MAP_REQUIRE(a->a_planes && a->b_planes && g->C, "map_gemm_bf16s: null operand");
+    MAP_REQUIRE(a->terms == 3 || a->terms == 6, "map_gemm_bf16s: terms=%d must be 3 or 6", a->terms);
+    const int need = a->terms == 6 ? 3 : 2;
+    MAP_REQUIRE(a->a_nplanes >= need && a->b_nplanes >= need, "map_gemm_bf16s: terms=%d needs %d planes of A and B (have %d, %d)", a->terms,
+                need, a->a_nplanes, a->b_nplanes);
+    MAP_REQUIRE(a->a_ld % 8 == 0 && a->b_ld % 8 == 0 && a->a_plane_stride % 8 == 0 && a->b_plane_stride % 8 == 0 && aligned16s(a->a_planes) &&
+                    aligned16s(a->b_planes),
+                "map_gemm_bf16s: operand planes need 16-byte aligned bases and row / plane strides that are multiples of 8 elements");
+    MAP_REQUIRE(g->ldc % 4 == 0 && aligned16s(g->C), "map_gemm_bf16s: C alignment");
+    MAP_REQUIRE(!g->bias || aligned16s(g->bias), "map_gemm_bf16s: bias alignment");
+    MAP_REQUIRE(!g->aux0 || (aligned16s(g->aux0) && g->ld_aux0 % 4 == 0), "map_gemm_bf16s: aux0 alignment");
+    MAP_REQUIRE(!g->aux1 || (aligned16s(g->aux1) && g->ld_aux1 % 4 == 0), "map_gemm_bf16s: aux1 alignment");
+    MAP_REQUIRE(!g->aux2 || (aligned16s(g->aux2) && g->ld_aux2 % 4 == 0), "map_gemm_bf16s: aux2 alignment");
+    MAP_REQUIRE(!g->aux_out || (aligned16s(g->aux_out) && g->ld_aux_out % 4 == 0), "map_gemm_bf16s: aux_out alignment");
+    MAP_REQUIRE(!g->acc_out || (aligned16s(g->acc_out) && g->ld_acc_out % 4 == 0), "map_gemm_bf16s: acc_out alignment");
+    MAP_REQUIRE(!g->colsum_out || aligned16s(g->colsum_out), "map_gemm_bf16s: colsum_out alignment");
+    MAP_REQUIRE(g->epilogue >= MAP_EPI_NONE && g->epilogue <= MAP_EPI_ADD3, "map_gemm_bf16s: unknown epilogue %d", g->epilogue);
+    if (a->c_planes != nullptr) {
+        MAP_REQUIRE(a->c_nplanes >= 1 && a->c_nplanes <= 3 && a->c_ld % 4 == 0 && ((uintptr_t)a->c_planes & 7) == 0 && a->c_plane_stride % 4 == 0,
+                    "map_gemm_bf16s: C planes need 8-byte aligned base, strides multiple of 4 elements, 1..3 planes");
+    }
+    return MAP_OK;
+}
+
+typedef void (*SKernelFn)(const SGroupArgs);
+struct SCombo {
+    int e[kSMaxGroup];  // epilogue kinds in DESCENDING order, -1 = unused slot
+    SKernelFn fn;
+};
+#define MAP_SCOMBO(a, b, c, d) {{a, b, c, d}, gemm_bf16s_kernel<a, b, c, d>}
+// the epilogue combinations the step issues (engine.py), plus every single problem
+static const SCombo kSCombos[] = {
+    MAP_SCOMBO(MAP_EPI_CROSS, MAP_EPI_BIAS_RELU, -1, -1),
+    MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, -1),
+    MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, MAP_EPI_NONE),
+    MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_NONE, -1, -1),
+    MAP_SCOMBO(MAP_EPI_ADD3, MAP_EPI_NONE, -1, -1),
+    MAP_SCOMBO(MAP_EPI_ADD3, MAP_EPI_NONE, MAP_EPI_NONE, -1),
+    MAP_SCOMBO(MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, -1, -1),
+    MAP_SCOMBO(MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, MAP_EPI_NONE, -1),
+    MAP_SCOMBO(MAP_EPI_NONE, MAP_EPI_NONE, -1, -1),
+    MAP_SCOMBO(MAP_EPI_NONE, MAP_EPI_NONE, MAP_EPI_NONE, -1),
+    MAP_SCOMBO(MAP_EPI_NONE, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_BIAS, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_BIAS_RELU, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_CROSS, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_MUL_RELUMASK, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_ADD, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_ADD_MUL, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_CROSS_BWD, -1, -1, -1),
+    MAP_SCOMBO(MAP_EPI_ADD3, -1, -1, -1),
+};
+#undef MAP_SCOMBO
+constexpr int kNumSCombos = (int)(sizeof(kSCombos) / sizeof(kSCombos[0]));
+
+static int find_scombo(const int* e, int count) {
+    for (int c = 0; c < kNumSCombos; ++c) {
+        bool ok = true;
+        for (int i = 0; i < kSMaxGroup; ++i) ok = ok && kSCombos[c].e[i] == (i < count ? e[i] : -1);
+        if (ok) return c;
+    }
+    return -1;
+}
+
+// pair-tile width: the widest BLOCK_N that wastes the fewest padded columns.  K-major B: any multiple of 16 in [128, 256];
+// MN-major B: whole 64-column chunks per CTA half -> 128 or 256.
+static int choose_block_n(int N, bool mn_major_b) {
+    if (mn_major_b) {
+        const int c128 = (int)ceil_div(N, 128) * 128, c256 = (int)ceil_div(N, 256) * 256;
+        return (c256 <= c128) ? 256 : 128;
+    }
+    if (N < 128) return (int)ceil_div(N, 16) * 16;
+    int best = 256, best_cols = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= 16) {
+        const int cols = (int)ceil_div(N, bn) * bn;
+        if (cols < best_cols) {
+            best_cols = cols;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+static unsigned long long* g_strace_buf = nullptr;
+static int64_t g_strace_words = 0;
+
+static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo, cudaStream_t st) {
+    SGroupArgs ga{};
+    ga.count = count;
+    int total = 0, stage_bytes = 0;
+    for (int i = 0; i < count; ++i) {
+        const map_gemm_split_args* a = &sorted[i];
+        const map_gemm_args* g = &a->g;
+        SProblem& pr = ga.pr[i];
+        GemmParams& p = pr.p;
+        p.M = g->M; p.N = g->N; p.K = g->K;
+        p.trans_a = g->trans_a ? 1 : 0;
+        p.trans_b = g->trans_b ? 1 : 0;
+        p.block_n = choose_block_n(g->N, p.trans_b != 0);
+        if (const char* e = getenv("MAP_B200_BLOCK_N")) {  // tuning override
+            const int bn = atoi(e);
+            if (bn >= 16 && bn <= 256 && bn % (p.trans_b ? 128 : 16) == 0) p.block_n = bn;
+        }
+        pr.half_n = p.block_n / 2;
+        pr.terms = a->terms;
+        pr.pa = pr.pb = (a->terms == 6) ? 3 : 2;
+        p.epilogue = g->epilogue;
+        p.C = g->C; p.ldc = g->ldc;
+        p.bias = g->bias;
+        p.aux0 = g->aux0; p.ld_aux0 = g->ld_aux0;
+        p.aux1 = g->aux1; p.ld_aux1 = g->ld_aux1;
+        p.aux_out = g->aux_out; p.ld_aux_out = g->ld_aux_out;
+        p.aux2 = g->aux2; p.ld_aux2 = g->ld_aux2;
+        p.acc_out = g->acc_out; p.ld_acc_out = g->ld_acc_out;
+        p.acc_accumulate = g->acc_accumulate;
+        p.colsum_out = g->colsum_out;
+        p.corr_cols = (a->terms == 6) ? kSAccCols : 0;
+        p.c_planes = reinterpret_cast<__nv_bfloat16*>(a->c_planes);
+        p.ld_cp = a->c_ld; p.cp_stride = a->c_plane_stride; p.pc = a->c_planes ? a->c_nplanes : 0;
+        p.b_tile_bytes = p.trans_b ? (pr.half_n / 64) * kSChunk : pr.half_n * 128;
+        p.b_tile_bytes = (p.b_tile_bytes + 1023) & ~1023;   // planes start on swizzle-pattern boundaries
+        const int sb = pr.pa * kSPlaneA + pr.pb * p.b_tile_bytes;
+        if (sb > stage_bytes) stage_bytes = sb;
+        p.tmem_cols = kSAccCols;
+        p.k_blocks_total = (int)ceil_div(g->K, kSBlockK);
+        // split-K (plain outputs only): a CTA pair's share of a long reduction (wgrad, K = batch) is ~16 k-blocks, like a dgrad tile
+        int split = 1;
+        const bool allow_split = g->epilogue == MAP_EPI_NONE && g->colsum_out == nullptr && a->c_planes == nullptr;
+        if (allow_split && p.k_blocks_total >= 32) {
+            split = (p.k_blocks_total + 8) / 16;
+            if (split > 16) split = 16;
+        }
+        if (const char* e = getenv("MAP_B200_SPLITK")) {
+            const int sk = atoi(e);
+            if (allow_split && sk >= 1 && sk <= 64) split = sk;
+        }
+        p.num_k_blocks = (int)ceil_div(p.k_blocks_total, split);
+        p.split_k = (int)ceil_div(p.k_blocks_total, p.num_k_blocks);
+        p.trace = nullptr;
+        pr.m_pairs = (int)ceil_div(g->M, 2 * kBlockM);
+        pr.n_tiles = (int)ceil_div(g->N, p.block_n);
+        total += pr.m_pairs * pr.n_tiles * p.split_k;
+        pr.tile_end = total;
+        int rc;
+        // A planes: K-major [M rows][K contiguous] box {64, 128}; MN-major [K rows][M contiguous] box {64, 64}
+        if (!p.trans_a) rc = make_tmap_planes(&ga.tmap[2 * i], a->a_planes, g->K, g->M, a->a_ld, a->a_plane_stride, pr.pa, kBlockM);
+        else rc = make_tmap_planes(&ga.tmap[2 * i], a->a_planes, g->M, g->K, a->a_ld, a->a_plane_stride, pr.pa, kSBlockK);
+        if (rc != MAP_OK) return rc;
+        if (!p.trans_b) rc = make_tmap_planes(&ga.tmap[2 * i + 1], a->b_planes, g->K, g->N, a->b_ld, a->b_plane_stride, pr.pb, pr.half_n);
+        else rc = make_tmap_planes(&ga.tmap[2 * i + 1], a->b_planes, g->N, g->K, a->b_ld, a->b_plane_stride, pr.pb, kSBlockK);
+        if (rc != MAP_OK) return rc;
+        if (p.split_k > 1) {
+            if (cudaMemset2DAsync(g->C, (size_t)g->ldc * sizeof(float), 0, (size_t)g->N * sizeof(float), (size_t)g->M, st) != cudaSuccess) {
+                set_error("map_gemm_bf16s: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return MAP_ECUDA;
+            }
+        }
+    }
+    for (int i = count; i < kSMaxGroup; ++i) ga.pr[i].tile_end = total;
+    ga.total_tiles = total;
+    ga.stage_bytes = stage_bytes;
+    int stages = (kSSmemBudget - 1024 - kSStagingBytes) / stage_bytes;
+    if (stages > kSMaxStages) stages = kSMaxStages;
+    if (const char* e = getenv("MAP_B200_STAGES")) {
+        const int s_ = atoi(e);
+        if (s_ >= 1 && s_ <= stages) stages = s_;
+    }
+    MAP_REQUIRE(stages >= 2, "map_gemm_bf16s: stage of %d bytes does not fit twice in shared memory", stage_bytes);
+    ga.stages = stages;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + kSStagingBytes + 1024;
+    const SKernelFn fn = kSCombos[combo].fn;
+    static bool attr_set[kNumSCombos] = {};
+    if (!attr_set[combo]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmemBudget) != cudaSuccess) {
+            set_error("map_gemm_bf16s: cannot raise dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+            return MAP_ECUDA;
+        }
+        attr_set[combo] = true;
+    }
+    int clusters = kNumSMs / 2;
+    if (const char* e = getenv("MAP_B200_GEMM_CLUSTERS")) {
+        const int c = atoi(e);
+        if (c >= 1 && c <= kNumSMs / 2) clusters = c;
+    }
+    if (clusters > total) clusters = total;
+    ga.trace = ((int64_t)2 * clusters * kSTraceWords <= g_strace_words) ? g_strace_buf : nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, fn, ga);
+    if (le != cudaSuccess) {
+        set_error("map_gemm_bf16s: launch failed: %s", cudaGetErrorString(le));
+        cudaGetLastError();
+        return MAP_ECUDA;
+    }
+    return check_launch("map_gemm_bf16s_group");
+}
+
+}  // namespace mapb
+
+extern "C" int map_gemm_bf16s_set_trace(unsigned long long* dev_buf, int64_t capacity_u64) {
+    mapb::g_strace_buf = dev_buf;
+    mapb::g_strace_words = dev_buf ? capacity_u64 : 0;
+    return MAP_OK;
+}
+
+extern "C" int map_split_bf16(const float* src, int64_t ld, int64_t rows, int64_t cols, uint16_t* planes, int64_t ld_p, int64_t plane_stride,
+                              int n_planes, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(src && planes && rows > 0 && cols > 0 && n_planes >= 1 && n_planes <= 3, "map_split_bf16: bad argument");
+    MAP_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && ld_p % 4 == 0 && plane_stride % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)planes & 7) == 0,
+                "map_split_bf16: cols / strides must be multiples of 4 elements, src 16-byte and planes 8-byte aligned");
+    const int64_t total = rows * (cols / 4);
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, ld, rows, cols / 4, reinterpret_cast<__nv_bfloat16*>(planes), ld_p,
+                                                                        plane_stride, n_planes);
+    return check_launch("map_split_bf16");
+}
+
+extern "C" int map_gemm_bf16s_group(const map_gemm_split_args* args, int count, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(args != nullptr && count >= 1 && count <= kSMaxGroup, "map_gemm_bf16s_group: count=%d must be in [1, %d]", count, kSMaxGroup);
+    cudaStream_t st = as_stream(stream);
+    for (int i = 0; i < count; ++i) {
+        const int rc = bf16s_check(&args[i]);
+        if (rc != MAP_OK) return rc;
+    }
+    // canonical order: epilogue kind descending (stable), which is how the instantiated combinations are listed
+    map_gemm_split_args sorted[kSMaxGroup];
+    for (int i = 0; i < count; ++i) sorted[i] = args[i];
+    for (int i = 1; i < count; ++i)
+        for (int j = i; j > 0 && sorted[j].g.epilogue > sorted[j - 1].g.epilogue; --j) {
+            const map_gemm_split_args tmp = sorted[j]; sorted[j] = sorted[j - 1]; sorted[j - 1] = tmp;
+        }
+    // greedy cover: the longest prefix of what is left that is an instantiated combination goes out as one launch
+    int pos = 0;
+    while (pos < count) {
+        int e[kSMaxGroup], len = 0, combo = -1;
+        for (int n = count - pos; n >= 1 && combo < 0; --n) {
+            for (int i = 0; i < n; ++i) e[i] = sorted[pos + i].g.epilogue;
+            combo = find_scombo(e, n);
+            len = n;
+        }
+        MAP_REQUIRE(combo >= 0, "map_gemm_bf16s_group: no kernel for epilogue %d", sorted[pos].g.epilogue);
+        const int rc = launch_sgroup(&sorted[pos], len, combo, st);
+        if (rc != MAP_OK) return rc;
+        pos += len;
+    }
+    return MAP_OK;
+}

@@ -171,6 +171,7 @@ class CollectiveShardedFusedStep(FusedStep):
         t = self.tables["embed.embedding.weight"]
         self._draw_noise()
         self.xch.embed_forward(self.embed_w.data, ids, self.ids_g, self.rows_g, self.X0.view(self.B * self.F, self.D))
+        self._split(self.X0, self.X0p)
         self.xch.local_keys(self.ids_g, self.embed_w.shape[0] - 1, self.keys_emb)
         t.plan.run(self.keys_emb)
 
@@ -521,6 +522,7 @@ class ShardedFusedStep(FusedStep):
                 if mfp:
                     self._merge_keys(te)
         ops.emb_gather_sharded(t.shard.ptrs, self.world, t.V_full, self.D, ids, out=self.X0)
+        self._split(self.X0, self.X0p)
 
     def _embed_backward(self):
         self._join("keys")

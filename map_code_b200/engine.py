@@ -69,6 +69,11 @@ class FusedStep:
         self.name = model.model_name.lower()
         if self.name not in ("dcnv2", "dnn", "deepfm"):
             raise NotImplementedError(f"FusedStep: backbone {model.model_name}")
+        if str(getattr(cfg, "hidden_act", "relu")).lower() != "relu" or float(getattr(cfg, "hidden_dropout_rate", 0.0)) != 0.0 \
+                or float(getattr(cfg, "embed_dropout_rate", 0.0)) != 0.0 or bool(getattr(cfg, "embed_norm", False)):
+            # the fused schedule hard-wires the reference defaults (arguments.py:109-124): ReLU towers, no dropout, no embedding
+            # LayerNorm; anything else must not silently compute a different model
+            raise NotImplementedError("FusedStep supports hidden_act='relu', dropout 0 and embed_norm=False (the reference defaults)")
         self.B, self.F, self.D = batch_size, cfg.num_fields, cfg.embed_size
         self.V = cfg.input_size
         self.in_dim = self.F * self.D
@@ -85,7 +90,13 @@ class FusedStep:
         self.sched = _lib.SCHED_COSINE if sched.lower() == "cosine" else _lib.SCHED_CONST
         self.warmup_steps, self.total_steps = warmup_steps, total_steps
         self.use_graph = use_graph
-        self.gemm_backend = gemm_backend
+        self.gemm_backend = ops._norm_backend(gemm_backend)
+        # split-bf16 backend: every GEMM operand is kept as bf16 planes next to its fp32 master (csrc/gemm_bf16s.cu)
+        self.use_planes = self.gemm_backend == "bf16s"
+        import os as _os
+        # CrossNet forward: linear in its operands (no ReLU behind it in MFP / CTR; in RFD its output reaches pred_rfd's ReLU only
+        # through one more GEMM) -> terms = 3 keeps every gradient within 4e-4 of fp32 (tests/test_fullshape_gpu.py)
+        self.cross_terms = int(_os.environ.get("MAP_B200_CROSS_TERMS", "3"))
         self.x_train, self.idx_low, self.idx_high = x_train, idx_low, idx_high
         if self.mode == "RFD" and self.rfd_mode in ("Unigram", "Whole-Unigram") and x_train is None:
             raise ValueError("RFD Unigram replacement needs the training id matrix on the device (x_train)")
@@ -130,7 +141,7 @@ class FusedStep:
         self.cross_off, self.cross_w = 0, (self.in_dim if self.name == "dcnv2" else 0)
         self.mlp_off = self.cross_w
         self.final_dim = self.cross_w + self.H + (1 if (self.has_fm and cfg.pretrain) else 0)
-        self.ld_final = (self.final_dim + 3) // 4 * 4  # TMA rows must be 16-byte multiples
+        self.ld_final = (self.final_dim + 7) // 8 * 8  # TMA rows must be 16-byte multiples (fp32 masters and bf16 planes)
         self.fm_col = self.H  # column of `final` that holds lr_fm in DeepFM pretraining (models.py:224)
         if self.has_fm:
             self.lr_w = m.lr_layer.embed_w.weight
@@ -171,14 +182,24 @@ class FusedStep:
         self.cross_out = self.final[:, self.cross_off:self.cross_off + self.cross_w] if nc else None
         self.mlp_out = self.final[:, self.mlp_off:self.mlp_off + self.H] if nh else None
         self.final_v = self.final[:, :self.final_dim]
+        # bf16 planes of the activations / gradients that GEMMs consume (written by the producing kernel)
+        PL = (lambda n, rows, cols: ops.alloc_planes(rows, cols, n, dev)) if self.use_planes else (lambda n, rows, cols: None)
+        self.X0p = PL(3, B, self.in_dim)
+        self.finalp_full = PL(3, B, self.ld_final)
+        fp_ = self.finalp_full
+        self.finalp = fp_[:, :, :self.final_dim] if fp_ is not None else None
+        self.Xcp = [self.X0p] + [PL(3, B, self.in_dim) for _ in range(max(nc - 1, 0))]
+        self.Hsp = [PL(3, B, self.H) for _ in range(max(nh - 1, 0))]
+        self.cross_outp = fp_[:, :, self.cross_off:self.cross_off + self.cross_w] if (fp_ is not None and nc) else None
+        self.mlp_outp = fp_[:, :, self.mlp_off:self.mlp_off + self.H] if (fp_ is not None and nh) else None
         # RFD head: pred_rfd.2 is Linear(F*P -> F) with F = 39: not a multiple of 4 floats, so its rows of logits / gradients
         # would be unaligned for TMA.  Its weight and bias are re-pointed at the first F rows of zero-padded storage
-        # ([Fp, F*P], Fp = roundup4(F)); the padded rows stay zero for ever (their gradients are exactly zero), the
+        # ([Fp, F*P], Fp = roundup8(F)); the padded rows stay zero for ever (their gradients are exactly zero), the
         # nn.Parameter keeps its reference shape, and every GEMM of the head runs on tensor cores at N = K = Fp.
         self._pad_rows: Dict[str, int] = {}
         if self.mode == "RFD":
             l2 = getattr(self.model.pred_rfd, "2")
-            self.Fp = (F + 3) // 4 * 4
+            self.Fp = (F + 7) // 8 * 8
             if sh is not None:      # the parameters already live in the other engine's padded storage
                 self.W2p, self.b2p = sh.W2p, sh.b2p
             else:
@@ -245,13 +266,29 @@ class FusedStep:
                 self.opt_param[n] = p.data
         self.exp_avg = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense} if sh is None else sh.exp_avg
         self.exp_avg_sq = {n: torch.zeros_like(self.opt_param[n]) for n in self.dense} if sh is None else sh.exp_avg_sq
+        # bf16 planes of every 2-D dense weight (3 planes: the forward GEMMs that feed a ReLU use all of them); the fused AdamW
+        # rewrites them with every update, refresh_weight_planes() after anything else changed the parameters
+        self.wplanes: Dict[str, torch.Tensor] = {}
+        if self.use_planes:
+            self._wplanes_full: Dict[str, torch.Tensor] = {} if sh is None else sh._wplanes_full
+            for n in self.dense:
+                w = self.opt_param[n]
+                if w.dim() == 2 and w.shape[1] % 8 == 0 and w.shape[0] >= 2:
+                    if sh is None:   # row-padded weights (pred_rfd.2): planes of the whole padded storage, AdamW sees the real rows
+                        rows = self._pad_rows.get(n, w.shape[0])
+                        self._wplanes_full[n] = torch.zeros(3, rows, w.shape[1], dtype=torch.bfloat16, device=dev)
+                    self.wplanes[n] = self._wplanes_full[n][:, :w.shape[0]]
         entries = [(self.opt_param[n], self.grad_flat[offs[n]:offs[n] + self.opt_param[n].numel()].view_as(self.opt_param[n]),
-                    self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None) for n in self.dense]
+                    self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None, self.wplanes.get(n)) for n in self.dense]
         self.adam_table, self.adam_n, self.adam_max = ops.make_adamw_tensor_list(entries, dev)
+        self._param_versions = None
+        self.refresh_weight_planes()
         # backward scratch
         md = max(self.in_dim, self.H, 1)
         self.dZ = [E(B, self.H) for _ in range(nh)]          # gradient at each MLP pre-activation (kept: dW reads it later)
         self.dUs = [E(B, self.in_dim) for _ in range(nc)]    # dU of each cross layer
+        self.dZp = [PL(2, B, self.H) for _ in range(nh)]
+        self.dUsp = [PL(2, B, self.in_dim) for _ in range(nc)]
         self.Gc = [E(B, self.in_dim) for _ in range(nc + 1)] # d(loss)/d(X_i) through the cross chain
         self.dX0_acc = E(B, self.in_dim) if nc else None
         self.dX0_mlp = E(B, self.in_dim) if nh else None
@@ -275,6 +312,7 @@ class FusedStep:
             self.labels = torch.empty(B, L, **i64)
             self.enc = E(B, F * P)
             self.d_enc = torch.zeros(B, F * P, **f32)
+            self.d_encp = PL(2, B, F * P)
             self.sel = E(max(N, 1), P)
             self.noise = torch.empty(max(N, 1), K, **i64)
             self.logits = E(max(N, 1), K + 1)
@@ -296,6 +334,7 @@ class FusedStep:
             self.d_logits = E(B, F)
             self.d_logits_p = torch.zeros(B, self.Fp, **f32)
             self.d_h = E(B, F * P)
+            self.rfd_hp, self.d_hp, self.d_logits_pp = PL(3, B, F * P), PL(2, B, F * P), PL(2, B, self.Fp)
         else:
             self.ctr_logits = E(B, 1)
             self.d_logits = E(B, 1)
@@ -337,6 +376,21 @@ class FusedStep:
                 return int(parts[prefix.count(".")]) // div
         return 99
 
+    def refresh_weight_planes(self):
+        """Re-derives the bf16 planes of the dense weights from their fp32 masters.  The fused AdamW keeps them current; call this
+        after anything else wrote the parameters (load_state_dict is detected by step(); raw .data writes are not)."""
+        if self.use_planes:
+            for n, pl in self.wplanes.items():
+                ops.split_planes(self.opt_param[n], pl)
+        self._param_versions = {n: p._version for n, p in self.dense.items()}
+
+    def _wp(self, name: str, cols=None):
+        """bf16 planes of a dense weight (optionally a column slice), None when the backend does not use planes"""
+        if not self.use_planes or name not in self.wplanes:
+            return None
+        pl = self._wplanes_full[name]
+        return pl if cols is None else pl[:, :, cols[0]:cols[1]]
+
     def _gemm(self, *a, **k):
         return ops.gemm(*a, backend=self.gemm_backend, **k)
 
@@ -346,12 +400,13 @@ class FusedStep:
         if problems:
             ops.gemm_group(problems, backend=self.gemm_backend)
 
-    def _wgrad_problem(self, dZ, X_in, layer_name, M, N, K):
+    def _wgrad_problem(self, dZ, X_in, layer_name, M, N, K, dZp=None, X_inp=None):
         """dW = dZ^T X as a problem of a grouped launch (the bias gradient comes from the colsum_out of the GEMM that wrote dZ)"""
         wname = layer_name + ".weight"
         if wname in self._pad_cols:  # column-padded head weight: compute on the aligned [N, ld_final] storage
-            return dict(A=dZ, B=self.final, C_out=self.grads_padded[wname], M=N, N=self.ld_final, K=M, trans_a=True, trans_b=True)
-        return dict(A=dZ, B=X_in, C_out=self.grads[wname], M=N, N=K, K=M, trans_a=True, trans_b=True)
+            return dict(A=dZ, B=self.final, C_out=self.grads_padded[wname], M=N, N=self.ld_final, K=M, trans_a=True, trans_b=True,
+                        Ap=dZp, Bp=self.finalp_full)
+        return dict(A=dZ, B=X_in, C_out=self.grads[wname], M=N, N=K, K=M, trans_a=True, trans_b=True, Ap=dZp, Bp=X_inp)
 
     def _on(self, name):
         """context: issue on side stream `name` (or stay on the main stream when multi_stream is off)"""
@@ -374,7 +429,7 @@ class FusedStep:
             ev.record(self.streams[name])
             torch.cuda.current_stream().wait_event(ev)
 
-    def _wgrad(self, dZ, X_in, layer_name, M, N, K, bias_done=False):
+    def _wgrad(self, dZ, X_in, layer_name, M, N, K, bias_done=False, dZp=None, X_inp=None):
         """dW = dZ^T X, db = colsum(dZ) for a Linear with input X_in [M,K] and pre-activation gradient dZ [M,N].
         Issued on the 'dw' stream: weight gradients are off the critical path (only the optimizer waits for them).
         bias_done: the GEMM that produced dZ already accumulated its column sums into the bias gradient (colsum_out)."""
@@ -382,9 +437,9 @@ class FusedStep:
         with self._on("dw"):
             wname = layer_name + ".weight"
             if wname in self._pad_cols:  # column-padded head weight: compute on the aligned [N, ld_final] storage
-                self._gemm(dZ, self.final, self.grads_padded[wname], N, self.ld_final, M, trans_a=True, trans_b=True)
+                self._gemm(dZ, self.final, self.grads_padded[wname], N, self.ld_final, M, trans_a=True, trans_b=True, Ap=dZp, Bp=self.finalp_full)
             else:
-                self._gemm(dZ, X_in, self.grads[wname], N, K, M, trans_a=True, trans_b=True)
+                self._gemm(dZ, X_in, self.grads[wname], N, K, M, trans_a=True, trans_b=True, Ap=dZp, Bp=X_inp)
             if not bias_done:
                 ops.colsum(dZ, out=self.grads[layer_name + ".bias"], ws=self.colsum_ws)
 
@@ -426,6 +481,11 @@ class FusedStep:
                 ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
                 self.tables["mfp_criterion.emb.weight"].plan.run(self.ids_all.view(-1))
         ops.emb_gather(self.embed_w.data, ids, out=self.X0)
+        self._split(self.X0, self.X0p)
+
+    def _split(self, t, planes):
+        if planes is not None:
+            ops.split_planes(t, planes)
 
     def _draw_noise(self):
         if self.mode != "MFP":
@@ -453,30 +513,38 @@ class FusedStep:
         if self.has_fm:  # lr_fm = LR(ids) + FM2(E): written straight into its column of `final` (pretrain) or kept apart (CTR)
             if self.cfg.pretrain:
                 self._lr_fm_forward(ids, self.final[:, self.fm_col:], self.ld_final)
+                if self.use_planes:   # the lr_fm column (+ its zero padding) of `final` as planes
+                    self._split(self.final[:, self.fm_col:self.fm_col + 4], self.finalp_full[:, :, self.fm_col:self.fm_col + 4])
             else:
                 self._lr_fm_forward(ids, self.lr_fm, 1)
         nh, nc = len(self.mlp), len(self.cross)
         # CrossNet layer i (layers.py:197-201, product fused in the epilogue) and MLP layer i (layers.py:187-188, ReLU fused) only
         # depend on layer i-1 of their own tower: one grouped launch per depth
-        x, k = self.X0, in_dim
+        pref_c = "cross_net.cross_layers"
+        pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
+        # GEMMs whose output goes through a ReLU run with terms = 6 (fp32-level products): the gradient is a discontinuous
+        # function of those pre-activations (csrc/gemm_bf16s.cu); everything linear runs with terms = 3.
+        x, k, xp = self.X0, in_dim, self.X0p
         for i in range(max(nh, nc)):
             probs = []
             if i < nc:
-                out = self.cross_out if i == nc - 1 else self.Xc[i + 1]
+                out, outp = (self.cross_out, self.cross_outp) if i == nc - 1 else (self.Xc[i + 1], self.Xcp[i + 1])
                 layer = self.cross[i]
                 probs.append(dict(A=self.Xc[i], B=layer.weight.data, C_out=out, M=B, N=in_dim, K=in_dim, epilogue=_lib.EPI_CROSS,
-                                  bias=layer.bias.data, aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i]))
+                                  bias=layer.bias.data, aux0=self.Xc[i], aux1=self.X0, aux_out=self.U[i],
+                                  Ap=self.Xcp[i], Bp=self._wp(f"{pref_c}.{i}.weight"), Cp=outp, terms=self.cross_terms))
             if i < nh:
-                out = self.mlp_out if i == nh - 1 else self.Hs[i]
+                out, outp = (self.mlp_out, self.mlp_outp) if i == nh - 1 else (self.Hs[i], self.Hsp[i])
                 layer = self.mlp[i]
-                probs.append(dict(A=x, B=layer.weight.data, C_out=out, M=B, N=H, K=k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data))
-                x, k = out, H
+                probs.append(dict(A=x, B=layer.weight.data, C_out=out, M=B, N=H, K=k, epilogue=_lib.EPI_BIAS_RELU, bias=layer.bias.data,
+                                  Ap=xp, Bp=self._wp(f"{pref_m}.{3 * i}.weight"), Cp=outp, terms=6))
+                x, k, xp = out, H, outp
             self._gemm_group(probs)
 
     def _lr_fm_forward(self, ids, out, ld_out):
         ops.fm_lr_fwd(self.X0.view(self.B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=out, ld_out=ld_out)
 
-    def _backward_backbone(self, head_W, dHead, n_head, head_wgrad=None):
+    def _backward_backbone(self, head_W, dHead, n_head, head_wgrad=None, head_Wname=None, dHeadp=None):
         """head_W [n_head, final_dim] is the weight of the first head layer, dHead [B, n_head] the gradient at its
         pre-activation, head_wgrad the (optional) weight-gradient problem of that layer: it consumes dHead like the two
         tower dgrads and goes out in the same grouped launch.  Propagates into the towers and the embedding table.
@@ -490,13 +558,16 @@ class FusedStep:
         pref_c = "cross_net.cross_layers"
         pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
         probs = [head_wgrad]
+        hw = (lambda lo, hi: self._wp(head_Wname, (lo, hi))) if head_Wname is not None else (lambda lo, hi: None)
         if nh:
             probs.append(dict(A=dHead, B=head_W[:, self.mlp_off:self.mlp_off + H], C_out=self.dZ[nh - 1], M=B, N=H, K=n_head, trans_b=True,
-                              epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out, colsum_out=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"]))
+                              epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out, colsum_out=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"],
+                              Ap=dHeadp, Bp=hw(self.mlp_off, self.mlp_off + H), Cp=self.dZp[nh - 1]))
         if nc:
             probs.append(dict(A=dHead, B=head_W[:, self.cross_off:self.cross_off + in_dim], C_out=self.dUs[nc - 1], M=B, N=in_dim, K=n_head,
                               trans_b=True, epilogue=_lib.EPI_CROSS_BWD, aux0=None, aux1=self.X0, aux2=self.U[nc - 1], aux_out=self.Gc[nc],
-                              acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"]))
+                              acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"],
+                              Ap=dHeadp, Bp=hw(self.cross_off, self.cross_off + in_dim), Cp=self.dUsp[nc - 1]))
         self._gemm_group(probs)
         last = []   # the final level: dE needs dX0_mlp, which the last MLP dgrad of the loop below produces
         for s_ in range(max(nc, nh)):
@@ -504,27 +575,32 @@ class FusedStep:
             probs = []
             if ic >= 0:
                 layer = self.cross[ic]
-                wg = self._wgrad_problem(self.dUs[ic], self.Xc[ic], f"{pref_c}.{ic}", B, in_dim, in_dim)
+                wname = f"{pref_c}.{ic}.weight"
+                wg = self._wgrad_problem(self.dUs[ic], self.Xc[ic], f"{pref_c}.{ic}", B, in_dim, in_dim, dZp=self.dUsp[ic], X_inp=self.Xcp[ic])
                 if ic > 0:
                     probs.append(wg)
                     probs.append(dict(A=self.dUs[ic], B=layer.weight.data, C_out=self.dUs[ic - 1], M=B, N=in_dim, K=in_dim, trans_b=True,
                                       epilogue=_lib.EPI_CROSS_BWD, aux0=self.Gc[ic + 1], aux1=self.X0, aux2=self.U[ic - 1], aux_out=self.Gc[ic],
-                                      acc_out=self.dX0_acc, acc_accumulate=True, colsum_out=self.grads[f"{pref_c}.{ic - 1}.bias"]))
+                                      acc_out=self.dX0_acc, acc_accumulate=True, colsum_out=self.grads[f"{pref_c}.{ic - 1}.bias"],
+                                      Ap=self.dUsp[ic], Bp=self._wp(wname), Cp=self.dUsp[ic - 1]))
                 else:
                     last.append(wg)
                     last.append(dict(A=self.dUs[0], B=layer.weight.data, C_out=self.dE, M=B, N=in_dim, K=in_dim, trans_b=True,
-                                     epilogue=_lib.EPI_ADD3, aux0=self.Gc[1], aux1=self.dX0_acc, aux2=self.dX0_mlp if nh else None))
+                                     epilogue=_lib.EPI_ADD3, aux0=self.Gc[1], aux1=self.dX0_acc, aux2=self.dX0_mlp if nh else None,
+                                     Ap=self.dUsp[0], Bp=self._wp(wname)))
             if im >= 0:
                 layer = self.mlp[im]
-                dZ = self.dZ[im]
-                x_in = self.X0 if im == 0 else self.Hs[im - 1]
+                dZ, dZp = self.dZ[im], self.dZp[im]
+                x_in, x_inp = (self.X0, self.X0p) if im == 0 else (self.Hs[im - 1], self.Hsp[im - 1])
                 k_in = in_dim if im == 0 else H
-                probs.append(self._wgrad_problem(dZ, x_in, f"{pref_m}.{3 * im}", B, H, k_in))
+                wname = f"{pref_m}.{3 * im}.weight"
+                probs.append(self._wgrad_problem(dZ, x_in, f"{pref_m}.{3 * im}", B, H, k_in, dZp=dZp, X_inp=x_inp))
                 if im > 0:
                     probs.append(dict(A=dZ, B=layer.weight.data, C_out=self.dZ[im - 1], M=B, N=k_in, K=H, trans_b=True,
-                                      epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.Hs[im - 1], colsum_out=self.grads[f"{pref_m}.{3 * (im - 1)}.bias"]))
+                                      epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.Hs[im - 1], colsum_out=self.grads[f"{pref_m}.{3 * (im - 1)}.bias"],
+                                      Ap=dZp, Bp=self._wp(wname), Cp=self.dZp[im - 1]))
                 else:
-                    probs.append(dict(A=dZ, B=layer.weight.data, C_out=self.dX0_mlp, M=B, N=k_in, K=H, trans_b=True))
+                    probs.append(dict(A=dZ, B=layer.weight.data, C_out=self.dX0_mlp, M=B, N=k_in, K=H, trans_b=True, Ap=dZp, Bp=self._wp(wname)))
             self._gemm_group(probs)
         if nc:
             self._gemm_group(last)
@@ -568,39 +644,49 @@ class FusedStep:
         m = self.model
         enc_W, enc_b = m.feat_encoder.weight.data, m.feat_encoder.bias.data
         crit = m.mfp_criterion
-        self._gemm_group([dict(A=self.final_v, B=enc_W, C_out=self.enc, M=B, N=F * P, K=self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b)])   # models.py:74
+        self._gemm_group([dict(A=self.final_v, B=enc_W, C_out=self.enc, M=B, N=F * P, K=self.final_dim, epilogue=_lib.EPI_BIAS, bias=enc_b,
+                               Ap=self.finalp, Bp=self._wp("feat_encoder.weight", (0, self.final_dim)))])   # models.py:74
         ops.gather_slices(self.enc, self.mi, F, P, out=self.sel)                                                   # models.py:75
         self._join("tab")  # noise drawn on the 'tab' stream
         self._nce_core()
         # ---- backward of the encoder (d_enc was zeroed on the 'tab' stream at the start of the step)
         ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
+        self._split(self.d_enc, self.d_encp)
         self._fork("dw")
         with self._on("dw"):   # bias gradient of the encoder: off the critical path
             ops.colsum(self.d_enc, out=self.grads["feat_encoder.bias"], ws=self.colsum_ws)
-        self._backward_backbone(enc_W, self.d_enc, F * P, head_wgrad=self._wgrad_problem(self.d_enc, self.final_v, "feat_encoder", B, F * P, self.final_dim))
+        self._backward_backbone(enc_W, self.d_enc, F * P, head_Wname="feat_encoder.weight", dHeadp=self.d_encp,
+                                head_wgrad=self._wgrad_problem(self.d_enc, self.final_v, "feat_encoder", B, F * P, self.final_dim,
+                                                               dZp=self.d_encp, X_inp=self.finalp))
 
     def _head_rfd(self):
         cfg, B, F, Fp = self.cfg, self.B, self.F, self.Fp
         P = cfg.proj_size
         l0 = getattr(self.model.pred_rfd, "0")
+        w2p = self._wp("pred_rfd.2.weight")
         self._gemm_group([dict(A=self.final_v, B=l0.weight.data, C_out=self.rfd_h, M=B, N=F * P, K=self.final_dim, epilogue=_lib.EPI_BIAS_RELU,
-                               bias=l0.bias.data)])
-        self._gemm(self.rfd_h, self.W2p, self.rfd_logits_p, B, Fp, F * P, epilogue=_lib.EPI_BIAS, bias=self.b2p)   # models.py:80
+                               bias=l0.bias.data, Ap=self.finalp, Bp=self._wp("pred_rfd.0.weight", (0, self.final_dim)), Cp=self.rfd_hp,
+                               terms=6)])   # feeds a ReLU
+        self._gemm(self.rfd_h, self.W2p, self.rfd_logits_p, B, Fp, F * P, epilogue=_lib.EPI_BIAS, bias=self.b2p,
+                   Ap=self.rfd_hp, Bp=w2p)   # models.py:80
         ops.copy2d(self.rfd_logits_p[:, :F], self.rfd_logits)
         ops.bce_logits(self.rfd_logits.view(-1), self.labels.view(-1), stats=self.stats, dlogits=self.d_logits.view(-1), ws=self.red_ws)
         if self.global_batch != B:  # mean over the GLOBAL batch
             ops.scale_by_scalar(self.d_logits.view(-1), self._ratio(), out=self.d_logits.view(-1))
         ops.copy2d(self.d_logits, self.d_logits_p[:, :F])      # padded columns stay 0
+        self._split(self.d_logits_p, self.d_logits_pp)
         # backward
         self._fork("dw")
         with self._on("dw"):
             ops.colsum(self.d_logits_p, out=self.grads_padded["pred_rfd.2.bias"].view(-1), ws=self.colsum_ws)
         self._gemm_group([
-            dict(A=self.d_logits_p, B=self.rfd_h, C_out=self.grads_padded["pred_rfd.2.weight"], M=Fp, N=F * P, K=B, trans_a=True, trans_b=True),
+            dict(A=self.d_logits_p, B=self.rfd_h, C_out=self.grads_padded["pred_rfd.2.weight"], M=Fp, N=F * P, K=B, trans_a=True, trans_b=True,
+                 Ap=self.d_logits_pp, Bp=self.rfd_hp),
             dict(A=self.d_logits_p, B=self.W2p, C_out=self.d_h, M=B, N=F * P, K=Fp, trans_b=True, epilogue=_lib.EPI_MUL_RELUMASK,
-                 aux0=self.rfd_h, colsum_out=self.grads["pred_rfd.0.bias"])])
-        self._backward_backbone(l0.weight.data, self.d_h, F * P,
-                                head_wgrad=self._wgrad_problem(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim))
+                 aux0=self.rfd_h, colsum_out=self.grads["pred_rfd.0.bias"], Ap=self.d_logits_pp, Bp=w2p, Cp=self.d_hp)])
+        self._backward_backbone(l0.weight.data, self.d_h, F * P, head_Wname="pred_rfd.0.weight", dHeadp=self.d_hp,
+                                head_wgrad=self._wgrad_problem(self.d_h, self.final_v, "pred_rfd.0", B, F * P, self.final_dim,
+                                                               dZp=self.d_hp, X_inp=self.finalp))
 
     def _head_ctr(self):
         B = self.B
@@ -719,9 +805,12 @@ class FusedStep:
     def _restore(self, snap):
         for t, s in snap:
             t.copy_(s)
+        self.refresh_weight_planes()
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None):
         """One training step on a device-resident batch [B, F] (int64).  No host synchronisation."""
+        if self.use_planes and any(p._version != self._param_versions[n] for n, p in self.dense.items()):
+            self.refresh_weight_planes()   # load_state_dict & co. since the last step
         self.in_ids.copy_(input_ids, non_blocking=True)
         if self.mode == "CTR":
             self.in_labels.copy_(labels.to(torch.float32), non_blocking=True)

@@ -94,7 +94,7 @@ class LinearFn(torch.autograd.Function):
         N = weight.shape[0]
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
         epi = _lib.EPI_BIAS_RELU if relu else (_lib.EPI_BIAS if bias is not None else _lib.EPI_NONE)
-        ops.gemm(x2, weight, y, M, N, K, epilogue=epi, bias=bias)
+        ops.gemm(x2, weight, y, M, N, K, epilogue=epi, bias=bias, terms=6 if relu else 3)   # a ReLU follows: fp32-level products
         ctx.relu = relu
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x2, weight, y if relu else None)

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, call
+from ._lib import GemmArgs, GemmSplitArgs, call
 
 
 def _stream() -> int:
@@ -144,15 +144,24 @@ def adamw_hyper_set(hyper, lr, beta1, beta2, eps, step: int):
 
 
 def make_adamw_tensor_list(entries, device) -> Tuple[torch.Tensor, int, int]:
-    """entries: list of (p, g, m, v, weight_decay, p_t or None).  Returns (device descriptor table, n, max_elems)."""
+    """entries: list of (p, g, m, v, weight_decay, p_t or None[, planes or None]).  `planes` [n_planes, *p.shape] bf16: the update
+    rewrites the parameter's bf16 planes (operands of the split-bf16 GEMMs).  Returns (device descriptor table, n, max_elems)."""
     arr = (_lib.AdamwTensor * len(entries))()
     mx = 1
-    for i, (p, g, m, v, wd, p_t) in enumerate(entries):
+    for i, ent in enumerate(entries):
+        p, g, m, v, wd, p_t = ent[:6]
+        planes = ent[6] if len(ent) > 6 else None
         for t in (p, g, m, v):
             _check(t, torch.float32, "adamw tensor")
         rows, cols = (p.shape[0], p.shape[1]) if (p_t is not None) else (0, 0)
+        n_pl, pl_ptr, pl_stride = 0, None, 0
+        if planes is not None:
+            _check(planes, torch.bfloat16, "adamw planes", contiguous=False)
+            if tuple(planes.shape[1:]) != tuple(p.shape) or p.numel() % 4 != 0 or not planes[0].is_contiguous():
+                raise ValueError("adamw planes must be [n_planes, *p.shape] with contiguous planes and p.numel() % 4 == 0")
+            n_pl, pl_ptr, pl_stride = planes.shape[0], planes.data_ptr(), planes.stride(0)
         arr[i] = _lib.AdamwTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_t), p.numel(), rows, cols,
-                                  float(wd), 0)
+                                  float(wd), n_pl, pl_ptr, pl_stride)
         mx = max(mx, p.numel())
     raw = bytes(arr)
     table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
@@ -380,8 +389,17 @@ def fm_lr_bwd(feat_embed, g, ld_g: int, d_embed, d_w_occ=None, accumulate=False)
 
 # ------------------------------------------------------------------------------------------------ GEMM
 def gemm_backend() -> str:
-    """'tcgen05' (default: TF32 tensor cores) or 'simt' (exact fp32 on CUDA cores; MAP_B200_GEMM=simt, used by tests)."""
-    return os.environ.get("MAP_B200_GEMM", "tcgen05")
+    """'bf16s' (default): split-bf16 tensor-core GEMM with fp32-level accuracy (gemm_bf16s.cu);
+    'tf32': single-pass TF32 tensor cores (gemm_tcgen05.cu; faster, ~1e-3 biased per product — does NOT meet the gradient
+    tolerance of north_star on this ReLU network, kept for A/B measurements);
+    'simt': exact fp32 on CUDA cores (tests).  MAP_B200_GEMM selects; 'tcgen05' is accepted as an alias of 'tf32'."""
+    b = os.environ.get("MAP_B200_GEMM", "bf16s")
+    return "tf32" if b == "tcgen05" else b
+
+
+def _norm_backend(backend: Optional[str]) -> str:
+    backend = backend or gemm_backend()
+    return "tf32" if backend == "tcgen05" else backend
 
 
 def _ld(t: torch.Tensor) -> int:
@@ -391,12 +409,12 @@ def _ld(t: torch.Tensor) -> int:
 
 def _gemm_args(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
                epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, aux2=None, acc_out=None,
-               acc_accumulate: bool = False, colsum_out=None, g: Optional[GemmArgs] = None) -> GemmArgs:
+               acc_accumulate: bool = False, colsum_out=None, g: Optional[GemmArgs] = None, **_ignored) -> GemmArgs:
     g = GemmArgs() if g is None else g
     g.M, g.N, g.K = M, N, K
     g.trans_a, g.trans_b, g.epilogue = int(trans_a), int(trans_b), int(epilogue)
-    g.A, g.lda = A.data_ptr(), _ld(A)
-    g.B, g.ldb = B.data_ptr(), _ld(B)
+    g.A, g.lda = (A.data_ptr(), _ld(A)) if A is not None else (None, 0)
+    g.B, g.ldb = (B.data_ptr(), _ld(B)) if B is not None else (None, 0)
     g.C, g.ldc = C_out.data_ptr(), _ld(C_out)
     g.bias = _ptr(bias)
     g.aux0, g.ld_aux0 = (aux0.data_ptr(), _ld(aux0)) if aux0 is not None else (None, 0)
@@ -409,54 +427,146 @@ def _gemm_args(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N:
     return g
 
 
+# ---- bf16 planes (operand format of the split-bf16 GEMM)
+def alloc_planes(rows: int, cols: int, n_planes: int, device) -> torch.Tensor:
+    """[n_planes, rows, cols] view (bf16) of storage whose row stride is a multiple of 8 elements (16-byte TMA rows)"""
+    ld = (cols + 7) // 8 * 8
+    return torch.zeros(n_planes, rows, ld, dtype=torch.bfloat16, device=device)[:, :, :cols]
+
+
+def split_planes(src: torch.Tensor, planes: torch.Tensor) -> torch.Tensor:
+    """planes[i] <- i-th bf16 piece of the fp32 matrix `src` (hi, lo, lo2)"""
+    rows, cols = src.shape
+    assert planes.dtype == torch.bfloat16 and planes.dim() == 3 and tuple(planes.shape[1:]) == (rows, cols) and planes.stride(2) == 1
+    if cols % 4 != 0 or _ld(src) % 4 != 0:
+        raise ValueError("split_planes: cols and row stride must be multiples of 4")
+    call("map_split_bf16", src.data_ptr(), _ld(src), rows, cols, planes.data_ptr(), planes.stride(1), planes.stride(0), planes.shape[0], _stream())
+    return planes
+
+
+def _planes_of(t: torch.Tensor, n_planes: int) -> torch.Tensor:
+    """temporary planes of an fp32 matrix nobody keeps planes for (module path, tests): one extra pass over the operand"""
+    rows, cols = t.shape
+    if cols % 4 != 0 or _ld(t) % 4 != 0 or t.data_ptr() % 16 != 0:   # odd shapes: go through an aligned copy
+        cp = (cols + 3) // 4 * 4
+        tmp = torch.zeros(rows, cp, dtype=torch.float32, device=t.device)
+        copy2d(t, tmp[:, :cols])
+        pl = alloc_planes(rows, cp, n_planes, t.device)
+        split_planes(tmp, pl)
+        return pl[:, :, :cols]
+    return split_planes(t, alloc_planes(rows, cols, n_planes, t.device))
+
+
+SIMT_GEMMS = {}   # (M, N, K) -> count of GEMMs that ran on the exact-fp32 CUDA-core kernel although a tensor-core backend was selected
+
+
+def bf16s_supported(pr) -> bool:
+    """shapes the split-bf16 kernel takes: everything except skinny problems (fc_out: N = 1 or K = 1)"""
+    return pr["N"] % 4 == 0 and pr["N"] >= 8 and pr["K"] >= 8 and pr["M"] >= 2
+
+
+def _split_args(pr) -> GemmSplitArgs:
+    terms = int(pr.get("terms", 3))
+    need = 3 if terms == 6 else 2
+    a = GemmSplitArgs()
+    _gemm_args(g=a.g, **{k: v for k, v in pr.items() if k not in ("Ap", "Bp", "Cp", "terms")})
+    Ap = pr.get("Ap")
+    Bp = pr.get("Bp")
+    if Ap is None:
+        Ap = _planes_of(pr["A"], need)
+    if Bp is None:
+        Bp = _planes_of(pr["B"], need)
+    for nm, P in (("A", Ap), ("B", Bp)):
+        if P.dtype != torch.bfloat16 or P.dim() != 3 or P.stride(2) != 1 or P.shape[0] < need:
+            raise ValueError(f"gemm: planes of {nm} must be a [>= {need}, rows, cols] bf16 view with unit inner stride")
+    a.a_planes, a.a_ld, a.a_plane_stride, a.a_nplanes, a.terms = Ap.data_ptr(), Ap.stride(1), Ap.stride(0), Ap.shape[0], terms
+    a.b_planes, a.b_ld, a.b_plane_stride, a.b_nplanes = Bp.data_ptr(), Bp.stride(1), Bp.stride(0), Bp.shape[0]
+    Cp = pr.get("Cp")
+    if Cp is not None:
+        a.c_planes, a.c_ld, a.c_plane_stride, a.c_nplanes = Cp.data_ptr(), Cp.stride(1), Cp.stride(0), Cp.shape[0]
+    a._keep = (Ap, Bp, Cp)
+    return a
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, C_out: torch.Tensor, M: int, N: int, K: int, trans_a=False, trans_b=False,
          epilogue: int = _lib.EPI_NONE, bias=None, aux0=None, aux1=None, aux_out=None, aux2=None, acc_out=None,
-         acc_accumulate: bool = False, colsum_out=None, backend: Optional[str] = None):
+         acc_accumulate: bool = False, colsum_out=None, backend: Optional[str] = None, Ap=None, Bp=None, Cp=None, terms: int = 3):
     """acc[m,n] = sum_k A[m,k]*B[n,k] with storage transposes; see include/map_b200.h.  Operands are 2-D row-major views
-    (row stride = leading dimension, so column slices of wider buffers work)."""
-    g = _gemm_args(A, B, C_out, M, N, K, trans_a, trans_b, epilogue, bias, aux0, aux1, aux_out, aux2, acc_out, acc_accumulate, colsum_out)
-    backend = backend or gemm_backend()
-    lib = _lib.load()
-    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
-        _lib.CURRENT_TAG = ("gemm", M, N, K, int(trans_a), int(trans_b), int(epilogue))
-    if backend == "tcgen05" and lib.map_gemm_tf32_supported(C.byref(g)):
-        call("map_gemm_tf32_tcgen05", C.byref(g), _stream())
-    else:  # skinny / unaligned shapes (N < 16, N % 4 != 0) and the exact-fp32 test mode
-        call("map_gemm_f32_simt", C.byref(g), _stream())
+    (row stride = leading dimension, so column slices of wider buffers work).  Ap / Bp: bf16 planes of A / B if the caller
+    keeps them (otherwise they are split on the fly); Cp: planes of C to be written; terms: 3 or 6 (split-bf16 backend)."""
+    gemm_group([dict(A=A, B=B, C_out=C_out, M=M, N=N, K=K, trans_a=trans_a, trans_b=trans_b, epilogue=epilogue, bias=bias, aux0=aux0,
+                     aux1=aux1, aux_out=aux_out, aux2=aux2, acc_out=acc_out, acc_accumulate=acc_accumulate, colsum_out=colsum_out,
+                     Ap=Ap, Bp=Bp, Cp=Cp, terms=terms)], backend=backend)
     return C_out
 
 
 GEMM_GROUP_MAX = 4
 
 
-def gemm_group_enabled() -> bool:
-    """MAP_B200_GEMM_GROUP=0 issues every problem of a group as its own launch (A/B switch for the persistent kernel)."""
-    return os.environ.get("MAP_B200_GEMM_GROUP", "1") != "0"
+def _tag(*t):
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
+        _lib.CURRENT_TAG = t
+
+
+def _gemm_simt(pr, count_fallback: bool):
+    g = _gemm_args(**pr)
+    if count_fallback:
+        key = (pr["M"], pr["N"], pr["K"])
+        SIMT_GEMMS[key] = SIMT_GEMMS.get(key, 0) + 1
+    _tag("gemm", pr["M"], pr["N"], pr["K"], int(bool(pr.get("trans_a"))), int(bool(pr.get("trans_b"))), int(pr.get("epilogue", 0)))
+    call("map_gemm_f32_simt", C.byref(g), _stream())
+    if pr.get("Cp") is not None:   # consumers on the tensor-core path read planes
+        split_planes(pr["C_out"], pr["Cp"])
 
 
 def gemm_group(problems, backend: Optional[str] = None):
     """problems: list of dicts with the keyword arguments of `gemm` (A, B, C_out, M, N, K, ...), all INDEPENDENT of each other.
-    Problems the tensor-core path supports go into persistent grouped launches (map_gemm_tf32_group, <= 4 per launch); the rest
-    (skinny shapes, the exact-fp32 test backend) are issued one by one."""
-    backend = backend or gemm_backend()
+    Tensor-core backends put up to 4 problems into one grouped launch; skinny problems (N = 1 / K = 1: fc_out) run on the
+    exact-fp32 CUDA-core kernel and are COUNTED in ops.SIMT_GEMMS (bench.py reports the count: no silent fallback)."""
+    backend = _norm_backend(backend)
     lib = _lib.load()
-    grouped, single = [], []
+    problems = [pr for pr in problems if pr is not None]
+    if backend == "simt":
+        for pr in problems:
+            _gemm_simt(pr, False)
+        return
+    if backend == "bf16s":
+        grouped = []
+        for pr in problems:
+            if bf16s_supported(pr):
+                grouped.append(pr)
+            else:
+                _gemm_simt(pr, True)
+        for i in range(0, len(grouped), GEMM_GROUP_MAX):
+            chunk = grouped[i:i + GEMM_GROUP_MAX]
+            arr = (GemmSplitArgs * len(chunk))()
+            keep = []
+            for j, pr in enumerate(chunk):
+                a = _split_args(pr)
+                keep.append(a)
+                C.memmove(C.byref(arr, j * C.sizeof(GemmSplitArgs)), C.byref(a), C.sizeof(GemmSplitArgs))
+            _tag("gemm_group", *[(pr["M"], pr["N"], pr["K"], int(pr.get("terms", 3))) for pr in chunk])
+            call("map_gemm_bf16s_group", arr, len(chunk), _stream())
+        return
+    if backend != "tf32":
+        raise ValueError(f"unknown GEMM backend {backend!r}")
+    grouped = []
     for pr in problems:
         g = _gemm_args(**pr)
-        if backend == "tcgen05" and gemm_group_enabled() and lib.map_gemm_tf32_supported(C.byref(g)):
-            grouped.append(g)
+        if lib.map_gemm_tf32_supported(C.byref(g)):
+            grouped.append((g, pr))
         else:
-            single.append(pr)
+            _gemm_simt(pr, True)
     for i in range(0, len(grouped), GEMM_GROUP_MAX):
         chunk = grouped[i:i + GEMM_GROUP_MAX]
         arr = (GemmArgs * len(chunk))()
-        for j, g in enumerate(chunk):
+        for j, (g, _) in enumerate(chunk):
             C.memmove(C.byref(arr, j * C.sizeof(GemmArgs)), C.byref(g), C.sizeof(GemmArgs))
-        if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
-            _lib.CURRENT_TAG = ("gemm_group",) + tuple((g.M, g.N, g.K) for g in chunk)
+        _tag("gemm_group", *[(g.M, g.N, g.K, 1) for g, _ in chunk])
         call("map_gemm_tf32_group", arr, len(chunk), _stream())
-    for pr in single:
-        gemm(backend=backend, **pr)
+        for _, pr in chunk:
+            if pr.get("Cp") is not None:
+                split_planes(pr["C_out"], pr["Cp"])
 
 
 _colsum_ws = {}

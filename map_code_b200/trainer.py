@@ -188,13 +188,30 @@ class Trainer:
             beta1, beta2 = (float(b) for b in a.adam_betas.split(","))
             need_x = cfg.pretrain and cfg.pt_type == "RFD" and a.RFD_replace in ("Unigram", "Whole-Unigram")
             lo, hi = getattr(cfg, "idx_low", None), getattr(cfg, "idx_high", None)
-            self._fused = FusedStep(
-                self.model, batch_size=batch_size or a.per_gpu_train_batch_size, mask_ratio=a.mask_ratio,
-                sampling_method=a.sampling_method, lr=a.learning_rate, weight_decay=a.weight_decay, betas=(beta1, beta2),
-                eps=a.adam_epsilon, sched=a.lr_sched, warmup_steps=warmup_steps, total_steps=total_steps, seed=a.seed,
-                optimizer_mode=getattr(a, "optimizer_mode", "sparse"), x_train=self._train_matrix() if need_x else None,
+            if getattr(a, "max_grad_norm", 0) and a.max_grad_norm > 0:
+                # reference trainer.py:137 clips when max_grad_norm > 0 (default 0: off); the fused step has no global-norm clip
+                raise NotImplementedError("max_grad_norm > 0 is not implemented on the fused step")
+            self._fused_kw = dict(
+                mask_ratio=a.mask_ratio, sampling_method=a.sampling_method, lr=a.learning_rate, weight_decay=a.weight_decay,
+                betas=(beta1, beta2), eps=a.adam_epsilon, sched=a.lr_sched, warmup_steps=warmup_steps, total_steps=total_steps,
+                seed=a.seed, optimizer_mode=getattr(a, "optimizer_mode", "sparse"), x_train=self._train_matrix() if need_x else None,
                 idx_low=None if lo is None else lo.to(self.device), idx_high=None if hi is None else hi.to(self.device))
+            self._fused = FusedStep(self.model, batch_size=batch_size or a.per_gpu_train_batch_size, **self._fused_kw)
+            self._ragged = {}
         return self._fused
+
+    def _engine_for(self, n_rows: int) -> FusedStep:
+        """The fused step for a batch of n_rows.  The last batch of an epoch may be short (the reference's DataLoader keeps it,
+        trainer.py:51-58): it runs through a second FusedStep of that size which SHARES the optimizer state, step counter and
+        schedule of the main one (engine.FusedStep share_state_with) — one optimizer for every batch, like the reference."""
+        eng = self._fused
+        if n_rows == eng.B:
+            return eng
+        if getattr(eng, "world", 1) > 1:
+            raise NotImplementedError("ragged batches are not supported by the sharded step: use a dataset size that is a multiple of the global batch")
+        if n_rows not in self._ragged:
+            self._ragged[n_rows] = FusedStep(self.model, batch_size=n_rows, share_state_with=eng, **self._fused_kw)
+        return self._ragged[n_rows]
 
     def supports_fused(self) -> bool:
         return self.model.model_name.lower() in ("dcnv2", "dnn", "deepfm")
@@ -202,12 +219,12 @@ class Trainer:
     def train_step(self, X, Y=None):
         """Public single-step API: X [B, F] int64 on the host (ideally pinned) or on the device; returns the reference's
         output tuple as device tensors.  Host inputs are copied with one async H2D transfer per tensor."""
-        eng = self._fused
-        if eng is None:
+        if self._fused is None:
             raise RuntimeError("call fused_step(total_steps, warmup_steps) (or MFP_pretrain/RFD_pretrain/train) first")
+        eng = self._engine_for(X.shape[0])
         if not X.is_cuda:
-            if self._h2d is None:
-                self._h2d = torch.empty(eng.B, eng.F, dtype=torch.int64, device=self.device)
+            if self._h2d is None or self._h2d.shape[0] != X.shape[0]:
+                self._h2d = torch.empty(X.shape[0], eng.F, dtype=torch.int64, device=self.device)
             self._h2d.copy_(X, non_blocking=True)
             X = self._h2d
         if Y is not None and not Y.is_cuda:
@@ -287,9 +304,9 @@ class Trainer:
             logger.info(f"-------------------- epoch-{epoch} --------------------")
             self.model.train()
             for X, _ in self.train_dataloader:
-                if fused and X.shape[0] == eng.B:
+                if fused:
                     outputs = self.train_step(X)
-                else:  # module path (DeepFM, ragged last batch): autograd over the same kernels
+                else:  # module path (backbones without a fused schedule): autograd over the same kernels
                     if self.optimizer is None:
                         self.optimizer, self.scheduler = self.get_optimizer(t_total, t_warmup)
                     inputs = self.dynamic_mask({"input_ids": X}, a.sampling_method, step=self.global_step)
@@ -377,7 +394,7 @@ class Trainer:
             logger.info(f"-------------------- epoch-{epoch} --------------------")
             self.model.train()
             for X, Y in self.train_dataloader:
-                if fused and X.shape[0] == eng.B:
+                if fused:
                     outputs = self.train_step(X, Y)
                 else:
                     if self.optimizer is None:

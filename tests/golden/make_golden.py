@@ -272,6 +272,8 @@ def _final(model, ids):
         return torch.cat([model.cross_net(fe), model.parallel_dnn(fe)], dim=-1)
     fe = model.embed(ids)
     dnn = model.dnn(fe.flatten(start_dim=1))
+    if model.model_name == "DNN":   # DNN.forward models.py:183-186
+        return dnn
     return torch.cat([dnn, model.lr_layer(ids)[0] + model.ip_layer(fe)], dim=1)
 
 
@@ -284,3 +286,6 @@ if __name__ == "__main__":
     golden_model("deepfm_mfp", "DeepFM", "MFP")
     golden_model("dcnv2_ctr", "DCNv2", "MFP", pretrain=False)
     golden_model("deepfm_ctr", "DeepFM", "MFP", pretrain=False)
+    golden_model("dnn_mfp", "DNN", "MFP")          # models.py:164-193
+    golden_model("dnn_rfd", "DNN", "RFD")
+    golden_model("dnn_ctr", "DNN", "MFP", pretrain=False)

@@ -37,7 +37,8 @@ def test_header_declares_and_library_exports_every_symbol(lib):
 def test_struct_layouts_match_header(lib):
     import ctypes as C
     assert C.sizeof(lib.GemmArgs) == 24 + 8 * 13 + 8 * 4 + 8 + 8  # + aux2/acc_out (+ld), acc_accumulate/reserved, colsum_out
-    assert C.sizeof(lib.AdamwTensor) == 64
+    assert C.sizeof(lib.AdamwTensor) == 80  # + planes pointer and plane stride (bf16 planes of the parameter)
+    assert C.sizeof(lib.GemmSplitArgs) == C.sizeof(lib.GemmArgs) + 3 * 32
 
 
 def test_errors_are_reported_not_swallowed(lib):

@@ -664,6 +664,111 @@ def test_gemm_tcgen05_strided_views(ops):
     assert final[:, :624].abs().sum() == 0
 
 
+# ---- split-bf16 backend (default): fp32-level accuracy from bf16 tensor-core MMAs (gemm_bf16s.cu)
+# terms = 3 (hi*hi + hi*lo + lo*hi): every product is exact to ~2^-17 -> Frobenius-relative error of a GEMM ~1e-5 (bar 4e-5);
+# terms = 6 (+ lo*lo + hi*lo2 + lo2*hi): ~2^-24 per product -> the error is the fp32 accumulation's (bar 4e-6: an fp32 dot product of
+# length K has ~sqrt(K) * 2^-24; the tensor core's accumulator rounding is measured here).
+BF16S_TOL = {3: 1.5e-5, 6: 3e-6}
+
+
+def _bf16s_log(rec):
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "gemm_bf16s_errors.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+
+@pytest.mark.parametrize("terms", [3, 6])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 96), (4096, 624, 624), (300, 1000, 1000), (1000, 624, 4096),
+                                   (4096, 1248, 1624), (129, 16, 40), (4096, 1624, 1248), (40, 1248, 4096), (4096, 40, 1248)])
+def test_gemm_bf16s(ops, M, N, K, ta, tb, terms):
+    gen = torch.Generator().manual_seed(M + N + K)
+    A, B, As, Bs = _gemm_case(gen, M, N, K, ta, tb)
+    want = A.double() @ B.double().t()
+    Cd = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(dev(As), dev(Bs), Cd, M, N, K, trans_a=ta, trans_b=tb, backend="bf16s", terms=terms)
+    torch.cuda.synchronize()
+    got = Cd.cpu().double()
+    assert torch.isfinite(got).all(), "NaN/garbage in the output (unwritten tile)"
+    rel = float((got - want).norm() / want.norm())
+    mx = float((got - want).abs().max())
+    _bf16s_log(dict(test="plain", M=M, N=N, K=K, ta=ta, tb=tb, terms=terms, rel=rel, max_abs=mx))
+    assert rel < BF16S_TOL[terms], f"frobenius rel err {rel:.3e}"
+
+
+@pytest.mark.parametrize("terms", [3, 6])
+@pytest.mark.parametrize("accumulate", [False, True])
+@pytest.mark.parametrize("epi", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_gemm_bf16s_epilogues_and_output_planes(ops, epi, accumulate, terms):
+    if accumulate and epi != 7:
+        pytest.skip("acc_accumulate only exists for MAP_EPI_CROSS_BWD")
+    from map_code_b200 import _lib as L
+    M, N, K, ta, tb = 515, 624, 624, False, epi in (4, 5, 6, 7, 8)
+    gen = torch.Generator().manual_seed(epi)
+    A, B, As, Bs = _gemm_case(gen, M, N, K, ta, tb)
+    bias = torch.randn(N, generator=gen)
+    aux0, aux1, aux2 = (torch.randn(M, N, generator=gen) for _ in range(3))
+    acc_prev = torch.randn(M, N, generator=gen) if accumulate else None
+    acc = A.double() @ B.double().t()
+    want, want_aux, want_acc = _epilogue_ref(epi, acc, bias.double(), aux0.double(), aux1.double(), aux2.double(),
+                                             acc_prev.double() if accumulate else None)
+    Cd = torch.full((M, N), float("nan"), device="cuda")
+    auxo = torch.full((M, N), float("nan"), device="cuda")
+    acco = dev(acc_prev) if accumulate else torch.full((M, N), float("nan"), device="cuda")
+    cs = torch.full((N,), 0.5, device="cuda")
+    n_pl = 3 if terms == 6 else 2
+    Cp = ops.alloc_planes(M, N, n_pl, "cuda")
+    ops.gemm(dev(As), dev(Bs), Cd, M, N, K, trans_a=ta, trans_b=tb, epilogue=epi, bias=dev(bias), aux0=dev(aux0), aux1=dev(aux1),
+             aux_out=auxo, aux2=dev(aux2), acc_out=acco if epi == L.EPI_CROSS_BWD else None, acc_accumulate=accumulate, colsum_out=cs,
+             backend="bf16s", terms=terms, Cp=Cp)
+    torch.cuda.synchronize()
+    got = Cd.cpu().double()
+    assert torch.isfinite(got).all()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 2e-4 * scale and float((got - want).norm() / want.norm()) < 10 * BF16S_TOL[terms]
+    if want_aux is not None:
+        assert float((auxo.cpu().double() - want_aux).norm() / want_aux.norm()) < 10 * BF16S_TOL[terms]
+    if want_acc is not None:
+        assert float((acco.cpu().double() - want_acc).norm() / want_acc.norm()) < 10 * BF16S_TOL[terms]
+    got_cs, want_cs = cs.cpu().double() - 0.5, got.sum(0)
+    assert (got_cs - want_cs).abs().max() < 1e-3 * max(1.0, float(want_cs.abs().max())), "fused column sums"
+    # the planes the epilogue wrote reproduce C: hi + lo to 2^-16, hi + lo + lo2 to 2^-24 (of each element)
+    rec = Cp.float().sum(0).cpu().double() if n_pl == 2 else (Cp[0].double() + Cp[1].double() + Cp[2].double()).cpu()
+    err = (rec - got).abs()
+    bound = got.abs() * (2.0 ** -15 if n_pl == 2 else 2.0 ** -22) + 1e-30
+    assert bool((err <= bound).all()), f"planes do not reproduce C: worst {float((err / (got.abs() + 1e-30)).max()):.3e}"
+    assert torch.equal(Cp[0].cpu(), Cd.cpu().to(torch.bfloat16)), "plane 0 must be bf16(C) rounded to nearest"
+
+
+@pytest.mark.parametrize("terms", [3, 6])
+@pytest.mark.parametrize("name", sorted(GROUPS))
+def test_gemm_group_bf16s(ops, name, terms):
+    """persistent launch of CTA pairs over the tiles of up to 4 problems (two TMEM accumulators): every problem vs fp64"""
+    probs, checks = [], []
+    for i, (M, N, K, ta, tb, epi, accumulate, colsum) in enumerate(GROUPS[name]):
+        kw, verify = _gemm_problem(M, N, K, ta, tb, epi, seed=10 * i + epi, accumulate=accumulate and epi == 7, colsum=colsum)
+        kw["terms"] = terms
+        probs.append(kw)
+        checks.append(verify)
+    ops.gemm_group(probs, backend="bf16s")
+    torch.cuda.synchronize()
+    for verify in checks:
+        verify()
+
+
+def test_split_planes_exact(ops):
+    gen = torch.Generator().manual_seed(3)
+    X = torch.randn(257, 624, generator=gen) * torch.exp(torch.randn(257, 624, generator=gen) * 4)   # wide dynamic range
+    P = ops.split_planes(dev(X), ops.alloc_planes(257, 624, 3, "cuda")).cpu()
+    hi = X.to(torch.bfloat16)
+    lo = (X - hi.float()).to(torch.bfloat16)
+    lo2 = (X - hi.float() - lo.float()).to(torch.bfloat16)
+    assert torch.equal(P[0], hi) and torch.equal(P[1], lo) and torch.equal(P[2], lo2)
+    assert float(((P[0].double() + P[1].double() + P[2].double()) - X.double()).abs().max() / X.abs().max()) < 2 ** -24
+
+
 # ------------------------------------------------------------------------------------------------ K13b peer-memory path
 @pytest.mark.parametrize("R", [1, 2, 3, 8])
 def test_peer_sharded_gather_and_merge_single_process(ops, R):

@@ -137,3 +137,48 @@ def test_check_health_reports_a_failed_device_wait(tmp_path):
     plan.ws[off:off + 4].view(torch.int32).fill_(1)
     with pytest.raises(_lib.MapB200Error):
         eng.check_health()
+
+
+@pytest.mark.parametrize("model_name,pt_type,pretrain", [("DCNv2", "MFP", True), ("DeepFM", "MFP", True), ("DCNv2", "RFD", True),
+                                                         ("DeepFM", "MFP", False)])
+def test_ragged_last_batch_keeps_one_optimizer_state(model_name, pt_type, pretrain, tmp_path):
+    """n % batch != 0 (reference DataLoader keeps the short last batch, trainer.py:51-58).  The short batch must run through the
+    SAME optimizer state, step counter and LR schedule as the full batches: the run over [256, 256, 256, 232] rows is compared
+    with a run that feeds the very same four batches through FusedSteps built by hand around one shared state."""
+    from map_code_b200.engine import FusedStep
+    from map_code_b200.trainer import Trainer
+    model, cfg, args, train, valid = make(pt_type, pretrain, model_name, tmp_path)
+    args.num_train_epochs = 1
+    n = 1000                                    # 3 full batches of 256 + one of 232
+    train = DS(train.X[:n], train.Y[:n])
+    tr = Trainer(model, cfg, args, train, valid)
+    # no shuffling: the batches are rows [0,256), ... in order, so the second run can replay them
+    orig = tr.get_dataloader
+    tr.get_dataloader = lambda ds, is_training=True: orig(ds, is_training=False) if ds is train else orig(ds, is_training)
+    args.per_gpu_eval_batch_size = args.per_gpu_train_batch_size
+    if pretrain:
+        getattr(tr, f"{pt_type}_pretrain")()
+    else:
+        tr.train()
+    assert tr.global_step == 4
+    eng = tr._fused
+    assert int(eng.step_counter.item()) == 4 and tr.optimizer is None       # no second optimizer was ever built
+    assert list(tr._ragged.keys()) == [232] and tr._ragged[232].exp_avg is eng.exp_avg
+    # replay by hand
+    m2, cfg2, args2, _, _ = make(pt_type, pretrain, model_name, tmp_path)
+    m2.cuda()
+    X = torch.from_numpy(train.X).cuda()
+    Y = torch.from_numpy(train.Y).cuda()
+    kw = dict(mask_ratio=0.1, sampling_method="randint", lr=1e-3, weight_decay=5e-2, sched="cosine", warmup_steps=0, total_steps=4, seed=42,
+              x_train=X if pt_type == "RFD" and pretrain else None)
+    e_full = FusedStep(m2, batch_size=256, **kw)
+    e_tail = FusedStep(m2, batch_size=232, share_state_with=e_full, **kw)
+    for i in range(3):
+        e_full.step(X[i * 256:(i + 1) * 256], Y[i * 256:(i + 1) * 256])
+    e_tail.step(X[768:1000], Y[768:1000])
+    torch.cuda.synchronize()
+    sd1, sd2 = model.state_dict(), m2.state_dict()
+    for k in sd1:
+        assert torch.allclose(sd1[k].float(), sd2[k].float(), rtol=1e-5, atol=1e-7), k
+    # and the tail step really moved the dense parameters with step-4 bias corrections (not a fresh t=1 optimizer)
+    assert float(eng.hyper[0].item()) < 1e-3  # cosine LR near the end of the 4-step schedule, not the base LR
