@@ -27,6 +27,7 @@
 //     {64 mn, 64 k} boxes (dgrad reads W [N,K] as B^T, wgrad reads dY and X transposed), no transposed copies anywhere.
 // Replaces the cuBLAS sgemm behind every nn.Linear of the step (code/layers.py:179-200, code/models.py:116-123), fwd + bwd.
 #define MAP_GEMM_TWO_ACCUMULATORS 1
+#define MAP_GEMM_STAGE_LD16 1
 #include "gemm_common.cuh"
 
 namespace mapb {
@@ -39,7 +40,9 @@ constexpr int kSMaxStages = 6;
 constexpr int kSMaxGroup = 4;
 constexpr int kSAccCols = 256;             // TMEM columns per accumulator
 constexpr int kSTmemCols = 2 * kSAccCols;
-constexpr int kSStagingBytes = 4 * 32 * kStageLd * 4;   // per-warp transpose tiles of the 4 epilogue warps
+constexpr int kSEpiWarps = 8;              // two per TMEM lane quarter: the column chunks of a tile alternate between them
+constexpr int kSThreads = 64 + 32 * kSEpiWarps;
+constexpr int kSStagingBytes = kSEpiWarps * 32 * kStageLd16 * 4;   // per-warp transpose tiles (16-column chunks)
 constexpr int kSSmemBudget = 227 * 1024 - 2048;
 
 struct SProblem {
@@ -47,13 +50,17 @@ struct SProblem {
     int pa, pb, terms;     // planes staged of A / B; MMAs per k-step (3 or 6; 6 = two accumulators, see above)
     int half_n;            // B columns staged by one CTA (block_n / 2)
     int n_tiles, m_pairs;  // tile grid (pair tiles)
-    int tile_end;          // exclusive prefix sum of pair tiles (x split_k) over the problems of the launch
+    int n_pair_tiles;      // m_pairs * n_tiles * split_k
 };
 
 struct SGroupArgs {
     CUtensorMap tmap[2 * kSMaxGroup];   // A, B of problem i at [2i], [2i+1]; 3-D {inner, rows, plane}
     SProblem pr[kSMaxGroup];
     int count, total_tiles;
+    // tile sequence of the launch: the problems in DESCENDING order of their per-tile cost (seq[i] = slot, seq_end[i] = exclusive
+    // prefix sum of tiles); cluster c takes sequence positions c, 2n-1-c, 2n+c, 4n-1-c, ... (snake), so every cluster gets
+    // a mix of expensive and cheap tiles and the launch ends within about one cheap tile of the average
+    int seq[kSMaxGroup], seq_end[kSMaxGroup];
     int stages, stage_bytes;            // one ring geometry for the whole launch (the largest problem's planes)
     unsigned long long* trace;          // optional per-CTA timeline (map_gemm_bf16s_set_trace), nullptr in production
 };
@@ -86,13 +93,14 @@ __device__ __forceinline__ uint32_t acc_pick(AccState& st, bool dual) {
 
 __device__ __forceinline__ TileInfo decode_tile(const SGroupArgs& g, int t) {
     TileInfo ti;
-    int gi = 0, start = 0;
+    int sp = 0, start = 0;
 #pragma unroll
     for (int i = 0; i < kSMaxGroup - 1; ++i)
-        if (t >= g.pr[i].tile_end) {
-            gi = i + 1;
-            start = g.pr[i].tile_end;
+        if (t >= g.seq_end[i]) {
+            sp = i + 1;
+            start = g.seq_end[i];
         }
+    const int gi = g.seq[sp];
     int nt, mp, nkb_split, kbt;
 #define MAP_LOAD_PR(i)                                                                                              \
     {                                                                                                               \
@@ -116,8 +124,14 @@ __device__ __forceinline__ TileInfo decode_tile(const SGroupArgs& g, int t) {
     return ti;
 }
 
+// i-th tile of cluster c (of n): sequence position in snake order, or -1 when the cluster has no i-th tile
+__device__ __forceinline__ int snake_tile(int i, int c, int n, int total) {
+    const int t = i * n + ((i & 1) ? (n - 1 - c) : c);
+    return t < total ? t : -1;
+}
+
 template <int E0, int E1, int E2, int E3>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __grid_constant__ SGroupArgs g) {
+__global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_constant__ SGroupArgs g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t full_bar[kSMaxStages];
@@ -145,7 +159,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __gri
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tmem_full_bar[b]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[b]), 8);   // 4 epilogue warps of each CTA of the pair (leader's barrier is used)
+            mbar_init(smem_u32(&tmem_empty_bar[b]), 2 * kSEpiWarps);   // the epilogue warps of both CTAs of the pair (leader's barrier)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __gri
             int s = 0;
             uint32_t ph = 0;
             int tj = 0;
-            for (int t = cluster_id; t < total; t += n_clusters, ++tj) {
+            for (int t; (t = snake_tile(tj, cluster_id, n_clusters, total)) >= 0; ++tj) {
                 const TileInfo ti = decode_tile(g, t);
                 const CUtensorMap* tmap_a = &g.tmap[2 * ti.gi];
                 const CUtensorMap* tmap_b = tmap_a + 1;
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __gri
             uint32_t ph = 0;
             AccState acc{{0u, 0u}, 0u};
             int tj = 0;
-            for (int t = cluster_id; t < total; t += n_clusters, ++tj) {
+            for (int t; (t = snake_tile(tj, cluster_id, n_clusters, total)) >= 0; ++tj) {
                 const TileInfo ti = decode_tile(g, t);
                 const bool dual = ti.terms == 6;
                 const uint32_t buf = acc_pick(acc, dual);
@@ -261,11 +275,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __gri
         }
     } else {
         // ===================== epilogue warps (both CTAs): TMEM -> registers -> smem transpose -> fused epilogue -> global =====
-        const int q = warp & 3;   // TMEM lane quarter this warp may access
-        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stages * stage_bytes) + q * (32 * kStageLd);
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int part = (warp - 2) >> 2;  // which of the quarter's two warps: takes every second 16-column chunk
+        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stages * stage_bytes) + (warp - 2) * (32 * kStageLd16);
         AccState acc{{0u, 0u}, 0u};
         int tj = 0;
-        for (int t = cluster_id; t < total; t += n_clusters, ++tj) {
+        for (int t; (t = snake_tile(tj, cluster_id, n_clusters, total)) >= 0; ++tj) {
             const TileInfo ti = decode_tile(g, t);
             const bool dual = ti.terms == 6;
             const uint32_t buf = acc_pick(acc, dual);
@@ -282,10 +297,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __gri
             // (epi_tile stamps ttr[5] when the accumulator is complete and ttr[6] at its end: words 8 and 9 (+6 per tile) of the record
             //  are written through the pointer shifted by -1 so that they land on [4 + 6 tj + 4] and [+5])
             unsigned long long* tt = ttr != nullptr ? ttr - 1 : nullptr;
-            if (ti.gi == 0) epi_slot<E0>(g.pr[0].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
-            else if (ti.gi == 1) epi_slot<E1>(g.pr[1].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
-            else if (ti.gi == 2) epi_slot<E2>(g.pr[2].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
-            else epi_slot<E3>(g.pr[3].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par);
+            if (ti.gi == 0) epi_slot<E0, 16>(g.pr[0].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par, part, 2);
+            else if (ti.gi == 1) epi_slot<E1, 16>(g.pr[1].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par, part, 2);
+            else if (ti.gi == 2) epi_slot<E2, 16>(g.pr[2].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par, part, 2);
+            else epi_slot<E3, 16>(g.pr[3].p, stg, lane, lane_addr, row_base, m0, n0, fb, tt, par, part, 2);
             // this warp has read its quarter of the accumulator: hand the buffer back to the MMA issuer (leader CTA's barrier)
             tcgen05_fence_before();
             __syncwarp();
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16s_kernel(const __gri
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         int my_tiles = 0;
-        for (int t = cluster_id; t < total; t += n_clusters) ++my_tiles;
+        while (snake_tile(my_tiles, cluster_id, n_clusters, total) >= 0) ++my_tiles;
         trace[2] = globaltimer_ns();
         trace[3] = (unsigned long long)smid | ((unsigned long long)my_tiles << 32);
     }
@@ -449,23 +464,155 @@ static int find_scombo(const int* e, int count) {
     return -1;
 }
 
-// pair-tile width: the widest BLOCK_N that wastes the fewest padded columns.  K-major B: any multiple of 16 in [128, 256];
-// MN-major B: whole 64-column chunks per CTA half -> 128 or 256.
-static int choose_block_n(int N, bool mn_major_b) {
-    if (mn_major_b) {
-        const int c128 = (int)ceil_div(N, 128) * 128, c256 = (int)ceil_div(N, 256) * 256;
-        return (c256 <= c128) ? 256 : 128;
+// ---- tile plan of one launch.  Measured (profiles/r02b_gemm_bf16s_levels.txt): in steady state the main loop is bound by L2 -> SM
+// operand traffic (~30 B/clk/SM at the clocks this kernel runs at), not by the tensor pipe; one level of the step is only 1.5 - 3
+// pair tiles per cluster, so the END of a launch is decided by tile quantisation.  The host therefore picks every problem's
+// BLOCK_N by simulating the launch: per-tile cost = k-blocks x max(operand bytes / 30, MMA clocks) + the exposed part of the
+// epilogue, tiles dealt to the 74 clusters in the kernel's own order (problems by descending tile cost, snake), makespan =
+// busiest cluster.  K-major B takes any multiple of 16 (<= 256); MN-major B whole 64-column chunks per CTA half: 128 or 256.
+struct TileModel {
+    int block_n, n_tiles, m_pairs, split, nkb, tiles;
+    double cost;
+};
+static const double kEpiCol[] = {15, 23, 25, 45, 60, 45, 60, 150, 47};   // epilogue clk per column: NONE, BIAS, BIAS_RELU, CROSS, RELUMASK, ADD, ADD_MUL, CROSS_BWD, ADD3
+
+static int split_for(const map_gemm_split_args* a, int kb_total) {
+    const map_gemm_args* g = &a->g;
+    int split = 1;
+    const bool allow_split = g->epilogue == MAP_EPI_NONE && g->colsum_out == nullptr && a->c_planes == nullptr;
+    if (allow_split && kb_total >= 32) {
+        split = (kb_total + 8) / 16;
+        if (split > 16) split = 16;
     }
-    if (N < 128) return (int)ceil_div(N, 16) * 16;
-    int best = 256, best_cols = 1 << 30;
-    for (int bn = 256; bn >= 128; bn -= 16) {
-        const int cols = (int)ceil_div(N, bn) * bn;
-        if (cols < best_cols) {
-            best_cols = cols;
-            best = bn;
+    if (const char* e = getenv("MAP_B200_SPLITK")) {
+        const int sk = atoi(e);
+        if (allow_split && sk >= 1 && sk <= 64) split = sk;
+    }
+    return split;
+}
+
+static TileModel model_tile(const map_gemm_split_args* a, int bn) {
+    const map_gemm_args* g = &a->g;
+    TileModel t{};
+    t.block_n = bn;
+    t.m_pairs = (int)ceil_div(g->M, 2 * kBlockM);
+    t.n_tiles = (int)ceil_div(g->N, bn);
+    const int kbt = (int)ceil_div(g->K, kSBlockK);
+    t.split = split_for(a, kbt);
+    t.nkb = (int)ceil_div(kbt, t.split);
+    t.split = (int)ceil_div(kbt, t.nkb);
+    t.tiles = t.m_pairs * t.n_tiles * t.split;
+    const int planes = a->terms == 6 ? 3 : 2;
+    const double bytes = planes * (kSPlaneA + bn / 2 * 128.0);
+    const double mma = a->terms * 4 * 128.0 * bn / 256.0;
+    const double per_kb = bytes / 30.0 > mma ? bytes / 30.0 : mma;
+    const double epi = kEpiCol[g->epilogue] * bn + (a->c_planes ? 10.0 * a->c_nplanes * bn : 0.0);
+    t.cost = t.nkb * per_kb * (a->terms == 6 ? 1.1 : 1.0) + (a->terms == 6 ? epi : 0.35 * epi) + 1500.0;
+    return t;
+}
+
+static double simulate_makespan(const TileModel* tm, int count, int clusters) {
+    int order[kSMaxGroup] = {0, 1, 2, 3};
+    for (int i = 1; i < count; ++i)
+        for (int j = i; j > 0 && tm[order[j]].cost > tm[order[j - 1]].cost; --j) {
+            const int tmp = order[j]; order[j] = order[j - 1]; order[j - 1] = tmp;
+        }
+    double load[kNumSMs / 2] = {};
+    int pos = 0;
+    for (int oi = 0; oi < count; ++oi) {
+        const TileModel& t = tm[order[oi]];
+        for (int k = 0; k < t.tiles; ++k, ++pos) {
+            const int round = pos / clusters, c = pos % clusters;
+            load[(round & 1) ? clusters - 1 - c : c] += t.cost;
         }
     }
-    return best;
+    double mx = 0;
+    for (int c = 0; c < clusters; ++c) mx = load[c] > mx ? load[c] : mx;
+    return mx;
+}
+
+struct PlanKey {
+    int v[kSMaxGroup][8];
+    int count, clusters;
+};
+struct PlanEntry {
+    PlanKey key;
+    int bn[kSMaxGroup];
+};
+static PlanEntry g_plan_cache[64];
+static int g_plan_cache_n = 0;
+
+static void plan_block_n_search(const map_gemm_split_args* sorted, int count, int clusters, int* out_bn);
+
+// the search result only depends on the shapes: remembered per (shapes, epilogues, terms) signature (eager steps relaunch the same
+// nine groups every step)
+static void plan_block_n(const map_gemm_split_args* sorted, int count, int clusters, int* out_bn) {
+    PlanKey k;
+    memset(&k, 0, sizeof(k));
+    k.count = count;
+    k.clusters = clusters;
+    for (int i = 0; i < count; ++i) {
+        const map_gemm_args* g = &sorted[i].g;
+        const int v[8] = {g->M, g->N, g->K, g->trans_a, g->trans_b, g->epilogue, sorted[i].terms,
+                          (sorted[i].c_planes ? sorted[i].c_nplanes : 0) | (g->colsum_out ? 16 : 0)};
+        memcpy(k.v[i], v, sizeof(v));
+    }
+    for (int e = 0; e < g_plan_cache_n; ++e)
+        if (memcmp(&g_plan_cache[e].key, &k, sizeof(k)) == 0) {
+            memcpy(out_bn, g_plan_cache[e].bn, sizeof(int) * kSMaxGroup);
+            return;
+        }
+    plan_block_n_search(sorted, count, clusters, out_bn);
+    if (getenv("MAP_B200_BLOCK_N") == nullptr && getenv("MAP_B200_SPLITK") == nullptr) {
+        PlanEntry& e = g_plan_cache[g_plan_cache_n < 64 ? g_plan_cache_n++ : 63];
+        e.key = k;
+        memcpy(e.bn, out_bn, sizeof(int) * kSMaxGroup);
+    }
+}
+
+static void plan_block_n_search(const map_gemm_split_args* sorted, int count, int clusters, int* out_bn) {
+    int cand[kSMaxGroup][16], ncand[kSMaxGroup];
+    for (int i = 0; i < kSMaxGroup; ++i) out_bn[i] = 0;
+    for (int i = 0; i < count; ++i) {
+        const map_gemm_args* g = &sorted[i].g;
+        ncand[i] = 0;
+        if (g->trans_b) {
+            cand[i][ncand[i]++] = 256;
+            cand[i][ncand[i]++] = 128;
+        } else if (g->N <= 64) {
+            cand[i][ncand[i]++] = (int)ceil_div(g->N, 16) * 16;
+        } else {
+            for (int bn = 256; bn >= 64; bn -= 16) {   // one candidate per distinct tile count: the narrowest width that still covers N
+                const int nt = (int)ceil_div(g->N, bn);
+                const int tight = (int)ceil_div((int)ceil_div(g->N, nt), 16) * 16;
+                bool seen = false;
+                for (int k = 0; k < ncand[i]; ++k) seen = seen || cand[i][k] == tight;
+                if (!seen && ncand[i] < 16) cand[i][ncand[i]++] = tight;
+            }
+        }
+        if (const char* e = getenv("MAP_B200_BLOCK_N")) {  // tuning override
+            const int bn = atoi(e);
+            if (bn >= 16 && bn <= 256 && bn % (g->trans_b ? 128 : 16) == 0) {
+                cand[i][0] = bn;
+                ncand[i] = 1;
+            }
+        }
+    }
+    int idx[kSMaxGroup] = {0, 0, 0, 0}, best[kSMaxGroup] = {0, 0, 0, 0};
+    double best_ms = 1e300;
+    for (;;) {
+        TileModel tm[kSMaxGroup];
+        for (int i = 0; i < count; ++i) tm[i] = model_tile(&sorted[i], cand[i][idx[i]]);
+        const double ms = simulate_makespan(tm, count, clusters);
+        if (ms < best_ms) {
+            best_ms = ms;
+            for (int i = 0; i < count; ++i) best[i] = idx[i];
+        }
+        int d = 0;
+        while (d < count && ++idx[d] == ncand[d]) idx[d++] = 0;
+        if (d == count) break;
+    }
+    for (int i = 0; i < count; ++i) out_bn[i] = cand[i][best[i]];
 }
 
 static unsigned long long* g_strace_buf = nullptr;
@@ -475,6 +622,14 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
     SGroupArgs ga{};
     ga.count = count;
     int total = 0, stage_bytes = 0;
+    double cost[kSMaxGroup] = {0, 0, 0, 0};
+    int clusters = kNumSMs / 2;
+    if (const char* e = getenv("MAP_B200_GEMM_CLUSTERS")) {
+        const int c = atoi(e);
+        if (c >= 1 && c <= kNumSMs / 2) clusters = c;
+    }
+    int plan_bn[kSMaxGroup];
+    plan_block_n(sorted, count, clusters, plan_bn);
     for (int i = 0; i < count; ++i) {
         const map_gemm_split_args* a = &sorted[i];
         const map_gemm_args* g = &a->g;
@@ -483,11 +638,7 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
         p.M = g->M; p.N = g->N; p.K = g->K;
         p.trans_a = g->trans_a ? 1 : 0;
         p.trans_b = g->trans_b ? 1 : 0;
-        p.block_n = choose_block_n(g->N, p.trans_b != 0);
-        if (const char* e = getenv("MAP_B200_BLOCK_N")) {  // tuning override
-            const int bn = atoi(e);
-            if (bn >= 16 && bn <= 256 && bn % (p.trans_b ? 128 : 16) == 0) p.block_n = bn;
-        }
+        p.block_n = plan_bn[i];
         pr.half_n = p.block_n / 2;
         pr.terms = a->terms;
         pr.pa = pr.pb = (a->terms == 6) ? 3 : 2;
@@ -511,23 +662,15 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
         p.tmem_cols = kSAccCols;
         p.k_blocks_total = (int)ceil_div(g->K, kSBlockK);
         // split-K (plain outputs only): a CTA pair's share of a long reduction (wgrad, K = batch) is ~16 k-blocks, like a dgrad tile
-        int split = 1;
-        const bool allow_split = g->epilogue == MAP_EPI_NONE && g->colsum_out == nullptr && a->c_planes == nullptr;
-        if (allow_split && p.k_blocks_total >= 32) {
-            split = (p.k_blocks_total + 8) / 16;
-            if (split > 16) split = 16;
-        }
-        if (const char* e = getenv("MAP_B200_SPLITK")) {
-            const int sk = atoi(e);
-            if (allow_split && sk >= 1 && sk <= 64) split = sk;
-        }
+        const int split = split_for(a, p.k_blocks_total);
         p.num_k_blocks = (int)ceil_div(p.k_blocks_total, split);
         p.split_k = (int)ceil_div(p.k_blocks_total, p.num_k_blocks);
         p.trace = nullptr;
         pr.m_pairs = (int)ceil_div(g->M, 2 * kBlockM);
         pr.n_tiles = (int)ceil_div(g->N, p.block_n);
-        total += pr.m_pairs * pr.n_tiles * p.split_k;
-        pr.tile_end = total;
+        pr.n_pair_tiles = pr.m_pairs * pr.n_tiles * p.split_k;
+        total += pr.n_pair_tiles;
+        cost[i] = model_tile(a, p.block_n).cost;
         int rc;
         // A planes: K-major [M rows][K contiguous] box {64, 128}; MN-major [K rows][M contiguous] box {64, 64}
         if (!p.trans_a) rc = make_tmap_planes(&ga.tmap[2 * i], a->a_planes, g->K, g->M, a->a_ld, a->a_plane_stride, pr.pa, kBlockM);
@@ -543,7 +686,19 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
             }
         }
     }
-    for (int i = count; i < kSMaxGroup; ++i) ga.pr[i].tile_end = total;
+    {
+        int order[kSMaxGroup] = {0, 1, 2, 3};
+        for (int i = 1; i < count; ++i)
+            for (int j = i; j > 0 && cost[order[j]] > cost[order[j - 1]]; --j) {
+                const int tmp = order[j]; order[j] = order[j - 1]; order[j - 1] = tmp;
+            }
+        int acc_tiles = 0;
+        for (int i = 0; i < kSMaxGroup; ++i) {
+            ga.seq[i] = i < count ? order[i] : 0;
+            if (i < count) acc_tiles += ga.pr[order[i]].n_pair_tiles;
+            ga.seq_end[i] = acc_tiles;
+        }
+    }
     ga.total_tiles = total;
     ga.stage_bytes = stage_bytes;
     int stages = (kSSmemBudget - 1024 - kSStagingBytes) / stage_bytes;
@@ -564,16 +719,11 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
         }
         attr_set[combo] = true;
     }
-    int clusters = kNumSMs / 2;
-    if (const char* e = getenv("MAP_B200_GEMM_CLUSTERS")) {
-        const int c = atoi(e);
-        if (c >= 1 && c <= kNumSMs / 2) clusters = c;
-    }
     if (clusters > total) clusters = total;
     ga.trace = ((int64_t)2 * clusters * kSTraceWords <= g_strace_words) ? g_strace_buf : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(kSThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

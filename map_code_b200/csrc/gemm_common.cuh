@@ -355,12 +355,18 @@ __device__ __forceinline__ void store_planes4(const GemmParams& p, int64_t row, 
 }
 
 constexpr int kStageLd = 36;  // floats per staging row (144 B: 16-byte aligned, conflict-free 128-bit phases)
+#ifdef MAP_GEMM_STAGE_LD16    // split-bf16 kernel: 8 epilogue warps with 16-column chunks only -> 20-float staging rows (2.5 KB per warp)
+constexpr int kStageLd16 = 20;
+#else
+constexpr int kStageLd16 = kStageLd;
+#endif
 
 // one chunk: TMEM -> registers -> per-warp smem transpose -> fused epilogue on the prefetched operands -> global
 template <int EPI, bool SPLIT, int W>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, int lane, uint32_t taddr, int row_base, int ncol0,
                                           bool full_tile, const EpiRegs& e) {
     constexpr int LPR = W / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+    constexpr int LD = (W == 16) ? kStageLd16 : kStageLd;
     float v[W];
     if (W == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
 #ifdef MAP_GEMM_TWO_ACCUMULATORS   // compiled into the split-bf16 kernel only (the TF32 kernel runs 2 CTAs per SM at 168 registers)
@@ -373,7 +379,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, int l
 #endif
 #pragma unroll
     for (int j = 0; j < W / 4; ++j)
-        *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(stg + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
     const int cg = lane % LPR, rr = lane / LPR;
     const int n = ncol0 + 4 * cg;
@@ -381,12 +387,12 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, int l
     float* aux_dst = (epi_has_aux_out(EPI) && p.aux_out != nullptr) ? p.aux_out + (int64_t)(row_base + rr) * p.ld_aux_out + n : nullptr;
     float* acc_dst = (EPI == MAP_EPI_CROSS_BWD) ? p.acc_out + (int64_t)(row_base + rr) * p.ld_acc_out + n : nullptr;
     const bool acc_accumulate = p.acc_accumulate != 0;
-    const float* src = stg + rr * kStageLd + 4 * cg;
+    const float* src = stg + rr * LD + 4 * cg;
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (full_tile) {  // interior tile (the common case): straight-line code, no per-row guards
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
-            const float4 a = *reinterpret_cast<const float4*>(src + i * RPI * kStageLd);
+            const float4 a = *reinterpret_cast<const float4*>(src + i * RPI * LD);
             const float4 o = epilogue_store4<EPI, SPLIT>(dst, aux_dst, acc_dst, acc_accumulate, a, e.bias, e.a0[i], e.a1[i], e.a2[i]);
             cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
             if (!SPLIT && p.c_planes != nullptr) store_planes4(p, row_base + i * RPI + rr, n, o);
@@ -398,7 +404,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, int l
         const bool n_ok = n < p.N;
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
-            const float4 a = *reinterpret_cast<const float4*>(src + i * RPI * kStageLd);
+            const float4 a = *reinterpret_cast<const float4*>(src + i * RPI * LD);
             if (n_ok && row_base + i * RPI + rr < p.M) {
                 const float4 o = epilogue_store4<EPI, SPLIT>(dst, aux_dst, acc_dst, acc_accumulate, a, e.bias, e.a0[i], e.a1[i], e.a2[i]);
                 cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
@@ -441,37 +447,43 @@ __device__ __forceinline__ void epi_chunk_any(const GemmParams& p, float* stg, i
 // Epilogue of one tile.  The operands of chunk i+1 (bias / aux0 / aux1 / aux2 rows) are requested BEFORE chunk i is pulled out
 // of TMEM and written, into the other of two register sets: their L2 round trip (the whole cost of a chunk in the
 // single-buffered version: ~2000 clk per 16-32 columns) overlaps the TMEM read, the transpose and the stores of chunk i.
-template <int EPI, bool SPLIT>
+// `part` / `nsplit`: the column chunks of the tile are dealt round-robin to the `nsplit` warps that share a TMEM lane quarter (the
+// split-bf16 kernel runs two epilogue warps per quarter: twice the loads in flight); FORCE_CW overrides the chunk width.
+template <int EPI, bool SPLIT, int FORCE_CW = 0>
 __device__ __forceinline__ void epi_tile(const GemmParams& p, float* stg, int lane, uint32_t lane_addr, int row_base, int m0, int n0,
-                                         uint32_t full_bar, unsigned long long* trace, uint32_t parity = 0) {
-    constexpr int CW = epi_chunk_w_group(EPI);
+                                         uint32_t full_bar, unsigned long long* trace, uint32_t parity = 0, int part = 0, int nsplit = 1) {
+    constexpr int CW = FORCE_CW != 0 ? FORCE_CW : epi_chunk_w_group(EPI);
     const bool full_tile = (m0 + kBlockM <= p.M) && (n0 + p.block_n <= p.N);
     const int bn = p.block_n;
+    const int step = nsplit * CW;
+    int c = part * CW;
     EpiRegs ea, eb;
-    epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, 0, full_tile, ea);
+    if (c < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c, full_tile, ea);
     mbar_wait(full_bar, parity);
     tcgen05_fence_after();
     if (trace != nullptr && threadIdx.x == 64) trace[5] = (unsigned long long)clock64();
-    for (int c = 0; c < bn; c += 2 * CW) {
-        if (c + CW < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c + CW, full_tile, eb);
+    while (c < bn) {
+        const int c1 = c + step;
+        if (c1 < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c1, full_tile, eb);
         epi_chunk_any<EPI, SPLIT, CW>(p, stg, lane, lane_addr, row_base, n0, c, full_tile, ea);
-        if (c + CW >= bn) break;
-        if (c + 2 * CW < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c + 2 * CW, full_tile, ea);
-        epi_chunk_any<EPI, SPLIT, CW>(p, stg, lane, lane_addr, row_base, n0, c + CW, full_tile, eb);
+        if (c1 >= bn) break;
+        const int c2 = c1 + step;
+        if (c2 < bn) epi_prefetch_any<EPI, CW>(p, lane, row_base, n0, c2, full_tile, ea);
+        epi_chunk_any<EPI, SPLIT, CW>(p, stg, lane, lane_addr, row_base, n0, c1, full_tile, eb);
+        c = c2;
     }
     if (trace != nullptr && threadIdx.x == 64) trace[6] = (unsigned long long)clock64();
 }
 
-template <int EPI>
+template <int EPI, int FORCE_CW = 0>
 __device__ __forceinline__ void epi_slot(const GemmParams& p, float* stg, int lane, uint32_t lane_addr, int row_base, int m0, int n0,
-                                         uint32_t full_bar, unsigned long long* trace, uint32_t parity = 0) {
+                                         uint32_t full_bar, unsigned long long* trace, uint32_t parity = 0, int part = 0, int nsplit = 1) {
     if constexpr (EPI == MAP_EPI_NONE) {
-        if (p.split_k > 1) epi_tile<MAP_EPI_NONE, true>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace, parity);
-        else epi_tile<MAP_EPI_NONE, false>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace, parity);
+        if (p.split_k > 1) epi_tile<MAP_EPI_NONE, true, FORCE_CW>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace, parity, part, nsplit);
+        else epi_tile<MAP_EPI_NONE, false, FORCE_CW>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace, parity, part, nsplit);
     } else if constexpr (EPI > MAP_EPI_NONE) {
-        epi_tile<EPI, false>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace, parity);
+        epi_tile<EPI, false, FORCE_CW>(p, stg, lane, lane_addr, row_base, m0, n0, full_bar, trace, parity, part, nsplit);
     }
 }
-
 
 }  // namespace mapb

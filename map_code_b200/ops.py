@@ -134,6 +134,30 @@ class DedupPlan:
         return dense
 
 
+def feat_count(ids: torch.Tensor, V: int, chunk: int = 1 << 23) -> torch.Tensor:
+    """Occurrence count of every id in `ids` (any shape, int64, on the device) -> float32 [V]: the device form of the reference's
+    `feat_count` builder (code/dataset.py:49-62 runs a Python Counter over every id of the training split).  Sort + run-length
+    with the K2 kernels: segment sums of ones over the sorted ids, scattered to the dense vector; chunked so that the sort
+    workspace stays bounded for 4e7-id training matrices."""
+    _check(ids, torch.int64, "ids", contiguous=False)
+    flat = ids.reshape(-1).contiguous()
+    dev = flat.device
+    total = torch.zeros(V, 1, dtype=torch.float32, device=dev)
+    part = torch.zeros(V, 1, dtype=torch.float32, device=dev)
+    for lo in range(0, flat.numel(), chunk):
+        piece = flat[lo:lo + chunk]
+        n = piece.numel()
+        plan = DedupPlan(n, V, dev).run(piece)
+        ones = torch.ones(n, 1, dtype=torch.float32, device=dev)
+        compact = plan.reduce_rows(ones, 1)
+        if lo == 0 and n == flat.numel():
+            return plan.scatter_dense(compact, 1, total).view(-1)
+        part.zero_()
+        plan.scatter_dense(compact, 1, part)
+        add3(total, part, None, total)
+    return total.view(-1)
+
+
 # ------------------------------------------------------------------------------------------------ AdamW
 def adamw_hyper_step(hyper, step_counter, base_lr, beta1, beta2, eps, sched: int, warmup: int, total: int):
     call("map_adamw_hyper_step", hyper.data_ptr(), step_counter.data_ptr(), base_lr, beta1, beta2, eps, sched, warmup, total, _stream())

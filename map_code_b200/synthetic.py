@@ -50,8 +50,12 @@ def make_ids(sizes: List[int], n_rows: int, seed: int = 0, device="cpu", chunk: 
 
 
 def feat_count(x_train: torch.Tensor, V: int) -> torch.Tensor:
-    """dataset.py:49-62 semantics: occurrence count of every id in the training split (float32 [V])."""
-    return torch.bincount(x_train.reshape(-1).cpu(), minlength=V).float()
+    """dataset.py:49-62 semantics: occurrence count of every id in the training split (float32 [V]).  A device-resident id matrix
+    is counted on the device (ops.feat_count: sort + run-length with the K2 kernels); a host matrix with torch.bincount."""
+    if x_train.is_cuda:
+        from . import ops
+        return ops.feat_count(x_train, V)
+    return torch.bincount(x_train.reshape(-1), minlength=V).float()
 
 
 def field_ranges(sizes: List[int]) -> Tuple[torch.Tensor, torch.Tensor]:

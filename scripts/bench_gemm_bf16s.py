@@ -22,14 +22,23 @@ LEVELS = {
     "S1 mlp fwd alone (terms 6)": [(B, 1000, 1000, 0, 0, 2, 6, 3)],
     "S2 mlp fwd alone (terms 3)": [(B, 1000, 1000, 0, 0, 2, 3, 3)],
     "S3 plain 4096x1024x1024 (terms 3, no epilogue operands)": [(B, 1024, 1024, 0, 0, 0, 3, 0)],
+    "E1 relumask dgrad, no colsum, no planes": [(B, 1000, 1000, 0, 1, 4, 3, 0, False)],
+    "E2 relumask dgrad, colsum, no planes": [(B, 1000, 1000, 0, 1, 4, 3, 0, True)],
+    "E3 relumask dgrad, colsum, 2 planes": [(B, 1000, 1000, 0, 1, 4, 3, 2, True)],
+    "E4 cross fwd, 3 planes": [(B, 624, 624, 0, 0, 3, 3, 3, False)],
+    "E5 cross fwd, no planes": [(B, 624, 624, 0, 0, 3, 3, 0, False)],
+    "E6 cross_bwd dgrad, colsum, 2 planes": [(B, 624, 624, 0, 1, 7, 3, 2, True)],
+    "E7 cross_bwd dgrad, no colsum, no planes": [(B, 624, 624, 0, 1, 7, 3, 0, False)],
     "S4 plain 8192x2048x2048 (terms 3)": [(8192, 2048, 2048, 0, 0, 0, 3, 0)],
 }
 if os.environ.get("LEVELS"):
     LEVELS = {k: v for k, v in LEVELS.items() if k.split()[0] in os.environ["LEVELS"].split(",")}
 
 
-def make(M, N, K, ta, tb, epi, terms, pc):
+def make(M, N, K, ta, tb, epi, terms, pc, colsum=None):
     dev = "cuda"
+    if colsum is None:
+        colsum = epi in (4, 7)
     A = torch.randn((K, M) if ta else (M, K), device=dev)
     Bm = torch.randn((K, N) if tb else (N, K), device=dev)
     Cm = torch.empty(M, N, device=dev)
@@ -40,7 +49,8 @@ def make(M, N, K, ta, tb, epi, terms, pc):
     Bp = ops.split_planes(Bm, ops.alloc_planes(Bm.shape[0], Bm.shape[1], 3, dev))
     Cp = ops.alloc_planes(M, N, pc, dev) if pc else None
     return dict(A=A, B=Bm, C_out=Cm, M=M, N=N, K=K, trans_a=bool(ta), trans_b=bool(tb), epilogue=epi, bias=bias, aux0=a0, aux1=a1, aux_out=ao,
-                aux2=a2, acc_out=acc if epi == 7 else None, Ap=Ap, Bp=Bp, Cp=Cp, terms=terms)
+                aux2=a2, acc_out=acc if epi == 7 else None, Ap=Ap, Bp=Bp, Cp=Cp, terms=terms,
+                colsum_out=torch.zeros(N, device=dev) if colsum else None)
 
 
 def graph_time(f, reps=20):

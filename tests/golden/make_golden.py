@@ -143,6 +143,37 @@ def golden_nce_kat():
                              alias_prob=il.alias.prob.clone(), alias_alias=il.alias.alias.clone()))
 
 
+def golden_nce_batched():
+    """per_word = False: one noise draw shared by every position -> the reference takes the batched-logit path
+    (index_linear.py:108-143: a real [N,P] x [P,K] matmul) and the full-softmax ce_loss (index_linear.py:145-151) on a case
+    large enough to exercise tiling (V = 300, P = 8, N = 15 positions)."""
+    g = torch.Generator().manual_seed(21)
+    V, P, K, B, L = 300, 8, 5, 5, 3
+    with tempfile.TemporaryDirectory() as tmp:
+        fc = torch.floor(torch.pow(torch.tensor(300.0), torch.rand(V, generator=g)))
+        cfg = make_config(tmp, input_size=V, num_fields=6, proj_size=P, pt_neg_num=K, feat_count=fc)
+        il = ref.nce.IndexLinear(cfg)
+        il.emb.weight.data = torch.randn(V, P, generator=g) * 0.3
+        inp = torch.randn(B, L, P, generator=g).requires_grad_(True)
+        target = torch.randint(0, V, (B, L), generator=g)
+        noise1 = torch.randint(0, V, (1, 1, K), generator=g)
+        il.per_word = False
+        il.alias.draw = lambda *s: noise1
+        outs = {}
+        for lt in ("nce", "sampled"):
+            il.zero_grad()
+            inp.grad = None
+            il.loss_type = lt
+            loss, logits, ids = il(target, inp)
+            loss.backward()
+            outs[lt] = dict(loss=loss.detach().clone(), logits=logits.detach().clone(), ids=ids.clone(), d_input=inp.grad.clone(),
+                            d_emb=il.emb.weight.grad.clone(), d_bias=il.bias.weight.grad.clone())
+        full = il.ce_loss(target, inp.detach())
+        save("nce_batched", dict(emb=il.emb.weight.detach().clone(), bias=il.bias.weight.detach().clone(),
+                                 logprob_noise=il.logprob_noise.clone(), norm_term=il.norm_term, input=inp.detach().clone(), target=target,
+                                 noise1=noise1, out=outs, full_ce=full.detach().clone(), feat_count=fc))
+
+
 def golden_dynamic_mask():
     X = (np.arange(60).reshape(10, 6) + 100).astype(np.int64)
     cfg = ref.arguments.Config.from_dict(dict(num_fields=6, input_size=200,
@@ -281,6 +312,7 @@ if __name__ == "__main__":
     golden_alias()
     golden_nce_kat()
     golden_dynamic_mask()
+    golden_nce_batched()
     golden_model("dcnv2_mfp", "DCNv2", "MFP")
     golden_model("dcnv2_rfd", "DCNv2", "RFD")
     golden_model("deepfm_mfp", "DeepFM", "MFP")

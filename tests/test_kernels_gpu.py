@@ -815,3 +815,30 @@ def test_peer_sharded_gather_and_merge_single_process(ops, R):
         assert U == want_rows.numel() and int(n_owned) == sum(int(((uniq[s].cpu()[:int(n_dev[s])] % R) == rank).sum()) for s in range(R))
         assert torch.equal(plan.uniq[:U].cpu(), want_rows)
         torch.testing.assert_close(merged[:U].cpu(), want, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ §8(f)1: input pipeline pieces
+def test_feat_count_device_matches_bincount(ops):
+    """native feat_count builder (reference code/dataset.py:49-62: Counter over every id of the training split)"""
+    from map_code_b200 import synthetic as S
+    sizes = [max(2, s // 50) for s in S.field_sizes("criteo")]
+    V = S.vocab_size(sizes)
+    X = S.make_ids(sizes, 5000, seed=3)
+    want = torch.bincount(X.reshape(-1), minlength=V).float()
+    got = ops.feat_count(X.cuda(), V)
+    assert torch.equal(got.cpu(), want)
+    got_chunked = ops.feat_count(X.cuda(), V, chunk=40000)      # several sort chunks accumulated
+    assert torch.equal(got_chunked.cpu(), want)
+    assert torch.equal(S.feat_count(X.cuda(), V).cpu(), S.feat_count(X, V))
+
+
+def test_gather_rows_i64_bit_exact(ops):
+    """the device batcher's kernel (DeviceBatcher: shuffled row indices -> one batch of id rows)"""
+    g = torch.Generator().manual_seed(0)
+    X = torch.randint(0, 1 << 40, (3000, 39), generator=g)
+    idx = torch.randperm(3000, generator=g)[:777]
+    got = ops.gather_rows_i64(dev(X), dev(idx))
+    assert torch.equal(got.cpu(), X[idx])
+    Xs = torch.randint(0, 100, (50, 24), generator=g)
+    i2 = torch.tensor([0, 49, 49, 7, 0])
+    assert torch.equal(ops.gather_rows_i64(dev(Xs), dev(i2)).cpu(), Xs[i2])
