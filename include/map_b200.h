@@ -180,6 +180,13 @@ int map_nce_fwd(const float* input, int64_t N, int P, int K, const int64_t* targ
                 const float* emb, const float* bias, const float* logprob_noise, int64_t V, float norm_term,
                 int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos, float* dz,
                 float* d_input, int32_t* acc_count, map_stream_t stream);
+/* Full-softmax cross entropy over the whole vocabulary: replaces IndexLinear.ce_loss (code/nce/index_linear.py:145-151, the
+ * `loss_type != nce/sampled` fallback of NCELoss.forward, nce_loss.py:133-135): loss_pos[n] = logsumexp_v(<input[n], emb[v]> +
+ * bias[v]) - (<input[n], emb[target[n]]> + bias[target[n]]).  Forward only (evaluation); the [N, V] score matrix of the
+ * reference is never materialised.  P <= 64. */
+size_t map_nce_full_ce_workspace_bytes(int64_t N, int64_t V);
+int map_nce_full_ce(const float* input, int64_t N, int P, const float* emb, const float* bias, int64_t V, const int64_t* target,
+                    float* loss_pos, void* workspace, size_t workspace_bytes, map_stream_t stream);
 /* sel[n,:] = enc[(b*F + masked_index[n])*P + :], n = b*L + l   (torch.gather of the masked slices, models.py:75) */
 int map_gather_slices(const float* enc, const int64_t* masked_index, int64_t N, int L, int F, int P, float* sel,
                       map_stream_t stream);

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "map_alias_build": (_i, [_p, _l, _p, _p]),
     "map_alias_draw_philox": (_i, [_p, _p, _l, _u64, _u64, _l, _l, _p, _p, _p]),
     "map_nce_fwd": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p, _l, _f, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "map_nce_full_ce_workspace_bytes": (_sz, [_l, _l]),
+    "map_nce_full_ce": (_i, [_p, _l, _i, _p, _p, _l, _p, _p, _p, _sz, _p]),
     "map_gather_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
     "map_scatter_add_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
     "map_reduce_sum_f32": (_i, [_p, _l, _f, _p, _p, _sz, _p]),
@@ -159,7 +161,7 @@ def last_error() -> str:
 # number of kernels one entry point launches (for the `gpu_launches` figure of bench.py)
 KERNELS_PER_CALL = {
     "map_segment_reduce_rows_ex": 2, "map_p2p_alloc": 0, "map_p2p_open": 0, "map_p2p_close": 0, "map_p2p_free": 0,
-    "map_segment_reduce_rows": 2, "map_reduce_sum_f32": 2, "map_bce_logits_fwd": 2, "map_colsum_f32": 2,
+    "map_segment_reduce_rows": 2, "map_reduce_sum_f32": 2, "map_bce_logits_fwd": 2, "map_colsum_f32": 2, "map_nce_full_ce": 2,
     "map_alias_build": 0,
 }
 PROFILE = None        # set to a list: every call is bracketed by CUDA events -> (name, tag, start_event, end_event)

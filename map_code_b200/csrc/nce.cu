@@ -314,3 +314,148 @@ extern "C" int map_scatter_add_slices(const float* d_input, const int64_t* maske
     scatter_add_slices_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_input, masked_index, N, L, F, P, d_enc);
     return check_launch("map_scatter_add_slices");
 }
+
+// ------------------------------------------------------------------------------------------------ full-softmax cross entropy
+// IndexLinear.ce_loss (code/nce/index_linear.py:145-151): score = F.linear(input, emb.weight, bias) over the WHOLE vocabulary,
+// loss[n] = logsumexp_v(score[n, v]) - score[n, target[n]].  The reference materialises score [N, V] (53 GB at N = 12288,
+// V = 1.09 M); here the scores never leave the SM: a CTA owns 64 positions and one slice of the vocabulary, computes 64 x 64
+// score tiles (register-tiled fp32 FMAs, both operand tiles transposed in shared memory) and folds them into a running
+// (max, sum of exp) per position; a second kernel merges the vocabulary slices and subtracts the target's score.
+namespace mapb {
+
+constexpr int kCeTile = 64;     // positions per CTA and vocabulary rows per tile
+constexpr int kCeMaxP = 64;
+
+__global__ void __launch_bounds__(256) nce_full_ce_partial_kernel(const float* __restrict__ input, int64_t N, int P,
+                                                                  const float* __restrict__ emb, const float* __restrict__ bias,
+                                                                  int64_t V, int64_t rows_per_split, float2* __restrict__ partial,
+                                                                  int n_splits) {
+    __shared__ float xs[kCeMaxP][kCeTile + 1];   // xs[k][position]
+    __shared__ float es[kCeMaxP][kCeTile + 1];   // es[k][vocabulary row]
+    __shared__ float bs[kCeTile];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 x 16 threads, 4 x 4 scores each
+    const int64_t n0 = (int64_t)blockIdx.x * kCeTile;
+    const int split = blockIdx.y;
+    const int64_t v_begin = (int64_t)split * rows_per_split;
+    int64_t v_end = v_begin + rows_per_split;
+    if (v_end > V) v_end = V;
+    for (int e = threadIdx.x; e < kCeTile * P; e += 256) {
+        const int r = e / P, k = e - r * P;
+        xs[k][r] = (n0 + r < N) ? input[(n0 + r) * P + k] : 0.f;
+    }
+    float m[4], s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; s[i] = 0.f; }
+    for (int64_t v0 = v_begin; v0 < v_end; v0 += kCeTile) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < kCeTile * P; e += 256) {
+            const int r = e / P, k = e - r * P;
+            es[k][r] = (v0 + r < v_end) ? __ldg(emb + (v0 + r) * P + k) : 0.f;
+        }
+        if (threadIdx.x < kCeTile) bs[threadIdx.x] = (v0 + threadIdx.x < v_end) ? __ldg(bias + v0 + threadIdx.x) : -INFINITY;
+        __syncthreads();
+        float acc[4][4] = {};
+        for (int k = 0; k < P; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = xs[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = es[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float tile_max = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[i][j] += bs[tx * 4 + j];     // rows past the end carry bias = -inf: exp() = 0
+                tile_max = fmaxf(tile_max, acc[i][j]);
+            }
+            const float m_new = fmaxf(m[i], tile_max);
+            if (m_new > -INFINITY) {
+                float add = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) add += __expf(acc[i][j] - m_new);
+                s[i] = s[i] * __expf(m[i] - m_new) + add;
+                m[i] = m_new;
+            }
+        }
+    }
+    // the 16 threads that share a position (same ty: one half warp) merge their running pairs
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m[i], o, 16);
+            const float s2 = __shfl_xor_sync(0xffffffffu, s[i], o, 16);
+            const float mn = fmaxf(m[i], m2);
+            if (mn > -INFINITY) {
+                s[i] = s[i] * __expf(m[i] - mn) + s2 * __expf(m2 - mn);
+                m[i] = mn;
+            }
+        }
+        const int64_t n = n0 + ty * 4 + i;
+        if (tx == 0 && n < N) partial[n * n_splits + split] = make_float2(m[i], s[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) nce_full_ce_merge_kernel(const float* __restrict__ input, int64_t N, int P,
+                                                                const float* __restrict__ emb, const float* __restrict__ bias,
+                                                                int64_t V, const int64_t* __restrict__ target,
+                                                                const float2* __restrict__ partial, int n_splits, float* __restrict__ loss_pos) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float m = -INFINITY;
+    for (int sp = 0; sp < n_splits; ++sp) m = fmaxf(m, partial[n * n_splits + sp].x);
+    float sum = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) {
+        const float2 p = partial[n * n_splits + sp];
+        if (p.x > -INFINITY) sum += p.y * expf(p.x - m);
+    }
+    const int64_t t = target[n];
+    float score = (t >= 0 && t < V) ? bias[t] : 0.f;
+    if (t >= 0 && t < V)
+        for (int k = 0; k < P; ++k) score = fmaf(input[n * P + k], emb[t * P + k], score);
+    loss_pos[n] = m + logf(sum) - score;
+}
+
+static int ce_splits(int64_t N, int64_t V) {
+    const int64_t pos_tiles = ceil_div(N, kCeTile);
+    int64_t splits = ceil_div((int64_t)kNumSMs * 4, pos_tiles);
+    const int64_t max_splits = ceil_div(V, kCeTile);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 4096) splits = 4096;
+    return (int)splits;
+}
+
+}  // namespace mapb
+
+extern "C" size_t map_nce_full_ce_workspace_bytes(int64_t N, int64_t V) {
+    return (size_t)N * (size_t)mapb::ce_splits(N, V) * sizeof(float2);
+}
+
+extern "C" int map_nce_full_ce(const float* input, int64_t N, int P, const float* emb, const float* bias, int64_t V,
+                               const int64_t* target, float* loss_pos, void* workspace, size_t workspace_bytes, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(input && emb && bias && target && loss_pos && workspace, "map_nce_full_ce: null pointer");
+    MAP_REQUIRE(N >= 0 && V >= 1 && P >= 1 && P <= kCeMaxP, "map_nce_full_ce: bad shape N=%lld V=%lld P=%d (P <= %d)", (long long)N,
+                (long long)V, P, kCeMaxP);
+    if (N == 0) return MAP_OK;
+    const int splits = ce_splits(N, V);
+    if (workspace_bytes < (size_t)N * splits * sizeof(float2)) {
+        set_error("map_nce_full_ce: workspace %zu < %zu", workspace_bytes, (size_t)N * splits * sizeof(float2));
+        return MAP_EWORKSPACE;
+    }
+    int64_t rows_per_split = ceil_div(V, splits);
+    rows_per_split = ceil_div(rows_per_split, kCeTile) * kCeTile;
+    dim3 grid((unsigned)ceil_div(N, kCeTile), (unsigned)splits);
+    cudaStream_t st = as_stream(stream);
+    nce_full_ce_partial_kernel<<<grid, 256, 0, st>>>(input, N, P, emb, bias, V, rows_per_split, static_cast<float2*>(workspace), splits);
+    nce_full_ce_merge_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(input, N, P, emb, bias, V, target, static_cast<const float2*>(workspace),
+                                                                         splits, loss_pos);
+    return check_launch("map_nce_full_ce");
+}

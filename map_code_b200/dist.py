@@ -130,6 +130,7 @@ class CollectiveShardedFusedStep(FusedStep):
         V = param.shape[0]
         self._full_shapes[name] = V
         param.data = shard_table(param.data, self.world, self.rank)
+        param._map_sharded = (self.world, self.rank, V)   # the module path refuses to read a shard (layers.TableEmbedding.forward)
 
     def _make_embed_table(self):
         name = "embed.embedding.weight"
@@ -381,6 +382,7 @@ class ShardedFusedStep(FusedStep):
         buf = self.pm.alloc((rows, D), torch.float32)
         buf.local.copy_(shard_table(param.data, self.world, self.rank))
         param.data = buf.local
+        param._map_sharded = (self.world, self.rank, V)   # the module path refuses to read a shard (layers.TableEmbedding.forward)
         return buf
 
     def _peer_table(self, name, param, n_ids, plan):

@@ -68,6 +68,12 @@ class TableEmbedding(nn.Module):
         self.weight._map_table_grad = self.table_grad
 
     def forward(self, input_ids):
+        if getattr(self.weight, "_map_sharded", None) is not None:
+            # a sharded engine re-pointed this parameter at ONE rank's [V/R + 1, D] shard: a local gather would silently return
+            # the wrong rows (the reference would raise an IndexError here)
+            from . import _lib
+            raise _lib.MapB200Error("this table is row-sharded over %d ranks: the module path cannot read it; use the sharded fused step "
+                                    "(and full_state_dict() to export the reference layout)" % self.weight._map_sharded[0])
         return Fn.EmbeddingFn.apply(self.weight, input_ids, self.table_grad)
 
     def _apply(self, fn, recurse=True):

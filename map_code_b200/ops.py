@@ -397,6 +397,25 @@ def auc_logloss(logits: torch.Tensor, labels: torch.Tensor):
     return auc, stats[0].double()
 
 
+def nce_full_ce(inp: torch.Tensor, emb: torch.Tensor, bias: torch.Tensor, target: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """per-position full-softmax cross entropy (IndexLinear.ce_loss, index_linear.py:145-151): inp [N,P], emb [V,P], bias [V] or [V,1],
+    target [N] -> [N].  The [N, V] scores stay on chip (online log-sum-exp over vocabulary slices)."""
+    _check(inp, torch.float32, "input")
+    _check(emb, torch.float32, "emb")
+    _check(target, torch.int64, "target")
+    N, P = inp.shape
+    V = emb.shape[0]
+    bias = bias.reshape(-1)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=inp.device)
+    lib = _lib.load()
+    ws_bytes = int(lib.map_nce_full_ce_workspace_bytes(N, V))
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=inp.device)
+    call("map_nce_full_ce", inp.data_ptr(), N, P, emb.data_ptr(), bias.data_ptr(), V, target.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+         _stream())
+    return out
+
+
 def fm_lr_fwd(feat_embed, ids, lr_w, lr_bias, out=None, ld_out: int = 1):
     B, F, D = feat_embed.shape
     if out is None:

@@ -53,7 +53,10 @@ class DeviceBatcher:
     """Device-resident replacement of DataLoader(shuffle=...) over OurDataset (trainer.py:51-58, dataset.py:78-87): the id
     matrix lives in HBM, an epoch is a permutation of row indices, a batch is one gather kernel."""
 
-    def __init__(self, X, Y, batch_size: int, shuffle: bool, device, seed: int = 0):
+    def __init__(self, X, Y, batch_size: int, shuffle: bool, device, seed: int = 0, rank: int = 0, world: int = 1):
+        """rank / world: data-parallel runs see the SAME permutation on every rank (same seed) and take disjoint slices of every
+        global batch of batch_size * world rows; the ragged tail of an epoch is dropped there (every rank must step together)."""
+        self.rank, self.world = rank, world
         self.X = torch.as_tensor(np.ascontiguousarray(X) if isinstance(X, np.ndarray) else X).to(device=device, dtype=torch.int64).contiguous()
         self.Y = None if Y is None else torch.as_tensor(np.ascontiguousarray(Y) if isinstance(Y, np.ndarray) else Y).to(device=device)
         self.batch_size, self.shuffle = batch_size, shuffle
@@ -61,6 +64,8 @@ class DeviceBatcher:
         self.dataset = self
 
     def __len__(self):  # number of batches, like len(DataLoader) with drop_last=False
+        if self.world > 1:
+            return self.X.shape[0] // (self.batch_size * self.world)
         return (self.X.shape[0] + self.batch_size - 1) // self.batch_size
 
     def num_rows(self):
@@ -69,6 +74,12 @@ class DeviceBatcher:
     def __iter__(self):
         n = self.X.shape[0]
         order = (torch.randperm(n, generator=self.gen) if self.shuffle else torch.arange(n)).to(self.X.device)
+        if self.world > 1:
+            gb = self.batch_size * self.world
+            for i in range(0, n - gb + 1, gb):
+                idx = order[i + self.rank * self.batch_size:i + (self.rank + 1) * self.batch_size]
+                yield ops.gather_rows_i64(self.X, idx), (self.Y[idx] if self.Y is not None else None)
+            return
         for i in range(0, n, self.batch_size):
             idx = order[i:i + self.batch_size]
             xb = ops.gather_rows_i64(self.X, idx)
@@ -113,7 +124,10 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------ data
     def get_dataloader(self, dataset, is_training=True):
         bs = self.args.per_gpu_train_batch_size if is_training else self.args.per_gpu_eval_batch_size
-        return DeviceBatcher(dataset.X, getattr(dataset, "Y", None), bs, shuffle=is_training, device=self.device, seed=self.args.seed)
+        eng = self._fused
+        world, rank = (getattr(eng, "world", 1), getattr(eng, "rank", 0)) if (eng is not None and is_training) else (1, 0)
+        return DeviceBatcher(dataset.X, getattr(dataset, "Y", None), bs, shuffle=is_training, device=self.device, seed=self.args.seed,
+                             rank=rank, world=world)
 
     def _train_matrix(self):
         if self._x_train_dev is None and self.train_dataset is not None:
@@ -327,9 +341,14 @@ class Trainer:
                     logger.info(f"step = {self.global_step}, {str(_log)}")
                     win_loss.zero_(); win_acc.zero_(); win_n = 0
                     start_time = time.time()
-            if a.local_rank in [-1, 0]:
+            sharded = self._fused is not None and getattr(self._fused, "world", 1) > 1
+            if sharded:
+                logger.info("per-epoch eval skipped: the tables are row-sharded (the module path cannot read a shard)")
+            elif a.local_rank in [-1, 0]:
                 self.MFP_pretrain_eval() if kind == "MFP" else self.RFD_pretrain_eval()
-        if a.local_rank in [-1, 0]:
+        if self._fused is not None and getattr(self._fused, "world", 1) > 1:
+            self.save_model(a.output_dir)      # collective: every rank takes part, rank 0 writes
+        elif a.local_rank in [-1, 0]:
             self.save_model(a.output_dir)
 
     def MFP_pretrain(self):
@@ -453,8 +472,17 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------ checkpoints
     def save_model(self, model_dir):
         """trainer.py:517-519: torch.save(state_dict) to {model_dir}/{global_step}.model (reference key names)."""
+        eng = self._fused
+        if eng is not None and getattr(eng, "world", 1) > 1:
+            # row-sharded tables: a COLLECTIVE (every rank calls save_model); shards are gathered to the reference's [V, D] layout and
+            # rank 0 writes the file, so the checkpoint loads into the reference and into load_for_finetune
+            sd = eng.full_state_dict()
+            if eng.rank != 0:
+                return
+        else:
+            sd = self.model.state_dict()
         os.makedirs(model_dir, exist_ok=True)
-        torch.save({k: v.detach().cpu() for k, v in self.model.state_dict().items()}, os.path.join(model_dir, "{}.model".format(self.global_step)))
+        torch.save({k: v.detach().cpu() for k, v in sd.items()}, os.path.join(model_dir, "{}.model".format(self.global_step)))
 
     def load_model(self, load_step, model_dir):
         state_dict = torch.load(os.path.join(model_dir, "{}.model".format(load_step)), map_location="cpu")

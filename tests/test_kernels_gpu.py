@@ -842,3 +842,64 @@ def test_gather_rows_i64_bit_exact(ops):
     Xs = torch.randint(0, 100, (50, 24), generator=g)
     i2 = torch.tensor([0, 49, 49, 7, 0])
     assert torch.equal(ops.gather_rows_i64(dev(Xs), dev(i2)).cpu(), Xs[i2])
+
+
+# ------------------------------------------------------------------------------------------------ §8(f)3: other NCE modes
+def _index_linear_from_golden(g, V, P, K):
+    from map_code_b200.arguments import Config
+    from map_code_b200.nce import IndexLinear
+    cfg = Config.from_dict(dict(input_size=V, num_fields=6, proj_size=P, pt_neg_num=K, feat_count=g["feat_count"], data_dir=None, seed=42,
+                                table_grad_mode="dense"))
+    il = IndexLinear(cfg).cuda()
+    with torch.no_grad():
+        il.emb.weight.copy_(g["emb"])
+        il.bias.weight.copy_(g["bias"])
+    assert torch.allclose(il.logprob_noise.cpu(), g["logprob_noise"], rtol=1e-6, atol=1e-7)   # NCELoss.__init__ (nce_loss.py:55-77)
+    assert abs(il.norm_term - g["norm_term"]) < 1e-12
+    return il
+
+
+def test_nce_full_softmax_ce_vs_reference(golden):
+    """IndexLinear.ce_loss (index_linear.py:145-151) against the reference's own output (V = 300) and its KAT (V = 16)"""
+    from map_code_b200 import ops
+    g = golden("nce_batched")
+    got = ops.nce_full_ce(dev(g["input"].reshape(-1, 8)), dev(g["emb"]), dev(g["bias"]), dev(g["target"].reshape(-1)))
+    torch.testing.assert_close(got.cpu().view_as(g["full_ce"]), g["full_ce"], rtol=2e-5, atol=2e-6)
+    k = golden("nce_kat")
+    got = ops.nce_full_ce(dev(k["input"].reshape(-1, 4)), dev(k["emb"]), dev(k["bias"]), dev(k["target"].reshape(-1)))
+    torch.testing.assert_close(got.cpu().view_as(k["full_ce"]), k["full_ce"], rtol=2e-5, atol=2e-6)
+    il = _index_linear_from_golden(g, 300, 8, 5)
+    torch.testing.assert_close(il.ce_loss(dev(g["target"]), dev(g["input"])).cpu(), g["full_ce"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("N,V,P", [(1, 7, 4), (130, 5000, 32), (777, 70001, 32), (64, 64, 64)])
+def test_nce_full_softmax_ce_vs_torch(ops, N, V, P):
+    gen = torch.Generator().manual_seed(N + V)
+    x = torch.randn(N, P, generator=gen)
+    emb = torch.randn(V, P, generator=gen) * 0.5
+    bias = torch.randn(V, generator=gen)
+    tgt = torch.randint(0, V, (N,), generator=gen)
+    want = torch.nn.functional.cross_entropy(x.double() @ emb.double().t() + bias.double(), tgt, reduction="none")
+    got = ops.nce_full_ce(dev(x), dev(emb), dev(bias), dev(tgt))
+    torch.testing.assert_close(got.cpu().double(), want, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("loss_type", ["nce", "sampled"])
+def test_nce_shared_noise_batched_vs_reference(golden, loss_type):
+    """per_word = False: one noise draw shared by every position.  The reference switches to its batched-logit path
+    (index_linear.py:108-143: matmul against the K gathered rows); here the same fused kernel reads the expanded noise (the K rows
+    stay in L1/L2).  Loss, logits, ids and all three gradients against the reference's own run."""
+    g = golden("nce_batched")
+    il = _index_linear_from_golden(g, 300, 8, 5)
+    il.per_word, il.loss_type = False, loss_type
+    il.alias.draw = lambda *s: dev(g["noise1"])
+    inp = dev(g["input"]).requires_grad_(True)
+    loss, logits, ids = il(dev(g["target"]), inp)
+    loss.backward()
+    o = g["out"][loss_type]
+    torch.testing.assert_close(loss.detach().cpu(), o["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits.detach().cpu(), o["logits"], rtol=1e-5, atol=1e-5)
+    assert torch.equal(ids.cpu(), o["ids"])
+    torch.testing.assert_close(inp.grad.cpu(), o["d_input"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(il.emb.weight.grad.cpu(), o["d_emb"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(il.bias.weight.grad.cpu(), o["d_bias"], rtol=1e-5, atol=1e-7)

@@ -182,3 +182,22 @@ def test_ragged_last_batch_keeps_one_optimizer_state(model_name, pt_type, pretra
         assert torch.allclose(sd1[k].float(), sd2[k].float(), rtol=1e-5, atol=1e-7), k
     # and the tail step really moved the dense parameters with step-4 bias corrections (not a fresh t=1 optimizer)
     assert float(eng.hyper[0].item()) < 1e-3  # cosine LR near the end of the 4-step schedule, not the base LR
+
+
+def test_device_batcher_rank_slices_partition_the_global_batch():
+    """data-parallel batching: same permutation on every rank, disjoint per-rank slices of every global batch, ragged tail
+    dropped; and the module path refuses to read a row-sharded table."""
+    from map_code_b200.trainer import DeviceBatcher
+    X = torch.arange(1000 * 3).view(1000, 3)
+    single = [xb.cpu() for xb, _ in DeviceBatcher(X, None, 128, True, "cuda", seed=5)]
+    r0 = [xb.cpu() for xb, _ in DeviceBatcher(X, None, 64, True, "cuda", seed=5, rank=0, world=2)]
+    r1 = [xb.cpu() for xb, _ in DeviceBatcher(X, None, 64, True, "cuda", seed=5, rank=1, world=2)]
+    assert len(r0) == len(r1) == 1000 // 128 == len(DeviceBatcher(X, None, 64, True, "cuda", seed=5, rank=1, world=2))
+    for i in range(len(r0)):
+        assert torch.equal(torch.cat([r0[i], r1[i]]), single[i])
+    from map_code_b200 import _lib
+    from map_code_b200.layers import TableEmbedding
+    t = TableEmbedding(10, 4).cuda()
+    t.weight._map_sharded = (2, 0, 10)
+    with pytest.raises(_lib.MapB200Error):
+        t(torch.zeros(3, dtype=torch.int64, device="cuda"))
