@@ -180,6 +180,11 @@ int map_nce_fwd(const float* input, int64_t N, int P, int K, const int64_t* targ
                 const float* emb, const float* bias, const float* logprob_noise, int64_t V, float norm_term,
                 int loss_type, float grad_scale, float* logits, int64_t* ids_out, float* loss_pos, float* dz,
                 float* d_input, int32_t* acc_count, map_stream_t stream);
+/* The backward of the slice gather as a DENSE, deterministic pass: d_enc[b, f*P + p] = sum_{l: masked_index[b,l] == f} d_input[b,l,p]
+ * (zero elsewhere) for every element of d_enc [B, F*P] — no pre-zeroing, no atomics (map_scatter_add_slices needs both);
+ * optionally also the bf16 planes of d_enc (operand format of map_gemm_bf16s_group).  P % 4 == 0. */
+int map_expand_slices(const float* d_input, const int64_t* masked_index, int64_t B, int L, int F, int P, float* d_enc, int64_t ld_enc,
+                      uint16_t* planes, int64_t ld_p, int64_t plane_stride, int n_planes, map_stream_t stream);
 /* Full-softmax cross entropy over the whole vocabulary: replaces IndexLinear.ce_loss (code/nce/index_linear.py:145-151, the
  * `loss_type != nce/sampled` fallback of NCELoss.forward, nce_loss.py:133-135): loss_pos[n] = logsumexp_v(<input[n], emb[v]> +
  * bias[v]) - (<input[n], emb[target[n]]> + bias[target[n]]).  Forward only (evaluation); the [N, V] score matrix of the

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "map_alias_build": (_i, [_p, _l, _p, _p]),
     "map_alias_draw_philox": (_i, [_p, _p, _l, _u64, _u64, _l, _l, _p, _p, _p]),
     "map_nce_fwd": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p, _l, _f, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "map_expand_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _l, _p, _l, _l, _i, _p]),
     "map_nce_full_ce_workspace_bytes": (_sz, [_l, _l]),
     "map_nce_full_ce": (_i, [_p, _l, _i, _p, _p, _l, _p, _p, _p, _sz, _p]),
     "map_gather_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),

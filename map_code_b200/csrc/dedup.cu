@@ -2,6 +2,8 @@
 //   radix sort (id, occurrence)  ->  unique ids + segment starts  ->  segmented row sums.
 // Replaces aten::embedding_dense_backward (thrust sort + dense [V,D] grad) behind code/layers.py:98 and the dense
 // index_add behind code/nce/index_linear.py:99-100.  Everything is integer / HBM-L2 bound; no tensor cores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mapb {
@@ -617,7 +619,16 @@ struct DedupLayout {
 static DedupLayout dedup_layout(int64_t n) {
     DedupLayout L;
     const int64_t ntiles = ceil_div(n > 0 ? n : 1, kSortTile);
-    L.persist_ctas = ntiles < kPersistMaxCtas ? (int)ntiles : kPersistMaxCtas;
+    // MAP_B200_DEDUP_CTAS caps the persistent grid: beside the one-CTA-per-SM persistent GEMMs a sort that wants every SM would
+    // spin at its grid barriers on the SMs it got while the rest of its CTAs wait for a GEMM launch to end (and the next GEMM
+    // launch waits for the spinning ones); a small grid fits on the SMs the GEMMs leave free (MAP_B200_GEMM_CLUSTERS)
+    static int cap = -1;
+    if (cap < 0) {
+        const char* e = getenv("MAP_B200_DEDUP_CTAS");
+        cap = (e != nullptr && atoi(e) >= 1) ? atoi(e) : kPersistMaxCtas;
+        if (cap > kPersistMaxCtas) cap = kPersistMaxCtas;
+    }
+    L.persist_ctas = ntiles < cap ? (int)ntiles : cap;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     L.keys_a = off; off += align((size_t)n * 4);

@@ -3,6 +3,8 @@
 // The "contraction" is a gather-dot (every position owns its K+1 rows): HBM/L2-bound, no tensor cores.
 // One warp per position; LANES = P/4 lanes own one gathered row (16-byte loads), 32/LANES rows in flight per step.
 // Forward and the input-side backward are produced in the same pass while the rows are in registers.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mapb {
@@ -207,6 +209,42 @@ __global__ void __launch_bounds__(256) scatter_add_slices_kernel(const float* __
     }
 }
 
+// The same scatter written as a DENSE pass over d_enc [B, F*P]: every output element is produced exactly once (sum over the l with
+// masked_index[b, l] == f, zero elsewhere), so there is no pre-zeroing, no atomics and the result is deterministic; the optional
+// bf16 planes (hi, lo) of d_enc — the operand format of the split-bf16 GEMMs that consume it — come out of the same pass.
+__global__ void __launch_bounds__(256) expand_slices_kernel(const float* __restrict__ d_sel, const int64_t* __restrict__ mi, int64_t B, int L,
+                                                            int F, int P4, float* __restrict__ d_enc, int64_t ld_enc,
+                                                            uint32_t* __restrict__ planes, int64_t ld_p2, int64_t plane_stride2, int n_planes) {
+    const int64_t per_row = (int64_t)F * P4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < B * per_row; e += stride) {
+        const int64_t b = e / per_row;
+        const int r = (int)(e - b * per_row);
+        const int f = r / P4, p4 = r - f * P4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < L; ++l)
+            if (__ldg(mi + b * L + l) == f) {
+                const float4 a = *reinterpret_cast<const float4*>(d_sel + ((b * L + l) * P4 + p4) * 4);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+        *reinterpret_cast<float4*>(d_enc + b * ld_enc + (int64_t)r * 4) = v;
+        if (planes != nullptr) {
+            float r0 = v.x, r1 = v.y, r2 = v.z, r3 = v.w;
+            uint32_t* dst = planes + b * ld_p2 + (int64_t)r * 2;
+            for (int pl = 0; pl < n_planes; ++pl) {
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(r0, r1), h23 = __floats2bfloat162_rn(r2, r3);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(dst) = pk;
+                r0 -= __uint_as_float(pk.x << 16); r1 -= __uint_as_float(pk.x & 0xFFFF0000u);
+                r2 -= __uint_as_float(pk.y << 16); r3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+                dst += plane_stride2;
+            }
+        }
+    }
+}
+
 // ids[n, 0] = target[n], ids[n, 1 + k] = noise[n, k]: the id list of the NCE tables' gradient (what nce_fwd also emits as ids_out),
 // available as soon as the noise is drawn so that its sort can start before the forward pass
 __global__ void __launch_bounds__(256) nce_ids_concat_kernel(const int64_t* __restrict__ target, const int64_t* __restrict__ noise,
@@ -313,6 +351,21 @@ extern "C" int map_scatter_add_slices(const float* d_input, const int64_t* maske
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     scatter_add_slices_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_input, masked_index, N, L, F, P, d_enc);
     return check_launch("map_scatter_add_slices");
+}
+
+extern "C" int map_expand_slices(const float* d_input, const int64_t* masked_index, int64_t B, int L, int F, int P, float* d_enc,
+                                 int64_t ld_enc, uint16_t* planes, int64_t ld_p, int64_t plane_stride, int n_planes, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(d_input && masked_index && d_enc && L >= 1 && F >= 1 && P >= 4 && P % 4 == 0 && B >= 0, "map_expand_slices: bad argument (P % 4 == 0)");
+    MAP_REQUIRE(ld_enc % 4 == 0 && ((uintptr_t)d_enc & 15) == 0 && ((uintptr_t)d_input & 15) == 0, "map_expand_slices: alignment");
+    MAP_REQUIRE(planes == nullptr || (n_planes >= 1 && n_planes <= 3 && ld_p % 4 == 0 && plane_stride % 4 == 0 && ((uintptr_t)planes & 7) == 0),
+                "map_expand_slices: planes alignment");
+    if (B == 0) return MAP_OK;
+    int64_t blocks = ceil_div(B * F * (P / 4), 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    expand_slices_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_input, masked_index, B, L, F, P / 4, d_enc, ld_enc,
+                                                                           reinterpret_cast<uint32_t*>(planes), ld_p / 2, plane_stride / 2, n_planes);
+    return check_launch("map_expand_slices");
 }
 
 // ------------------------------------------------------------------------------------------------ full-softmax cross entropy

@@ -109,6 +109,9 @@ class FusedStep:
         self.overrides = None
         # Independent branches of the step (MLP tower vs CrossNet, weight gradients vs the dgrad chain, table sorts vs
         # GEMMs) are issued on side streams; under capture they become parallel branches of the CUDA graph.
+        import os as _os2
+        if _os2.environ.get("MAP_B200_SINGLE_STREAM") == "1":   # A/B switch: the whole step on one stream (no side branches)
+            multi_stream = False
         self.multi_stream = multi_stream
         # The table stream ('tab') has NORMAL priority.  While the sort was 13 tiny launches, high priority let them slip in
         # between GEMM waves; with the single-launch sort (persistent CTAs that spin at grid barriers) high priority takes SM
@@ -490,7 +493,8 @@ class FusedStep:
     def _draw_noise(self):
         if self.mode != "MFP":
             return
-        self.d_enc.zero_()   # (20 MB memset for the backward of the slice gather: off the critical path here)
+        if self.P % 4 != 0:
+            self.d_enc.zero_()   # (memset for the atomic form of the slice scatter; proj sizes that are multiples of 4 need none)
         crit = self.model.mfp_criterion
         if self.overrides is not None and "noise" in self.overrides:
             self.noise.copy_(self.overrides["noise"].reshape(self.N, self.K))
@@ -650,8 +654,11 @@ class FusedStep:
         self._join("tab")  # noise drawn on the 'tab' stream
         self._nce_core()
         # ---- backward of the encoder (d_enc was zeroed on the 'tab' stream at the start of the step)
-        ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
-        self._split(self.d_enc, self.d_encp)
+        if P % 4 == 0:   # dense, deterministic pass: writes every element of d_enc (and its planes) once; no memset, no atomics
+            ops.expand_slices(self.d_sel, self.mi, F, P, self.d_enc, self.d_encp)
+        else:
+            ops.scatter_add_slices(self.d_sel, self.mi, F, P, self.d_enc)
+            self._split(self.d_enc, self.d_encp)
         self._fork("dw")
         with self._on("dw"):   # bias gradient of the encoder: off the critical path
             ops.colsum(self.d_enc, out=self.grads["feat_encoder.bias"], ws=self.colsum_ws)

@@ -343,6 +343,14 @@ def scatter_add_slices(d_sel: torch.Tensor, masked_index: torch.Tensor, F: int, 
     return d_enc
 
 
+def expand_slices(d_sel: torch.Tensor, masked_index: torch.Tensor, F: int, P: int, d_enc: torch.Tensor, planes: Optional[torch.Tensor] = None):
+    """d_enc [B, F*P] <- dense form of the slice scatter (every element written once; no memset, no atomics) + its bf16 planes"""
+    B, L = masked_index.shape
+    pl = (planes.data_ptr(), planes.stride(1), planes.stride(0), planes.shape[0]) if planes is not None else (None, 0, 0, 0)
+    call("map_expand_slices", d_sel.data_ptr(), masked_index.data_ptr(), B, L, F, P, d_enc.data_ptr(), _ld(d_enc), *pl, _stream())
+    return d_enc
+
+
 _red_ws = {}
 
 
