@@ -212,6 +212,12 @@ def algorithmic(tag):
     if kind == "sparse_adamw":
         _, n, d = tag
         return n * (8 + 7 * 4 * d), 0.0
+    if kind in ("field_enc_fwd", "field_enc_dgrad", "field_enc_wgrad"):   # by-field encoder: N positions x P outputs x K inputs
+        _, N, Pn, Kd = tag   # gathered rows of `final` (or the per-position gradient rows) dominate the traffic
+        return 4.0 * N * (Kd + Pn), 2.0 * N * Pn * Kd
+    if kind == "head_bwd_fold":   # L partial rows read, ~4 fp32 rows + operand planes written per sample
+        _, Bn, Ln, nc = tag
+        return 4.0 * Bn * nc * (Ln + 5), 0.0
     if kind == "dedup":   # ids read once + (key, value) read and written per 8-bit radix pass
         _, n, bits = tag
         return n * (8 + 4 * 4 * ((bits + 7) // 8)), 0.0
@@ -733,6 +739,7 @@ def main_ours(args):
     # ---- beside the headline (single GPU, default run only): the reference algorithm as torch eager on this GPU, and the other
     # configurations north_star names, each device-timed for a bounded number of steps
     gpu_ref, secondary = None, None
+    field_enc_used = getattr(eng, "field_enc", False)
     if world == 1 and not args.no_secondary and WORKLOAD != "c5":
         del eng, trainer
         run.eng = run.trainer = run.model = None
@@ -748,6 +755,8 @@ def main_ours(args):
                     (f"c2 DCNv2 {args.task} mask_ratio {MASK_RATIO:g} dense_exact (the reference's optimizer semantics on every table row)", args.task, "dense_exact", MASK_RATIO, None),
                     (f"c2 DCNv2 {args.task} mask_ratio 0.3 sparse (the reference's own run scripts)", args.task, "sparse", 0.3, None),
                     (f"c2 DCNv2 {args.task} mask_ratio {MASK_RATIO:g} sparse, TF32 single-pass GEMMs (fails the 1e-3 gradient tolerance: A/B only)", args.task, "sparse", MASK_RATIO, {"MAP_B200_GEMM": "tf32"})]
+            if args.task == "MFP":
+                plan.append((f"c2 DCNv2 MFP mask_ratio {MASK_RATIO:g} sparse, dense encoder GEMM over all fields + gather (A/B of the by-field encoder)", "MFP", "sparse", MASK_RATIO, {"MAP_B200_FIELD_ENC": "0"}))
             for name, task_, mode_, ratio_, env_ in plan:
                 try:
                     secondary[name] = quick_measure(task_, mode_, ratio_, args.batch, dev, run.data, env=env_)
@@ -763,6 +772,7 @@ def main_ours(args):
         "vs_baseline": None, "dtype": DTYPE_NOTE[gemm_backend_name()], "data": "synthetic",
         "config": shared_config(args.task, args.batch, world),
         "impl_detail": {"gemm_backend": gemm_backend_name(), "optimizer_mode": args.optimizer_mode, "cuda_graph": not args.no_graph,
+                        "mfp_encoder": ({"hybrid": "by field (only the L masked slices, csrc/fieldenc.cu): forward + weight gradient; input gradient as dense GEMMs", "full": "by field: forward, dgrad, wgrad"}[field_enc_used] if field_enc_used else "dense [B, F*P] GEMM + gather") if args.task == "MFP" else None,
                         "parallelism": "single GPU" if world == 1 else f"tables row-sharded by id mod {world} in NVLink peer memory (remote rows read directly by the gather / NCE kernels, owners pull gradients); dense params replicated + NCCL all-reduce",
                         "simt_gemm_calls_per_step": {f"{k[0]}x{k[1]}x{k[2]}": v for k, v in simt_per_step.items()}},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": args.batch * n_fields * 8, "d2h_bytes_per_step": 4,

@@ -198,6 +198,54 @@ int map_gather_slices(const float* enc, const int64_t* masked_index, int64_t N, 
 /* d_enc[(b*F + masked_index[n])*P + :] += d_input[n, :]   (autograd of torch.gather, models.py:75; d_enc pre-zeroed) */
 int map_scatter_add_slices(const float* d_input, const int64_t* masked_index, int64_t N, int L, int F, int P,
                            float* d_enc, map_stream_t stream);
+/* ------------------------------------------------------------------ K16  MFP feature encoder evaluated BY FIELD
+ * replaces `enc = feat_encoder(final).view(B, F, P)` + `torch.gather(enc, 1, masked_index)` (code/models.py:73-78) and their
+ * autograd: only the L masked P-wide slices of the [B, F*P] encoder output are ever used, so forward / dgrad / wgrad are computed
+ * for those slices alone (F/L times fewer flops, no [B, F*P] tensor).  n = b*L + l indexes the masked positions,
+ * f(n) = masked_index[n], W_f = rows [f*P, (f+1)*P) of feat_encoder.weight [F*P, K].  Exact fp32 FMAs, deterministic order.
+ * F <= 256, P in {8, 16, 32, 64} (map_field_enc_supported), K and all strides multiples of 4 floats.
+ *
+ * map_field_bucket: stable counting sort of the positions by field: perm[s] = n of the s-th position in (field, n) order,
+ *   fstart[f] .. fstart[f+1] = the slots of field f (fstart has F+1 entries).
+ * map_field_enc_fwd:   sel[n, :] = X[n / L, 0:K] . W_f(n)^T + bias[f(n)*P : (f(n)+1)*P]              (X = `final` [B, ldx])
+ * map_field_enc_dgrad: dxpos[n, 0:K] = d_sel[n, :] . W_f(n)     (one row per POSITION; map_head_bwd_fold sums the L rows of a sample)
+ * map_field_enc_wgrad: dW[f*P + j, 0:K] = sum_{n: f(n) = f} d_sel[n, j] * X[n / L, 0:K];  dbias[f*P + j] = sum_{n: f(n) = f} d_sel[n, j]
+ *   (every row of dW / dbias is written: fields without masked positions get zeros; dbias may be NULL) */
+int map_field_enc_supported(int F, int P);
+int map_field_bucket(const int64_t* masked_index, int64_t N, int F, int32_t* perm, int32_t* fstart, map_stream_t stream);
+int map_field_enc_fwd(const float* X, int64_t ldx, int K, const float* W, int64_t ldw, const float* bias, const int32_t* perm,
+                      const int32_t* fstart, int64_t N, int L, int F, int P, float* sel, map_stream_t stream);
+int map_field_enc_dgrad(const float* d_sel, const float* W, int64_t ldw, int K, const int32_t* perm, const int32_t* fstart,
+                        int64_t N, int F, int P, float* dxpos, int64_t ld_dx, map_stream_t stream);
+int map_field_enc_wgrad(const float* d_sel, const float* X, int64_t ldx, int K, const int32_t* perm, const int32_t* fstart, int64_t N,
+                        int L, int F, int P, float* dW, int64_t ldw, float* dbias, map_stream_t stream);
+/* Fold of the per-position gradients + the first stage of the towers' backward (what the epilogues of the dense head dgrad GEMMs
+ * do: MAP_EPI_CROSS_BWD with no layer above, MAP_EPI_MUL_RELUMASK, fused bias column sums, bf16 operand planes), one pass:
+ *   g[b, c] = sum_l dxpos[b*L + l, c]                                            (fixed order l = 0 .. L-1)
+ *   CrossNet columns [cross_col0, +cross_w): g_out = g ; du_out = g * x0 ; dx0_out = g * u ; cross_bias_grad += colsum(du_out)
+ *   ReLU columns     [relu_col0,  +relu_w):  dz_out = g * (y > 0) ;                         relu_bias_grad  += colsum(dz_out)
+ *   scalar_col (>= 0): scalar_out[b * ld_scalar] = g[b, scalar_col]               (DeepFM: d(lr_fm), code/models.py:224)
+ * Region pointers are indexed from the region's first column; the *_bias_grad accumulate with fp32 reductions (pre-zeroed by the
+ * caller, may be NULL); planes are bf16 [n_planes][B][pl_ld] (operand format of map_gemm_bf16s_group), may be NULL. */
+typedef struct {
+    const float* dxpos; int64_t ld_dx;
+    int64_t B; int32_t L; int32_t ncols;
+    int32_t cross_col0, cross_w;
+    const float* x0; int64_t ld_x0;
+    const float* u; int64_t ld_u;
+    float* g_out; int64_t ld_g;
+    float* du_out; int64_t ld_du;
+    float* dx0_out; int64_t ld_dx0;
+    uint16_t* du_planes; int64_t du_pl_ld; int64_t du_pl_stride; int32_t du_nplanes; int32_t reserved0_;
+    float* cross_bias_grad;
+    int32_t relu_col0, relu_w;
+    const float* y; int64_t ld_y;
+    float* dz_out; int64_t ld_dz;
+    uint16_t* dz_planes; int64_t dz_pl_ld; int64_t dz_pl_stride; int32_t dz_nplanes; int32_t scalar_col;
+    float* relu_bias_grad;
+    float* scalar_out; int64_t ld_scalar;
+} MapHeadBwdArgs;
+int map_head_bwd_fold(const MapHeadBwdArgs* args, map_stream_t stream);
 /* deterministic mean/sum: out[0] = scale * sum(x[0..n)) */
 int map_reduce_sum_f32(const float* x, int64_t n, float scale, float* out, void* workspace, size_t workspace_bytes,
                        map_stream_t stream);

@@ -56,6 +56,27 @@ class GemmSplitArgs(C.Structure):
     ]
 
 
+class HeadBwdArgs(C.Structure):
+    _fields_ = [
+        ("dxpos", C.c_void_p), ("ld_dx", C.c_int64),
+        ("B", C.c_int64), ("L", C.c_int32), ("ncols", C.c_int32),
+        ("cross_col0", C.c_int32), ("cross_w", C.c_int32),
+        ("x0", C.c_void_p), ("ld_x0", C.c_int64),
+        ("u", C.c_void_p), ("ld_u", C.c_int64),
+        ("g_out", C.c_void_p), ("ld_g", C.c_int64),
+        ("du_out", C.c_void_p), ("ld_du", C.c_int64),
+        ("dx0_out", C.c_void_p), ("ld_dx0", C.c_int64),
+        ("du_planes", C.c_void_p), ("du_pl_ld", C.c_int64), ("du_pl_stride", C.c_int64), ("du_nplanes", C.c_int32), ("reserved0_", C.c_int32),
+        ("cross_bias_grad", C.c_void_p),
+        ("relu_col0", C.c_int32), ("relu_w", C.c_int32),
+        ("y", C.c_void_p), ("ld_y", C.c_int64),
+        ("dz_out", C.c_void_p), ("ld_dz", C.c_int64),
+        ("dz_planes", C.c_void_p), ("dz_pl_ld", C.c_int64), ("dz_pl_stride", C.c_int64), ("dz_nplanes", C.c_int32), ("scalar_col", C.c_int32),
+        ("relu_bias_grad", C.c_void_p),
+        ("scalar_out", C.c_void_p), ("ld_scalar", C.c_int64),
+    ]
+
+
 _p, _i, _l, _f, _u64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes).  Kept in the order of include/map_b200.h; tests/test_abi.py checks it against the header.
@@ -88,6 +109,12 @@ PROTOTYPES = {
     "map_nce_full_ce": (_i, [_p, _l, _i, _p, _p, _l, _p, _p, _p, _sz, _p]),
     "map_gather_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
     "map_scatter_add_slices": (_i, [_p, _p, _l, _i, _i, _i, _p, _p]),
+    "map_field_enc_supported": (_i, [_i, _i]),
+    "map_field_bucket": (_i, [_p, _l, _i, _p, _p, _p]),
+    "map_field_enc_fwd": (_i, [_p, _l, _i, _p, _l, _p, _p, _p, _l, _i, _i, _i, _p, _p]),
+    "map_field_enc_dgrad": (_i, [_p, _p, _l, _i, _p, _p, _l, _i, _i, _p, _l, _p]),
+    "map_field_enc_wgrad": (_i, [_p, _p, _l, _i, _p, _p, _l, _i, _i, _i, _p, _l, _p, _p]),
+    "map_head_bwd_fold": (_i, [C.POINTER(HeadBwdArgs), _p]),
     "map_reduce_sum_f32": (_i, [_p, _l, _f, _p, _p, _sz, _p]),
     "map_reduce_workspace_bytes": (_sz, [_l]),
     "map_bce_logits_fwd": (_i, [_p, _p, _l, _p, _p, _p, _sz, _p]),

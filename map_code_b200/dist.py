@@ -569,14 +569,28 @@ class ShardedFusedStep(FusedStep):
     def forward_backward(self):
         self._ar_hi = self.grad_flat.numel()      # [_ar_hi, end) has been handed to NCCL
         self._ar_done = set()
+        self._ar_wait = []                        # events of gradients finished on side streams (by-field encoder wgrad on 'dw')
         self._xr_event = None                     # the chain of cross-rank operations restarts with every step
         super().forward_backward()
 
     def _all_reduce_range(self, lo: int, hi: int):
         self._fork("comm")
         with self._on("comm"), self._cross_rank():
+            for ev in getattr(self, "_ar_wait", ()):
+                torch.cuda.current_stream().wait_event(ev)
+            self._ar_wait = []
             dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.grad_group)
             _lib.mark("nccl_all_reduce", ("bytes", (hi - lo) * 4))
+
+    def _field_wgrad(self, W, Kd):
+        """by-field encoder: its weight gradient is produced on the 'dw' stream, not by a grouped GEMM launch: mark it finished for
+        the bucket logic below and make the next bucket wait for it"""
+        super()._field_wgrad(W, Kd)
+        if self.multi_stream and hasattr(self, "_ar_hi"):
+            self._ar_done.add("feat_encoder.weight")
+            ev = torch.cuda.Event()
+            ev.record(self.streams["dw"])
+            self._ar_wait.append(ev)
 
     def _gemm_group(self, problems):
         super()._gemm_group(problems)

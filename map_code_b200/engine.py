@@ -48,7 +48,7 @@ class FusedStep:
                  warmup_steps: int = 0, total_steps: int = 1000, seed: int = 42, optimizer_mode: str = "sparse",
                  x_train: Optional[torch.Tensor] = None, idx_low=None, idx_high=None, use_graph: bool = True,
                  row0: int = 0, global_batch: Optional[int] = None, gemm_backend: Optional[str] = None,
-                 multi_stream: bool = True, share_state_with: Optional["FusedStep"] = None):
+                 multi_stream: bool = True, share_state_with: Optional["FusedStep"] = None, field_encoder: Optional[bool] = None):
         """share_state_with: another FusedStep over the SAME model with a different batch size (the Trainer's ragged last batch,
         reference trainer.py:51-58 has drop_last=False).  Parameters, padded parameter storage, AdamW moments of every dense
         parameter and table, the step counter and the schedule state are the other engine's tensors; only the activations, the
@@ -98,10 +98,26 @@ class FusedStep:
         # through one more GEMM) -> terms = 3 keeps every gradient within 4e-4 of fp32 (tests/test_fullshape_gpu.py)
         self.cross_terms = int(_os.environ.get("MAP_B200_CROSS_TERMS", "3"))
         self.x_train, self.idx_low, self.idx_high = x_train, idx_low, idx_high
-        if self.mode == "RFD" and self.rfd_mode in ("Unigram", "Whole-Unigram") and x_train is None:
-            raise ValueError("RFD Unigram replacement needs the training id matrix on the device (x_train)")
-        if sampling_method not in ("randint", "normal"):
-            raise NotImplementedError(sampling_method)
+        # MFP head: evaluate feat_encoder only for the L masked fields of every sample (csrc/fieldenc.cu, K16) instead of all F
+        # fields + gather (models.py:73-78).  "hybrid" (default whenever the kernels take the shape and F >= 8 L): forward and
+        # weight gradient by field (13x fewer flops at mask_ratio 0.1; the weight gradient leaves the critical path), the input
+        # gradient stays a dense tensor-core GEMM over the expanded d_enc, whose epilogues already carry the first backward stage
+        # of the towers (measured r02e: a by-field dgrad has to write one [Kd] row per POSITION and fold them afterwards — 80 MB
+        # of round trip at C2 — and loses to the dense GEMM).  "full": dgrad by field as well (kept for A/B and for shapes with
+        # very small L / F).  MAP_B200_FIELD_ENC=0 / 1 (hybrid) / 2 (full) overrides.
+        fe_env = _os.environ.get("MAP_B200_FIELD_ENC")
+        if fe_env is not None:
+            field_encoder = {"0": False, "1": "hybrid", "2": "full"}[fe_env]
+        if field_encoder is True:
+            field_encoder = "hybrid"
+        if field_encoder not in (None, False, "hybrid", "full"):
+            raise ValueError(f"field_encoder={field_encoder!r}")
+        fe_ok = self.mode == "MFP" and self.L >= 1 and ops.field_enc_supported(self.F, cfg.proj_size)
+        if field_encoder and not fe_ok:
+            raise NotImplementedError(f"by-field encoder: needs MFP, F <= 256 and proj_size in (8, 16, 32, 64); got {self.mode}, F={self.F}, P={cfg.proj_size}")
+        if field_encoder is None:
+            field_encoder = "hybrid" if (fe_ok and self.F >= 8 * self.L) else False
+        self.field_enc = field_encoder
         self._collect_params()
         self._alloc()
         self.graph = None
@@ -313,9 +329,17 @@ class FusedStep:
             self.N, self.P, self.K = N, P, K
             crit = self.model.mfp_criterion
             self.labels = torch.empty(B, L, **i64)
-            self.enc = E(B, F * P)
-            self.d_enc = torch.zeros(B, F * P, **f32)
-            self.d_encp = PL(2, B, F * P)
+            self.enc = self.d_enc = self.d_encp = self.dxpos = None
+            if self.field_enc:   # by-field encoder: the [B, F*P] output never exists; positions bucketed by field
+                self.fe_perm = torch.zeros(N, dtype=torch.int32, device=dev)
+                self.fe_fstart = torch.zeros(F + 1, dtype=torch.int32, device=dev)
+            else:
+                self.enc = E(B, F * P)
+            if self.field_enc == "full":   # one gradient row per position, folded per sample afterwards
+                self.dxpos = E(N, self.ld_final)
+            else:
+                self.d_enc = torch.zeros(B, F * P, **f32)
+                self.d_encp = PL(2, B, F * P)
             self.sel = E(max(N, 1), P)
             self.noise = torch.empty(max(N, 1), K, **i64)
             self.logits = E(max(N, 1), K + 1)
@@ -493,7 +517,9 @@ class FusedStep:
     def _draw_noise(self):
         if self.mode != "MFP":
             return
-        if self.P % 4 != 0:
+        if self.field_enc:   # (needs only the mask: rides on the table stream with the noise draw, far ahead of the head)
+            ops.field_bucket(self.mi, self.F, self.fe_perm, self.fe_fstart)
+        elif self.P % 4 != 0:
             self.d_enc.zero_()   # (memset for the atomic form of the slice scatter; proj sizes that are multiples of 4 need none)
         crit = self.model.mfp_criterion
         if self.overrides is not None and "noise" in self.overrides:
@@ -548,7 +574,7 @@ class FusedStep:
     def _lr_fm_forward(self, ids, out, ld_out):
         ops.fm_lr_fwd(self.X0.view(self.B, self.F, self.D), ids, self.lr_w.data.view(-1), self.lr_b.data, out=out, ld_out=ld_out)
 
-    def _backward_backbone(self, head_W, dHead, n_head, head_wgrad=None, head_Wname=None, dHeadp=None):
+    def _backward_backbone(self, head_W, dHead, n_head, head_wgrad=None, head_Wname=None, dHeadp=None, from_fold=False):
         """head_W [n_head, final_dim] is the weight of the first head layer, dHead [B, n_head] the gradient at its
         pre-activation, head_wgrad the (optional) weight-gradient problem of that layer: it consumes dHead like the two
         tower dgrads and goes out in the same grouped launch.  Propagates into the towers and the embedding table.
@@ -556,18 +582,24 @@ class FusedStep:
           G_i = d(loss)/d(X_i);  dU_i = G_{i+1} * X0;  dX0 += G_{i+1} * U_i;  G_i = G_{i+1} + dU_i W_i;  db_i = colsum(dU_i)
         the GEMM that produces G_{i+1} also writes dU_i, accumulates dX0 and db_i (MAP_EPI_CROSS_BWD); the last one adds
         everything into dE (MAP_EPI_ADD3).  MLP: the gradient through each ReLU and the bias gradient (column sums of dZ) are
-        fused into the dgrad GEMM's epilogue.  One grouped launch per depth: {dgrad, wgrad} x {CrossNet, MLP}."""
+        fused into the dgrad GEMM's epilogue.  One grouped launch per depth: {dgrad, wgrad} x {CrossNet, MLP}.
+        from_fold: the head level (dZ / dU / G / dX0 of the last tower layers, their bias gradients, d_lrfm) has already been
+        produced by ops.head_bwd_fold (by-field MFP encoder); head_W / dHead are not used."""
         B, in_dim, H = self.B, self.in_dim, self.H
         nc, nh = len(self.cross), len(self.mlp)
         pref_c = "cross_net.cross_layers"
         pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
         probs = [head_wgrad]
         hw = (lambda lo, hi: self._wp(head_Wname, (lo, hi))) if head_Wname is not None else (lambda lo, hi: None)
-        if nh:
+        if from_fold:
+            nh_, nc_ = 0, 0
+        else:
+            nh_, nc_ = nh, nc
+        if nh_:
             probs.append(dict(A=dHead, B=head_W[:, self.mlp_off:self.mlp_off + H], C_out=self.dZ[nh - 1], M=B, N=H, K=n_head, trans_b=True,
                               epilogue=_lib.EPI_MUL_RELUMASK, aux0=self.mlp_out, colsum_out=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"],
                               Ap=dHeadp, Bp=hw(self.mlp_off, self.mlp_off + H), Cp=self.dZp[nh - 1]))
-        if nc:
+        if nc_:
             probs.append(dict(A=dHead, B=head_W[:, self.cross_off:self.cross_off + in_dim], C_out=self.dUs[nc - 1], M=B, N=in_dim, K=n_head,
                               trans_b=True, epilogue=_lib.EPI_CROSS_BWD, aux0=None, aux1=self.X0, aux2=self.U[nc - 1], aux_out=self.Gc[nc],
                               acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"],
@@ -611,7 +643,7 @@ class FusedStep:
         else:
             ops.copy2d(self.dX0_mlp, self.dE)
         if self.has_fm:  # d(lr_fm) flows into the embeddings (FM term) and into the first-order table + its bias
-            if self.cfg.pretrain:
+            if self.cfg.pretrain and not from_fold:
                 self._gemm(dHead, head_W[:, self.fm_col:self.fm_col + 1], self.d_lrfm, B, 1, n_head, trans_b=True)
             ops.fm_lr_bwd(self.X0.view(B, self.F, self.D), self.d_lrfm, 1, self.dE.view(B, self.F, self.D), self.d_w_occ, accumulate=True)
             ops.reduce_sum(self.d_lrfm.view(-1), 1.0, out=self.grads["lr_layer.bias"], ws=self.red_ws2)
@@ -643,7 +675,52 @@ class FusedStep:
                     ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.plan, t.grad, self.hyper, t.wd)
                     self._tables_done.add(t.name)
 
+    def _head_mfp_by_field(self):
+        """models.py:73-78 and its autograd for the L masked fields only (csrc/fieldenc.cu): forward on the bucketed positions;
+        the encoder's weight / bias gradients by field on the 'dw' stream; the input gradient either as dense GEMMs over the
+        expanded d_enc ("hybrid") or by field: dgrad per position -> fold over the L rows of a sample fused with the first
+        backward stage of the towers ("full")."""
+        B, F, P, L = self.B, self.F, self.P, self.L
+        m = self.model
+        wname = "feat_encoder.weight"
+        # aligned [F*P, ld_final] storage of the weight (DeepFM: zero-padded columns, which meet the zero padding of `final`)
+        W = self._pad_cols[wname] if wname in self._pad_cols else m.feat_encoder.weight.data
+        Kd = self.ld_final
+        self._join("tab")   # noise and the field buckets come from the 'tab' stream
+        ops.field_enc_fwd(self.final, Kd, W, m.feat_encoder.bias.data, self.fe_perm, self.fe_fstart, L, F, P, out=self.sel)
+        self._nce_core()
+        if self.field_enc == "hybrid":   # input gradient: dense GEMMs over the expanded d_enc (their epilogues start the towers' backward)
+            ops.expand_slices(self.d_sel, self.mi, F, P, self.d_enc, self.d_encp)
+            self._field_wgrad(W, Kd)
+            return self._backward_backbone(m.feat_encoder.weight.data, self.d_enc, F * P, head_Wname=wname, dHeadp=self.d_encp)
+        ops.field_enc_dgrad(self.d_sel, W, Kd, self.fe_perm, self.fe_fstart, F, P, self.dxpos)
+        nc, nh = len(self.cross), len(self.mlp)
+        pref_m = "parallel_dnn.dnn" if self.name == "dcnv2" else "dnn.dnn"
+        cross = relu = scalar = None
+        if nc:
+            cross = dict(col0=self.cross_off, width=self.in_dim, x0=self.X0, u=self.U[nc - 1], g_out=self.Gc[nc], du_out=self.dUs[nc - 1],
+                         dx0_out=self.dX0_acc, du_planes=self.dUsp[nc - 1], bias_grad=self.grads[f"cross_net.cross_layers.{nc - 1}.bias"])
+        if nh:
+            relu = dict(col0=self.mlp_off, width=self.H, y=self.mlp_out, dz_out=self.dZ[nh - 1], dz_planes=self.dZp[nh - 1],
+                        bias_grad=self.grads[f"{pref_m}.{3 * (nh - 1)}.bias"])
+        if self.has_fm:
+            scalar = dict(col=self.fm_col, out=self.d_lrfm)
+        ops.head_bwd_fold(self.dxpos, B, L, Kd, cross=cross, relu=relu, scalar=scalar)
+        self._field_wgrad(W, Kd)   # issued after the fold: the SIMT weight gradient then shares the SMs with the next GEMM level, not with the dgrad
+        self._backward_backbone(None, None, F * P, from_fold=True)
+
+    def _field_wgrad(self, W, Kd):
+        """encoder weight + bias gradients of the by-field head on the 'dw' stream (only the optimizer waits for them)"""
+        wname = "feat_encoder.weight"
+        self._fork("dw")
+        with self._on("dw"):
+            dW = self.grads_padded[wname] if wname in self._pad_cols else self.grads[wname]
+            ops.field_enc_wgrad(self.d_sel, self.final, Kd, self.fe_perm, self.fe_fstart, self.L, self.F, self.P, dW,
+                                dbias=self.grads["feat_encoder.bias"])
+
     def _head_mfp(self):
+        if self.field_enc:
+            return self._head_mfp_by_field()
         cfg, B, F, P, K, N, L = self.cfg, self.B, self.F, self.P, self.K, self.N, self.L
         m = self.model
         enc_W, enc_b = m.feat_encoder.weight.data, m.feat_encoder.bias.data
@@ -786,7 +863,15 @@ class FusedStep:
         torch.cuda.synchronize()
         self._restore(snap)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # The main branch of the step (the GEMM chain = the critical path) is captured on a stream of HIGHER priority than the side
+        # branches (table sorts, SIMT weight gradients, optimizer): kernel nodes inherit the priority of the stream they were
+        # captured on, and the block scheduler then hands freed SM resources to a pending GEMM launch (one persistent CTA per SM
+        # needing ~200 KB of shared memory) before it places more CTAs of a side kernel.  MAP_B200_MAIN_PRIO=0 restores equal
+        # priorities (A/B).
+        import os
+        prio = int(os.environ.get("MAP_B200_MAIN_PRIO", "-1"))
+        cap_stream = torch.cuda.Stream(device=self.dev, priority=prio)
+        with torch.cuda.graph(g, stream=cap_stream):
             self._step_body()
         self.graph = g
         self._restore(snap)

@@ -351,6 +351,92 @@ def expand_slices(d_sel: torch.Tensor, masked_index: torch.Tensor, F: int, P: in
     return d_enc
 
 
+# ------------------------------------------------------------------------------------------------ K16: by-field MFP encoder
+def field_enc_supported(F: int, P: int) -> bool:
+    return bool(_lib.load().map_field_enc_supported(int(F), int(P)))
+
+
+def field_bucket(masked_index: torch.Tensor, F: int, perm: Optional[torch.Tensor] = None, fstart: Optional[torch.Tensor] = None):
+    """stable counting sort of the masked positions n = b*L + l by field: perm [N] int32 (slot -> n), fstart [F+1] int32"""
+    N = masked_index.numel()
+    dev = masked_index.device
+    if perm is None:
+        perm = torch.empty(N, dtype=torch.int32, device=dev)
+    if fstart is None:
+        fstart = torch.empty(F + 1, dtype=torch.int32, device=dev)
+    _check(masked_index, torch.int64, "masked_index")
+    call("map_field_bucket", masked_index.data_ptr(), N, F, perm.data_ptr(), fstart.data_ptr(), _stream())
+    return perm, fstart
+
+
+def field_enc_fwd(X: torch.Tensor, K: int, W: torch.Tensor, bias: torch.Tensor, perm, fstart, L: int, F: int, P: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sel[n, :] = X[n // L, :K] @ W[f(n)*P:(f(n)+1)*P, :K].T + bias[f(n)*P:...]   (models.py:73-78 for the masked slices only)"""
+    N = perm.numel()
+    if out is None:
+        out = torch.empty(N, P, dtype=torch.float32, device=X.device)
+    _lib.CURRENT_TAG = ("field_enc_fwd", N, P, K)
+    call("map_field_enc_fwd", X.data_ptr(), _ld(X), K, W.data_ptr(), _ld(W), bias.data_ptr(), perm.data_ptr(), fstart.data_ptr(),
+         N, L, F, P, out.data_ptr(), _stream())
+    return out
+
+
+def field_enc_dgrad(d_sel: torch.Tensor, W: torch.Tensor, K: int, perm, fstart, F: int, P: int, dxpos: torch.Tensor) -> torch.Tensor:
+    """dxpos[n, :K] = d_sel[n, :] @ W[f(n)*P:(f(n)+1)*P, :K]"""
+    N = perm.numel()
+    _lib.CURRENT_TAG = ("field_enc_dgrad", N, P, K)
+    call("map_field_enc_dgrad", d_sel.data_ptr(), W.data_ptr(), _ld(W), K, perm.data_ptr(), fstart.data_ptr(), N, F, P,
+         dxpos.data_ptr(), _ld(dxpos), _stream())
+    return dxpos
+
+
+def field_enc_wgrad(d_sel: torch.Tensor, X: torch.Tensor, K: int, perm, fstart, L: int, F: int, P: int, dW: torch.Tensor,
+                    dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[f*P + j, :K] = sum over the positions of field f of d_sel[n, j] * X[n // L, :K]; dbias[f*P + j] = sum d_sel[n, j]"""
+    N = perm.numel()
+    _lib.CURRENT_TAG = ("field_enc_wgrad", N, P, K)
+    call("map_field_enc_wgrad", d_sel.data_ptr(), X.data_ptr(), _ld(X), K, perm.data_ptr(), fstart.data_ptr(), N, L, F, P,
+         dW.data_ptr(), _ld(dW), _ptr(dbias), _stream())
+    return dW
+
+
+def head_bwd_fold(dxpos: torch.Tensor, B: int, L: int, ncols: int, *, cross=None, relu=None, scalar=None):
+    """Sum of the L per-position gradient rows of every sample + the first backward stage of the towers (csrc/fieldenc.cu K16d).
+    cross = dict(col0, width, x0, u, g_out, du_out, dx0_out, du_planes=None, bias_grad=None)
+    relu  = dict(col0, width, y, dz_out, dz_planes=None, bias_grad=None);  scalar = dict(col, out)"""
+    import ctypes as C
+    a = _lib.HeadBwdArgs()
+    a.dxpos, a.ld_dx, a.B, a.L, a.ncols = dxpos.data_ptr(), _ld(dxpos), B, L, ncols
+    a.scalar_col = -1
+    keep = [dxpos]
+    if cross is not None:
+        a.cross_col0, a.cross_w = cross["col0"], cross["width"]
+        for k_, t_ in (("x0", "x0"), ("u", "u"), ("g_out", "g"), ("du_out", "du"), ("dx0_out", "dx0")):
+            setattr(a, k_, cross[k_].data_ptr())
+            setattr(a, "ld_" + t_, _ld(cross[k_]))
+        pl = cross.get("du_planes")
+        if pl is not None:
+            a.du_planes, a.du_pl_ld, a.du_pl_stride, a.du_nplanes = pl.data_ptr(), pl.stride(1), pl.stride(0), pl.shape[0]
+        if cross.get("bias_grad") is not None:
+            a.cross_bias_grad = cross["bias_grad"].data_ptr()
+        keep.append(cross)
+    if relu is not None:
+        a.relu_col0, a.relu_w = relu["col0"], relu["width"]
+        a.y, a.ld_y = relu["y"].data_ptr(), _ld(relu["y"])
+        a.dz_out, a.ld_dz = relu["dz_out"].data_ptr(), _ld(relu["dz_out"])
+        pl = relu.get("dz_planes")
+        if pl is not None:
+            a.dz_planes, a.dz_pl_ld, a.dz_pl_stride, a.dz_nplanes = pl.data_ptr(), pl.stride(1), pl.stride(0), pl.shape[0]
+        if relu.get("bias_grad") is not None:
+            a.relu_bias_grad = relu["bias_grad"].data_ptr()
+        keep.append(relu)
+    if scalar is not None:
+        a.scalar_col, a.scalar_out, a.ld_scalar = scalar["col"], scalar["out"].data_ptr(), _ld(scalar["out"])
+        keep.append(scalar)
+    _lib.CURRENT_TAG = ("head_bwd_fold", B, L, ncols)
+    call("map_head_bwd_fold", C.byref(a), _stream())
+
+
 _red_ws = {}
 
 

@@ -39,6 +39,7 @@ def test_struct_layouts_match_header(lib):
     assert C.sizeof(lib.GemmArgs) == 24 + 8 * 13 + 8 * 4 + 8 + 8  # + aux2/acc_out (+ld), acc_accumulate/reserved, colsum_out
     assert C.sizeof(lib.AdamwTensor) == 80  # + planes pointer and plane stride (bf16 planes of the parameter)
     assert C.sizeof(lib.GemmSplitArgs) == C.sizeof(lib.GemmArgs) + 3 * 32
+    assert C.sizeof(lib.HeadBwdArgs) == 256 and lib.HeadBwdArgs.scalar_col.offset == 228   # MapHeadBwdArgs (by-field encoder fold)
 
 
 def test_errors_are_reported_not_swallowed(lib):

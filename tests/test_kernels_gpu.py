@@ -406,6 +406,96 @@ def test_gather_scatter_slices(ops):
     torch.testing.assert_close(d_enc.cpu(), ref, rtol=1e-6, atol=1e-6)
 
 
+# ------------------------------------------------------------------------------------------------ K16: by-field MFP encoder
+def _bf16_planes_ref(x, n):
+    out, r = [], x.clone()
+    for _ in range(n):
+        h = r.to(torch.bfloat16)
+        out.append(h)
+        r = r - h.float()
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("B,F,L,P,K,few_fields", [(300, 39, 3, 32, 1624, False), (64, 24, 2, 32, 1008, False), (12, 6, 2, 8, 40, False),
+                                                 (257, 39, 11, 16, 100, False), (33, 5, 1, 64, 68, False), (500, 39, 3, 32, 200, True),
+                                                 (4096, 39, 3, 32, 1624, False)])
+def test_field_encoder_kernels(ops, B, F, L, P, K, few_fields):
+    """models.py:73-78 (feat_encoder + gather of the masked slices) and its autograd, evaluated for the masked fields only, against
+    the dense fp64 formulation of the reference; bucket order and operand planes bit-exact."""
+    gen = torch.Generator().manual_seed(B + F + K)
+    N = B * L
+    X = torch.randn(B, K, generator=gen)
+    W = torch.randn(F * P, K, generator=gen) / math.sqrt(K)
+    bias = torch.randn(F * P, generator=gen)
+    mi = torch.randint(0, 3 if few_fields else F, (B, L), generator=gen)   # few_fields: most fields have no masked position
+    if few_fields:
+        mi = mi * 7 + 2
+    perm, fstart = ops.field_bucket(dev(mi), F)
+    order = torch.sort(mi.view(-1), stable=True).indices
+    assert torch.equal(perm.cpu().long(), order)
+    cnt = torch.bincount(mi.view(-1), minlength=F)
+    assert torch.equal(fstart.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)]))
+    Xd, Wd = dev(X), dev(W)
+    # forward
+    sel = ops.field_enc_fwd(Xd, K, Wd, dev(bias), perm, fstart, L, F, P)
+    enc = (X.double() @ W.double().T + bias.double()).view(B, F, P)
+    want = torch.gather(enc, 1, mi.unsqueeze(-1).repeat(1, 1, P)).view(N, P)
+    torch.testing.assert_close(sel.cpu().double(), want, rtol=2e-5, atol=2e-5)
+    # dgrad per position
+    d_sel = torch.randn(N, P, generator=gen)
+    dxpos = torch.full((N, K + 4), float("nan"), device="cuda")[:, :K]   # strided output rows
+    ops.field_enc_dgrad(dev(d_sel), Wd, K, perm, fstart, F, P, dxpos)
+    Wf = W.double().view(F, P, K)[mi.view(-1)]                            # [N, P, K]
+    want_dx = torch.einsum("np,npk->nk", d_sel.double(), Wf)
+    torch.testing.assert_close(dxpos.cpu().double(), want_dx, rtol=2e-5, atol=2e-5)
+    # wgrad + bias gradient (every row written, empty fields -> zeros)
+    dW = torch.full((F * P, K), float("nan"), device="cuda")
+    db = torch.full((F * P,), float("nan"), device="cuda")
+    ops.field_enc_wgrad(dev(d_sel), Xd, K, perm, fstart, L, F, P, dW, db)
+    d_enc = torch.zeros(B, F, P, dtype=torch.float64).scatter_add_(1, mi.unsqueeze(-1).repeat(1, 1, P), d_sel.double().view(B, L, P))
+    want_dW = d_enc.view(B, F * P).T @ X.double()
+    torch.testing.assert_close(dW.cpu().double(), want_dW, rtol=2e-5, atol=2e-5 * math.sqrt(B))
+    torch.testing.assert_close(db.cpu().double(), d_enc.view(B, F * P).sum(0), rtol=2e-5, atol=2e-5 * math.sqrt(B))
+    # fold of the L rows per sample + first backward stage: [CrossNet columns | ReLU columns | one scalar column | padding]
+    cw = (K // 3) // 4 * 4
+    rw = (K - cw - 4) // 4 * 4
+    scol = cw + rw + 1 if cw + rw + 4 <= K else -1
+    x0, u = torch.randn(B, cw, generator=gen), torch.randn(B, cw, generator=gen)
+    y = torch.relu(torch.randn(B, rw, generator=gen))
+    g_out, du, dx0 = (torch.empty(B, cw, device="cuda") for _ in range(3))
+    dz = torch.empty(B, rw, device="cuda")
+    dup, dzp = ops.alloc_planes(B, cw, 2, "cuda"), ops.alloc_planes(B, rw, 2, "cuda")
+    cb, rb = torch.zeros(cw, device="cuda"), torch.zeros(rw, device="cuda")
+    sc = torch.empty(B, 1, device="cuda")
+    ops.head_bwd_fold(dxpos, B, L, K,
+                      cross=dict(col0=0, width=cw, x0=dev(x0), u=dev(u), g_out=g_out, du_out=du, dx0_out=dx0, du_planes=dup, bias_grad=cb) if cw else None,
+                      relu=dict(col0=cw, width=rw, y=dev(y), dz_out=dz, dz_planes=dzp, bias_grad=rb) if rw else None,
+                      scalar=dict(col=scol, out=sc) if scol >= 0 else None)
+    gsum = dxpos.cpu().view(B, L, K)[:, 0].clone()
+    for l in range(1, L):
+        gsum += dxpos.cpu().view(B, L, K)[:, l]              # same order as the kernel: bit-exact
+    if cw:
+        assert torch.equal(g_out.cpu(), gsum[:, :cw])
+        assert torch.equal(du.cpu(), gsum[:, :cw] * x0) and torch.equal(dx0.cpu(), gsum[:, :cw] * u)
+        assert torch.equal(dup.cpu(), _bf16_planes_ref(du.cpu(), 2))
+        torch.testing.assert_close(cb.cpu().double(), du.cpu().double().sum(0), rtol=2e-5, atol=2e-5 * math.sqrt(B))
+    if rw:
+        want_dz = torch.where(y > 0, gsum[:, cw:cw + rw], torch.zeros(()))
+        assert torch.equal(dz.cpu(), want_dz)
+        assert torch.equal(dzp.cpu(), _bf16_planes_ref(dz.cpu(), 2))
+        torch.testing.assert_close(rb.cpu().double(), dz.cpu().double().sum(0), rtol=2e-5, atol=2e-5 * math.sqrt(B))
+    if scol >= 0:
+        assert torch.equal(sc.cpu().view(-1), gsum[:, scol])
+
+
+def test_field_encoder_rejects_unsupported(ops):
+    assert ops.field_enc_supported(39, 32) and not ops.field_enc_supported(39, 12) and not ops.field_enc_supported(1000, 32)
+    from map_code_b200 import _lib
+    with pytest.raises(_lib.MapB200Error):
+        ops.field_enc_fwd(torch.zeros(4, 8, device="cuda"), 8, torch.zeros(24, 8, device="cuda"), torch.zeros(24, device="cuda"),
+                          torch.zeros(4, dtype=torch.int32, device="cuda"), torch.zeros(3, dtype=torch.int32, device="cuda"), 1, 2, 12)
+
+
 # ------------------------------------------------------------------------------------------------ K10 / K11 / reductions
 @pytest.mark.parametrize("n", [1, 4096, 4096 * 39, 1_000_003])
 def test_bce_logits(ops, n):

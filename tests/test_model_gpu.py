@@ -119,7 +119,7 @@ def test_modules_vs_reference_golden(golden, case, backend, monkeypatch):
                 torch.testing.assert_close(sd[k].cpu(), pref, rtol=2e-4, atol=2e-6, msg=lambda m, k=k: f"param {k}: {m}")
 
 
-@pytest.mark.parametrize("backend", ["simt", "tcgen05", "bf16s"])
+@pytest.mark.parametrize("backend", ["simt", "tcgen05", "bf16s", "bf16s+hybrid", "bf16s+full", "simt+full"])
 @pytest.mark.parametrize("case", CASES)
 def test_fused_step_vs_reference_golden(golden, case, backend):
     """The graph-capturable FusedStep (explicit backward, dedup'd table gradients, dense_exact optimizer) fed the reference's
@@ -127,13 +127,21 @@ def test_fused_step_vs_reference_golden(golden, case, backend):
     from map_code_b200.engine import FusedStep
     if backend == "tcgen05" and case.startswith("dnn"):
         pytest.skip("TF32 is the A/B backend only; at batch 12 the all-ReLU DNN backbone amplifies its operand truncation to 1e-1")
+    # "+hybrid" / "+full": the MFP encoder evaluated for the masked fields only (csrc/fieldenc.cu) instead of all fields + gather;
+    # without it the goldens (F = 6, L = 2) take the dense encoder, which is what the automatic choice picks at that ratio
+    field_enc = backend.split("+")[1] if "+" in backend else False
+    backend = backend.split("+")[0]
+    if field_enc and not case.endswith("_mfp"):
+        pytest.skip("by-field encoder: MFP head only")
     g = golden(case)
     model = build_model(g)
     opt = g["optim"]
     B = g["steps"][0]["batch"].shape[0]
     eng = FusedStep(model, batch_size=B, mask_ratio=g["config"]["mask_ratio"], lr=opt["lr"], weight_decay=opt["weight_decay"],
                     betas=opt["betas"], eps=opt["eps"], sched="cosine", warmup_steps=opt["t_warmup"], total_steps=opt["t_total"],
-                    optimizer_mode="dense_exact", use_graph=False, gemm_backend=backend, x_train=g["X_train"].cuda())
+                    optimizer_mode="dense_exact", use_graph=False, gemm_backend=backend, x_train=g["X_train"].cuda(),
+                    field_encoder=field_enc)
+    assert eng.field_enc == field_enc
     named = dict(model.named_parameters())
     for st in g["steps"]:
         if eng.mode == "CTR":
