@@ -77,11 +77,14 @@ __global__ void __launch_bounds__(1024) field_bucket_kernel(const int64_t* __res
 
 // tile table of a launch: tstart[f] = number of position tiles of the fields before f (kFeTM positions per tile)
 __device__ __forceinline__ void build_tile_starts(const int32_t* __restrict__ fstart, int F, int* tstart) {
+    for (int f = threadIdx.x; f < F; f += blockDim.x) tstart[f] = (fstart[f + 1] - fstart[f] + kFeTM - 1) / kFeTM;   // tiles of field f
+    __syncthreads();
     if (threadIdx.x == 0) {
         int t = 0;
         for (int f = 0; f < F; ++f) {
+            const int n = tstart[f];
             tstart[f] = t;
-            t += (fstart[f + 1] - fstart[f] + kFeTM - 1) / kFeTM;
+            t += n;
         }
         tstart[F] = t;
     }
@@ -275,49 +278,64 @@ __device__ __forceinline__ void store_planes4(uint16_t* planes, int64_t ld, int6
     }
 }
 
-constexpr int kFeRB = 32;   // rows per CTA of the fold
+constexpr int kFeRB = 8;   // rows per CTA of the fold (two in flight per thread: the kernel is a latency-bound stream)
 __global__ void __launch_bounds__(128) head_bwd_fold_kernel(MapHeadBwdArgs a) {
-    const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int c = (blockIdx.y * 128 + threadIdx.x) * 4;
     if (c >= a.ncols) return;
-    const int64_t b0 = (int64_t)blockIdx.y * kFeRB;
+    const int64_t b0 = (int64_t)blockIdx.x * kFeRB;
     const int64_t b1 = b0 + kFeRB < a.B ? b0 + kFeRB : a.B;
     const bool in_cross = a.cross_w > 0 && c >= a.cross_col0 && c < a.cross_col0 + a.cross_w;
     const bool in_relu = a.relu_w > 0 && c >= a.relu_col0 && c < a.relu_col0 + a.relu_w;
     const bool has_scalar = a.scalar_col >= c && a.scalar_col < c + 4;
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t b = b0; b < b1; ++b) {
-        const float* src = a.dxpos + b * a.L * a.ld_dx + c;
-        float4 g = ld_stream_f4(reinterpret_cast<const float4*>(src));
-        for (int l = 1; l < a.L; ++l) {
-            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(src + (int64_t)l * a.ld_dx));
-            g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    const int cc = c - (in_cross ? a.cross_col0 : in_relu ? a.relu_col0 : 0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 cs = zero4;
+    for (int64_t bb = b0; bb < b1; bb += 2) {
+        float4 g[2], p[2], q[2];   // p = X0 (CrossNet) or y (ReLU); q = U (CrossNet)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t b = bb + r < b1 ? bb + r : bb;   // odd tail: the second lane repeats the first row and is not stored
+            const float* src = a.dxpos + b * a.L * a.ld_dx + c;
+            g[r] = ld_stream_f4(reinterpret_cast<const float4*>(src));
+            for (int l = 1; l < a.L; ++l) {
+                const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(src + (int64_t)l * a.ld_dx));
+                g[r].x += v.x; g[r].y += v.y; g[r].z += v.z; g[r].w += v.w;
+            }
+            p[r] = q[r] = zero4;
+            if (in_cross) {
+                p[r] = *reinterpret_cast<const float4*>(a.x0 + b * a.ld_x0 + cc);
+                q[r] = *reinterpret_cast<const float4*>(a.u + b * a.ld_u + cc);
+            } else if (in_relu) {
+                p[r] = *reinterpret_cast<const float4*>(a.y + b * a.ld_y + cc);
+            }
         }
-        if (in_cross) {   // G = g ; dU = G * X0 ; dX0 = G * U   (MAP_EPI_CROSS_BWD with no layer above)
-            const int cc = c - a.cross_col0;
-            const float4 x0 = *reinterpret_cast<const float4*>(a.x0 + b * a.ld_x0 + cc);
-            const float4 u = *reinterpret_cast<const float4*>(a.u + b * a.ld_u + cc);
-            *reinterpret_cast<float4*>(a.g_out + b * a.ld_g + cc) = g;
-            *reinterpret_cast<float4*>(a.dx0_out + b * a.ld_dx0 + cc) = make_float4(g.x * u.x, g.y * u.y, g.z * u.z, g.w * u.w);
-            const float4 du = make_float4(g.x * x0.x, g.y * x0.y, g.z * x0.z, g.w * x0.w);
-            *reinterpret_cast<float4*>(a.du_out + b * a.ld_du + cc) = du;
-            if (a.du_planes != nullptr) store_planes4(a.du_planes, a.du_pl_ld, a.du_pl_stride, a.du_nplanes, b, cc, du);
-            cs.x += du.x; cs.y += du.y; cs.z += du.z; cs.w += du.w;
-        } else if (in_relu) {   // dZ = g * (y > 0)   (MAP_EPI_MUL_RELUMASK)
-            const int cc = c - a.relu_col0;
-            const float4 y = *reinterpret_cast<const float4*>(a.y + b * a.ld_y + cc);
-            const float4 dz = make_float4(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f, y.z > 0.f ? g.z : 0.f, y.w > 0.f ? g.w : 0.f);
-            *reinterpret_cast<float4*>(a.dz_out + b * a.ld_dz + cc) = dz;
-            if (a.dz_planes != nullptr) store_planes4(a.dz_planes, a.dz_pl_ld, a.dz_pl_stride, a.dz_nplanes, b, cc, dz);
-            cs.x += dz.x; cs.y += dz.y; cs.z += dz.z; cs.w += dz.w;
-        }
-        if (has_scalar) {
-            const int o = a.scalar_col - c;
-            a.scalar_out[b * a.ld_scalar] = o == 0 ? g.x : o == 1 ? g.y : o == 2 ? g.z : g.w;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t b = bb + r;
+            if (b >= b1) break;
+            const float4 gg = g[r];
+            if (in_cross) {   // G = g ; dU = G * X0 ; dX0 = G * U   (MAP_EPI_CROSS_BWD with no layer above)
+                *reinterpret_cast<float4*>(a.g_out + b * a.ld_g + cc) = gg;
+                *reinterpret_cast<float4*>(a.dx0_out + b * a.ld_dx0 + cc) = make_float4(gg.x * q[r].x, gg.y * q[r].y, gg.z * q[r].z, gg.w * q[r].w);
+                const float4 du = make_float4(gg.x * p[r].x, gg.y * p[r].y, gg.z * p[r].z, gg.w * p[r].w);
+                *reinterpret_cast<float4*>(a.du_out + b * a.ld_du + cc) = du;
+                if (a.du_planes != nullptr) store_planes4(a.du_planes, a.du_pl_ld, a.du_pl_stride, a.du_nplanes, b, cc, du);
+                cs.x += du.x; cs.y += du.y; cs.z += du.z; cs.w += du.w;
+            } else if (in_relu) {   // dZ = g * (y > 0)   (MAP_EPI_MUL_RELUMASK)
+                const float4 dz = make_float4(p[r].x > 0.f ? gg.x : 0.f, p[r].y > 0.f ? gg.y : 0.f, p[r].z > 0.f ? gg.z : 0.f, p[r].w > 0.f ? gg.w : 0.f);
+                *reinterpret_cast<float4*>(a.dz_out + b * a.ld_dz + cc) = dz;
+                if (a.dz_planes != nullptr) store_planes4(a.dz_planes, a.dz_pl_ld, a.dz_pl_stride, a.dz_nplanes, b, cc, dz);
+                cs.x += dz.x; cs.y += dz.y; cs.z += dz.z; cs.w += dz.w;
+            }
+            if (has_scalar) {
+                const int o = a.scalar_col - c;
+                a.scalar_out[b * a.ld_scalar] = o == 0 ? gg.x : o == 1 ? gg.y : o == 2 ? gg.z : gg.w;
+            }
         }
     }
     float* bg = in_cross ? a.cross_bias_grad : in_relu ? a.relu_bias_grad : nullptr;
     if (bg != nullptr) {
-        bg += c - (in_cross ? a.cross_col0 : a.relu_col0);
+        bg += cc;
         atomicAdd(bg + 0, cs.x); atomicAdd(bg + 1, cs.y); atomicAdd(bg + 2, cs.z); atomicAdd(bg + 3, cs.w);
     }
 }
@@ -390,7 +408,10 @@ __global__ void __launch_bounds__(128) field_enc_wgrad_kernel(const float* __res
                 const float d = dv[j];
                 acc[j].x = fmaf(d, x.x, acc[j].x); acc[j].y = fmaf(d, x.y, acc[j].y);
                 acc[j].z = fmaf(d, x.z, acc[j].z); acc[j].w = fmaf(d, x.w, acc[j].w);
-                bacc[j] += d;
+            }
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int j = 0; j < PJ; ++j) bacc[j] += dv[j];
             }
         }
         __syncthreads();
@@ -457,8 +478,7 @@ extern "C" int map_field_enc_dgrad(const float* d_sel, const float* W, int64_t l
     MAP_REQUIRE(K % 4 == 0 && ldw % 4 == 0 && ld_dx % 4 == 0 && ld_dx >= K && ((uintptr_t)d_sel & 15) == 0 && ((uintptr_t)W & 15) == 0 &&
                     ((uintptr_t)dxpos & 15) == 0,
                 "map_field_enc_dgrad: K, ldw, ld_dx must be multiples of 4 floats and the pointers 16-byte aligned");
-    const int64_t max_tiles = (ceil_div(N, kFeTM) + F) * ceil_div(K, kFeDC);
-    const int64_t grid = max_tiles < (int64_t)kNumSMs * 8 ? max_tiles : (int64_t)kNumSMs * 8;
+    const int64_t grid = (ceil_div(N, kFeTM) + F) * ceil_div(K, kFeDC);   // upper bound of the tile count: one CTA per tile
     FE_DISPATCH_P(P, { field_enc_dgrad_kernel<P_><<<(unsigned)grid, 128, 0, as_stream(stream)>>>(d_sel, W, ldw, K, perm, fstart, F, dxpos, ld_dx); });
     return check_launch("map_field_enc_dgrad");
 }
@@ -498,7 +518,7 @@ extern "C" int map_head_bwd_fold(const MapHeadBwdArgs* a, map_stream_t stream) {
                     "map_head_bwd_fold: dZ planes alignment");
     }
     MAP_REQUIRE(a->scalar_col < a->ncols && (a->scalar_col < 0 || a->scalar_out != nullptr), "map_head_bwd_fold: scalar column");
-    const dim3 grid((unsigned)ceil_div(a->ncols / 4, 128), (unsigned)ceil_div(a->B, kFeRB));
+    const dim3 grid((unsigned)ceil_div(a->B, kFeRB), (unsigned)ceil_div(a->ncols / 4, 128));
     head_bwd_fold_kernel<<<grid, 128, 0, as_stream(stream)>>>(*a);
     return check_launch("map_head_bwd_fold");
 }
