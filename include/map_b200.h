@@ -246,6 +246,27 @@ typedef struct {
     float* scalar_out; int64_t ld_scalar;
 } MapHeadBwdArgs;
 int map_head_bwd_fold(const MapHeadBwdArgs* args, map_stream_t stream);
+/* ------------------------------------------------------------------ K17  Compressed Interaction Network (xDeepFM)
+ * replaces CIN.forward (code/layers.py:709-721) and its autograd.  One layer of the reference is
+ *   hadamard[b, h*M + m, d] = X0[b,h,d] * Xi[b,m,d];  X_next = Conv1d(F*M -> O, kernel 1)(hadamard);  pooled = X_next.sum(-1).
+ * The 1x1 convolution is a GEMM over the pairs p = b*D + d, so CIN activations are kept PAIR-MAJOR ([B*D, channels]) and the
+ * contraction runs on map_gemm_bf16s_group; these entry points are the glue around it (exact fp32, deterministic):
+ * map_cin_relayout:     to_pairs=1: src [B, C, D] -> dst [(b*D + d), c] (leading dimension ld_pairs);
+ *                       to_pairs=0: src pairs -> dst [B, C, D] (accumulate=1 adds into dst)
+ * map_cin_hadamard_fwd: z[p, h*M + m] = x0[p, h] * xi[p, m]; columns [F*M, ldz) are written as zeros (K padding of the GEMM)
+ * map_cin_hadamard_bwd: dx0[p, h] (+)= sum_m dz[p, h*M + m] * xi[p, m];  dxi[p, m] = sum_h dz[p, h*M + m] * x0[p, h]
+ * map_cin_pool_fwd:     pooled[b, o] = sum_d y[b*D + d, o]
+ * map_cin_pool_bwd:     dy[b*D + d, o] = d_pooled[b, o] (+ d_next[b*D + d, o] if d_next != NULL); columns [O, ld_dy) zeroed */
+int map_cin_relayout(const float* src, float* dst, int64_t B, int C, int D, int64_t ld_pairs, int to_pairs, int accumulate,
+                     map_stream_t stream);
+int map_cin_hadamard_fwd(const float* x0, int64_t ld_x0, const float* xi, int64_t ld_xi, int64_t P, int F, int M, float* z,
+                         int64_t ldz, map_stream_t stream);
+int map_cin_hadamard_bwd(const float* dz, int64_t ldz, const float* x0, int64_t ld_x0, const float* xi, int64_t ld_xi, int64_t P,
+                         int F, int M, float* dx0, int64_t ld_dx0, int accumulate_dx0, float* dxi, int64_t ld_dxi,
+                         map_stream_t stream);
+int map_cin_pool_fwd(const float* y, int64_t ldy, int64_t B, int D, int O, float* pooled, int64_t ld_pooled, map_stream_t stream);
+int map_cin_pool_bwd(const float* d_pooled, int64_t ld_pooled, const float* d_next, int64_t ld_next, int64_t B, int D, int O,
+                     float* dy, int64_t ld_dy, map_stream_t stream);
 /* deterministic mean/sum: out[0] = scale * sum(x[0..n)) */
 int map_reduce_sum_f32(const float* x, int64_t n, float scale, float* out, void* workspace, size_t workspace_bytes,
                        map_stream_t stream);

@@ -115,6 +115,11 @@ PROTOTYPES = {
     "map_field_enc_dgrad": (_i, [_p, _p, _l, _i, _p, _p, _l, _i, _i, _p, _l, _p]),
     "map_field_enc_wgrad": (_i, [_p, _p, _l, _i, _p, _p, _l, _i, _i, _i, _p, _l, _p, _p]),
     "map_head_bwd_fold": (_i, [C.POINTER(HeadBwdArgs), _p]),
+    "map_cin_relayout": (_i, [_p, _p, _l, _i, _i, _l, _i, _i, _p]),
+    "map_cin_hadamard_fwd": (_i, [_p, _l, _p, _l, _l, _i, _i, _p, _l, _p]),
+    "map_cin_hadamard_bwd": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _i, _p, _l, _i, _p, _l, _p]),
+    "map_cin_pool_fwd": (_i, [_p, _l, _l, _i, _i, _p, _l, _p]),
+    "map_cin_pool_bwd": (_i, [_p, _l, _p, _l, _l, _i, _i, _p, _l, _p]),
     "map_reduce_sum_f32": (_i, [_p, _l, _f, _p, _p, _sz, _p]),
     "map_reduce_workspace_bytes": (_sz, [_l]),
     "map_bce_logits_fwd": (_i, [_p, _p, _l, _p, _p, _p, _sz, _p]),

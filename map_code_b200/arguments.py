@@ -88,6 +88,8 @@ class ModelArguments:
     layer_norm_eps: float = 1e-12
     embed_norm: bool = False
     num_cross_layers: int = 1
+    use_lr: bool = False            # xDeepFM (arguments.py:141)
+    cin_layer_units: str = "50,50"  # xDeepFM (arguments.py:144)
     pt_neg_num: int = 25
     proj_size: int = 32
 

@@ -148,6 +148,85 @@ class CrossLayerFn(torch.autograd.Function):
         return dxi, dx0, dw, db
 
 
+# ------------------------------------------------------------------------------------------------ CIN (xDeepFM)
+class CINRelayoutFn(torch.autograd.Function):
+    """[B, C, D] -> pair-major [B*D, C] (p = b*D + d): the layout in which the 1x1 convolutions of CIN are GEMMs (csrc/cin.cu)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, C_, D = x.shape
+        ctx.shape = (B, C_, D)
+        out = torch.empty(B * D, C_, dtype=torch.float32, device=x.device)
+        return ops.cin_relayout(x, out, B, C_, D, to_pairs=True)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C_, D = ctx.shape
+        dx = torch.empty(B, C_, D, dtype=torch.float32, device=g.device)
+        return ops.cin_relayout(_rows(g), dx, B, C_, D, to_pairs=False)
+
+
+class CINHadamardFn(torch.autograd.Function):
+    """z[p, h*M + m] = x0[p, h] * xi[p, m] with the row padded to `ldz` columns of zeros.  reference: torch.einsum("bhd,bmd->bhmd")
+    + view, code/layers.py:714-715"""
+
+    @staticmethod
+    def forward(ctx, x0, xi, ldz: int):
+        x0, xi = _rows(x0), _rows(xi)
+        P, F = x0.shape
+        M = xi.shape[1]
+        z = torch.empty(P, ldz, dtype=torch.float32, device=x0.device)
+        ops.cin_hadamard_fwd(x0, xi, F, M, z)
+        ctx.save_for_backward(x0, xi)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x0, xi = ctx.saved_tensors
+        P, F = x0.shape
+        M = xi.shape[1]
+        dx0 = torch.empty(P, F, dtype=torch.float32, device=gz.device)
+        dxi = torch.empty(P, M, dtype=torch.float32, device=gz.device)
+        ops.cin_hadamard_bwd(_rows(gz), x0, xi, F, M, dx0, dxi)
+        return dx0, dxi, None
+
+
+class CINPoolFn(torch.autograd.Function):
+    """pooled[b, o] = sum_d y[b*D + d, o]   (X_i.sum(dim=-1), code/layers.py:719); y may carry padding columns beyond O"""
+
+    @staticmethod
+    def forward(ctx, y, B: int, D: int, O: int):
+        y = _rows(y)
+        ctx.dims = (B, D, O, y.shape[1])
+        return ops.cin_pool_fwd(y, B, D, O, torch.empty(B, O, dtype=torch.float32, device=y.device))
+
+    @staticmethod
+    def backward(ctx, g):
+        B, D, O, width = ctx.dims
+        dy = torch.empty(B * D, width, dtype=torch.float32, device=g.device)
+        return ops.cin_pool_bwd(_rows(g), B, D, O, dy), None, None, None
+
+
+class PadMatrixFn(torch.autograd.Function):
+    """zero-padded copy [rows, cols] -> [rows_p, cols_p] (TMA-aligned operand of a GEMM); backward = the top-left block"""
+
+    @staticmethod
+    def forward(ctx, w, rows_p: int, cols_p: int):
+        w = _rows(w)
+        ctx.shape = tuple(w.shape)
+        out = torch.zeros(rows_p, cols_p, dtype=torch.float32, device=w.device)
+        ops.copy2d(w, out[:w.shape[0], :w.shape[1]])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        r, c = ctx.shape
+        dw = torch.empty(r, c, dtype=torch.float32, device=g.device)
+        ops.copy2d(_rows(g)[:r, :c], dw)
+        return dw, None, None
+
+
 # ------------------------------------------------------------------------------------------------ MFP head
 class GatherSlicesFn(torch.autograd.Function):
     """selected_output = gather(enc_output[B,F,P], 1, masked_index).  reference: code/models.py:75"""

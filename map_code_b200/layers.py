@@ -158,3 +158,49 @@ class CrossNetV2(nn.Module):
             layer = self.cross_layers[i]
             Xi = Fn.CrossLayerFn.apply(Xi, X0, layer.weight, layer.bias)
         return Xi
+
+
+class Conv1dK1(nn.Module):
+    """Parameters and init of nn.Conv1d(in_channels, out_channels, kernel_size=1) (weight [O, C, 1], bias [O]); the compute is
+    the pair-major GEMM inside CIN.forward."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, 1))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))   # torch.nn.modules.conv._ConvNd.reset_parameters
+        bound = 1 / math.sqrt(in_channels) if in_channels > 0 else 0
+        init.uniform_(self.bias, -bound, bound)
+
+
+class CIN(nn.Module):
+    """layers.py:696-721 (xDeepFM's Compressed Interaction Network).  Same parameter names (cin_layer.layer_i.weight/bias).
+    Activations are pair-major [B*D, channels]; each layer = outer product kernel -> tensor-core GEMM over the pairs (K padded to
+    a multiple of 8, outputs to a multiple of 4 and at least 8: zero rows / columns) -> sum over d."""
+
+    def __init__(self, num_fields, cin_layer_units):
+        super().__init__()
+        self.cin_layer_units = list(cin_layer_units)
+        self.num_fields = num_fields
+        self.cin_layer = nn.ModuleDict()
+        for i, unit in enumerate(self.cin_layer_units):
+            in_channels = num_fields * self.cin_layer_units[i - 1] if i > 0 else num_fields ** 2
+            self.cin_layer["layer_" + str(i + 1)] = Conv1dK1(in_channels, unit)
+
+    def forward(self, X_0):
+        B, F, D = X_0.shape
+        x0 = Fn.CINRelayoutFn.apply(X_0)   # [B*D, F]
+        xi, M = x0, F
+        pooled = []
+        for i, O in enumerate(self.cin_layer_units):
+            layer = self.cin_layer["layer_" + str(i + 1)]
+            K8 = (F * M + 7) // 8 * 8
+            Op = max(8, (O + 3) // 4 * 4)
+            z = Fn.CINHadamardFn.apply(x0, xi, K8)                                         # [B*D, K8]
+            w = Fn.PadMatrixFn.apply(layer.weight.view(O, F * M), Op, K8)
+            b = Fn.PadMatrixFn.apply(layer.bias.view(1, O), 1, Op).view(Op)
+            y = Fn.LinearFn.apply(z, w, b, False)                                          # [B*D, Op]; columns >= O are zero
+            pooled.append(Fn.CINPoolFn.apply(y, B, D, O))
+            xi, M = y[:, :O], O
+        return torch.cat(pooled, dim=-1)   # layout glue only (layers.py:720)

@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import functional as Fn
-from .layers import CrossNetV2, Embeddings, InnerProductLayer, Linear, MLPBlock, TableEmbedding
+from .layers import CIN, CrossNetV2, Embeddings, InnerProductLayer, Linear, MLPBlock, TableEmbedding
 from .nce import IndexLinear
 
 logger = logging.getLogger(__name__)
@@ -46,7 +46,9 @@ class BaseModel(nn.Module):
             model_class = DeepFM
         elif name == "dcnv2":
             model_class = DCNV2
-        elif name in ("autoint", "trans", "fignn", "fgcnn", "xdeepfm"):
+        elif name == "xdeepfm":
+            model_class = xDeepFM
+        elif name in ("autoint", "trans", "fignn", "fgcnn"):
             raise NotImplementedError(f"{config.model_name}: backbone outside the accelerated hot path (SURVEY.md §8f)")
         else:
             raise NotImplementedError(config.model_name)
@@ -125,6 +127,15 @@ class LR(BaseModel):
         self.bias = nn.Parameter(torch.zeros(1), requires_grad=True)
 
 
+    def forward(self, input_ids, labels=None):
+        """models.py:137-143: logits = sum_f w[ids[b,f]] + bias (used by xDeepFM with use_lr; DeepFM goes through the fused
+        FM + LR kernel instead)."""
+        wx = self.embed_w(input_ids)            # [B, F, 1]
+        ones = torch.ones(wx.shape[1], 1, dtype=torch.float32, device=wx.device)
+        logits = Fn.LinearFn.apply(wx.view(wx.shape[0], -1), ones.view(1, -1), self.bias, False)
+        return self.get_outputs(logits, labels, is_pretrain=False)
+
+
 class DNN(BaseModel):
     used_params = ["embed_size", "hidden_size", "num_hidden_layers", "hidden_dropout_rate", "hidden_act"]
 
@@ -176,6 +187,43 @@ class DeepFM(BaseModel):
             return self.get_outputs(final_vec, labels, masked_index, noise_samples=noise_samples)
         logits = self.dnn_fc_out(dnn_vec)
         logits = logits + self._lr_fm(input_ids, feat_embed)
+        return self.get_outputs(logits, labels)
+
+
+class xDeepFM(BaseModel):
+    """models.py:235-279.  CIN over the field embeddings (+ an MLP tower), pretraining heads on cat([cin, dnn])."""
+    used_params = ["embed_size", "hidden_size", "num_hidden_layers", "hidden_dropout_rate", "hidden_act", "cin_layer_units", "use_lr"]
+
+    def __init__(self, config):
+        super().__init__(model_name="xDeepFM", config=config)
+        self.embed = Embeddings(config)
+        input_dim = config.num_fields * config.embed_size
+        cin_layer_units = [int(c) for c in str(config.cin_layer_units).split(",")]
+        self.cin = CIN(config.num_fields, cin_layer_units)
+        if config.num_hidden_layers > 0:
+            self.dnn = MLPBlock(input_dim=input_dim, hidden_size=config.hidden_size, num_hidden_layers=config.num_hidden_layers,
+                                hidden_dropout_rate=config.hidden_dropout_rate, hidden_act=config.hidden_act)
+            final_dim = sum(cin_layer_units) + config.hidden_size
+        else:
+            self.dnn = None
+            final_dim = sum(cin_layer_units)
+        if config.pretrain:
+            self.create_pretraining_predictor(final_dim)
+        else:
+            self.lr_layer = LR(config) if getattr(config, "use_lr", False) else None
+            self.fc = Linear(final_dim, 1)
+
+    def forward(self, input_ids, labels=None, masked_index=None, noise_samples=None):
+        feat_embed = self.embed(input_ids)
+        final_vec = self.cin(feat_embed)
+        if self.dnn is not None:
+            dnn_vec = self.dnn(feat_embed.flatten(start_dim=1))
+            final_vec = torch.cat([final_vec, dnn_vec], dim=1)   # layout glue only (models.py:269)
+        if self.config.pretrain:
+            return self.get_outputs(final_vec, labels, masked_index, noise_samples=noise_samples)
+        logits = self.fc(final_vec)
+        if self.lr_layer is not None:
+            logits = logits + self.lr_layer(input_ids)[0]
         return self.get_outputs(logits, labels)
 
 

@@ -437,6 +437,40 @@ def head_bwd_fold(dxpos: torch.Tensor, B: int, L: int, ncols: int, *, cross=None
     call("map_head_bwd_fold", C.byref(a), _stream())
 
 
+# ------------------------------------------------------------------------------------------------ K17: CIN (xDeepFM)
+def cin_relayout(src: torch.Tensor, dst: torch.Tensor, B: int, C: int, D: int, to_pairs: bool, accumulate: bool = False):
+    """to_pairs: src [B, C, D] -> dst [(b*D + d), c];  else: src pairs -> dst [B, C, D] (optionally accumulating)"""
+    pairs = dst if to_pairs else src
+    _lib.CURRENT_TAG = ("cin_relayout", B, C, D)
+    call("map_cin_relayout", src.data_ptr(), dst.data_ptr(), B, C, D, _ld(pairs), int(to_pairs), int(accumulate), _stream())
+    return dst
+
+
+def cin_hadamard_fwd(x0: torch.Tensor, xi: torch.Tensor, F: int, M: int, z: torch.Tensor) -> torch.Tensor:
+    """z[p, h*M + m] = x0[p, h] * xi[p, m] (layers.py:714-715), zero in the padding columns of z"""
+    _lib.CURRENT_TAG = ("cin_hadamard", x0.shape[0], F, M)
+    call("map_cin_hadamard_fwd", x0.data_ptr(), _ld(x0), xi.data_ptr(), _ld(xi), x0.shape[0], F, M, z.data_ptr(), _ld(z), _stream())
+    return z
+
+
+def cin_hadamard_bwd(dz: torch.Tensor, x0: torch.Tensor, xi: torch.Tensor, F: int, M: int, dx0: torch.Tensor, dxi: torch.Tensor,
+                     accumulate_dx0: bool = False):
+    _lib.CURRENT_TAG = ("cin_hadamard_bwd", x0.shape[0], F, M)
+    call("map_cin_hadamard_bwd", dz.data_ptr(), _ld(dz), x0.data_ptr(), _ld(x0), xi.data_ptr(), _ld(xi), x0.shape[0], F, M,
+         dx0.data_ptr(), _ld(dx0), int(accumulate_dx0), dxi.data_ptr(), _ld(dxi), _stream())
+
+
+def cin_pool_fwd(y: torch.Tensor, B: int, D: int, O: int, pooled: torch.Tensor) -> torch.Tensor:
+    call("map_cin_pool_fwd", y.data_ptr(), _ld(y), B, D, O, pooled.data_ptr(), _ld(pooled), _stream())
+    return pooled
+
+
+def cin_pool_bwd(d_pooled: torch.Tensor, B: int, D: int, O: int, dy: torch.Tensor, d_next: Optional[torch.Tensor] = None) -> torch.Tensor:
+    call("map_cin_pool_bwd", d_pooled.data_ptr(), _ld(d_pooled), _ptr(d_next), _ld(d_next) if d_next is not None else 0, B, D, O,
+         dy.data_ptr(), _ld(dy), _stream())
+    return dy
+
+
 _red_ws = {}
 
 

@@ -311,6 +311,23 @@ def fm_lr_forward(params, input_ids, feat_embed):
     return lr + ((sum_sq - sq_sum) * 0.5).sum(dim=-1, keepdim=True)
 
 
+def cin_forward(params: Dict[str, torch.Tensor], prefix: str, x0: torch.Tensor, units) -> torch.Tensor:
+    """CIN.forward, layers.py:709-721: hadamard[b, h*M + m, d] = X0[b,h,d] * Xi[b,m,d]; X_{i+1} = Conv1d(kernel 1)(hadamard);
+    pooled_i = X_{i+1}.sum(-1); output = cat(pooled)."""
+    B, _, D = x0.shape
+    xi, pooled = x0, []
+    for i in range(len(units)):
+        had = torch.einsum("bhd,bmd->bhmd", x0, xi).reshape(B, -1, D)
+        w, b = params[f"{prefix}.cin_layer.layer_{i + 1}.weight"], params[f"{prefix}.cin_layer.layer_{i + 1}.bias"]
+        xi = torch.nn.functional.conv1d(had, w, b).view(B, -1, D)
+        pooled.append(xi.sum(dim=-1))
+    return torch.cat(pooled, dim=-1)
+
+
+def cin_units(cfg):
+    return [int(c) for c in str(cfg.cin_layer_units).split(",")]
+
+
 class OracleConfig:
     """Attribute bag with the reference's config field names (arguments.py:103-157, run.py:49-61)."""
 
@@ -318,7 +335,7 @@ class OracleConfig:
         d = dict(model_name="DCNv2", embed_size=16, hidden_size=1000, num_hidden_layers=3, num_cross_layers=3,
                  hidden_act="relu", hidden_dropout_rate=0.0, embed_dropout_rate=0.0, embed_norm=False,
                  layer_norm_eps=1e-12, pt_neg_num=25, proj_size=32, input_size=None, num_fields=None,
-                 pretrain=True, pt_type="MFP", RFD_replace="Unigram")
+                 pretrain=True, pt_type="MFP", RFD_replace="Unigram", cin_layer_units="50,50", use_lr=False)
         d.update(kw)
         for k, v in d.items():
             setattr(self, k, v)
@@ -343,6 +360,11 @@ def backbone_forward(cfg, params: Dict[str, torch.Tensor], input_ids: torch.Tens
         return dnn_vec
     if name == "dnn":
         return mlp_block_forward(params, "dnn", flat, cfg.num_hidden_layers)
+    if name == "xdeepfm":   # xDeepFM.forward models.py:262-269
+        final = cin_forward(params, "cin", feat, cin_units(cfg))
+        if cfg.num_hidden_layers > 0:
+            final = torch.cat([final, mlp_block_forward(params, "dnn", flat, cfg.num_hidden_layers)], dim=1)
+        return final
     raise NotImplementedError(cfg.model_name)
 
 
@@ -378,6 +400,11 @@ def model_forward(cfg, params, input_ids, labels=None, masked_index=None, noise=
         feat = embeddings_forward(params["embed.embedding.weight"], input_ids)
         logits = torch.nn.functional.linear(final, params["dnn_fc_out.weight"], params["dnn_fc_out.bias"])
         logits = logits + fm_lr_forward(params, input_ids, feat)
+    elif name == "xdeepfm":  # models.py:273-276
+        logits = torch.nn.functional.linear(final, params["fc.weight"], params["fc.bias"])
+        if getattr(cfg, "use_lr", False):
+            wx = torch.nn.functional.embedding(input_ids, params["lr_layer.embed_w.weight"])
+            logits = logits + wx.sum(dim=1) + params["lr_layer.bias"]
     else:
         logits = torch.nn.functional.linear(final, params["fc_out.weight"], params["fc_out.bias"])
     if labels is None:
@@ -421,6 +448,22 @@ def init_params(cfg, feat_count: Optional[torch.Tensor], seed: int = 1) -> Dict[
             p["lr_layer.bias"] = torch.zeros(1)
             if cfg.pretrain:
                 final = H + 1
+    elif name == "xdeepfm":
+        units, prev = cin_units(cfg), F
+        for i, u in enumerate(units):
+            c_in = F * prev
+            bound = 1.0 / math.sqrt(c_in)
+            p[f"cin.cin_layer.layer_{i + 1}.weight"] = (torch.rand(u, c_in, 1, generator=g) * 2 - 1) * bound
+            p[f"cin.cin_layer.layer_{i + 1}.bias"] = (torch.rand(u, generator=g) * 2 - 1) * bound
+            prev = u
+        d = in_dim
+        for i in range(cfg.num_hidden_layers):
+            linear(f"dnn.dnn.{3 * i}", H, d)
+            d = H
+        final = sum(units) + (H if cfg.num_hidden_layers > 0 else 0)
+        if not cfg.pretrain and getattr(cfg, "use_lr", False):
+            p["lr_layer.embed_w.weight"] = torch.randn(V, 1, generator=g)
+            p["lr_layer.bias"] = torch.zeros(1)
     else:
         raise NotImplementedError(cfg.model_name)
     if cfg.pretrain:
@@ -437,7 +480,7 @@ def init_params(cfg, feat_count: Optional[torch.Tensor], seed: int = 1) -> Dict[
         else:
             raise NotImplementedError(cfg.pt_type)
     else:
-        linear("dnn_fc_out" if name == "deepfm" else "fc_out", 1, final)
+        linear({"deepfm": "dnn_fc_out", "xdeepfm": "fc"}.get(name, "fc_out"), 1, final)
     return p
 
 

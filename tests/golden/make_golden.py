@@ -225,7 +225,7 @@ def _grads(model):
 
 
 def golden_model(name, model_name, pt_type, pretrain=True, F=6, D=4, H=16, P=8, K=5, B=12, mask_ratio=0.34,
-                 field_sizes=(7, 40, 3, 120, 15, 60), steps=3):
+                 field_sizes=(7, 40, 3, 120, 15, 60), steps=3, extra=None):
     """A small model end-to-end through the reference: forward, backward, and `steps` HF-AdamW steps driven by the
     reference Trainer.get_optimizer (param grouping + cosine schedule: trainer.py:60-85)."""
     g = torch.Generator().manual_seed(11)
@@ -234,7 +234,7 @@ def golden_model(name, model_name, pt_type, pretrain=True, F=6, D=4, H=16, P=8, 
     torch.manual_seed(5)
     with tempfile.TemporaryDirectory() as tmp:
         cfg = make_config(tmp, model_name=model_name, pt_type=pt_type, pretrain=pretrain, input_size=V, num_fields=F,
-                          embed_size=D, hidden_size=H, proj_size=P, pt_neg_num=K, feat_count=feat_count)
+                          embed_size=D, hidden_size=H, proj_size=P, pt_neg_num=K, feat_count=feat_count, **(extra or {}))
         model = ref.models.BaseModel.from_config(cfg)
     L = int(F * mask_ratio)
     args = Args(pt_type=pt_type, mask_ratio=mask_ratio)
@@ -243,7 +243,7 @@ def golden_model(name, model_name, pt_type, pretrain=True, F=6, D=4, H=16, P=8, 
     sd0 = {k: v.clone() for k, v in model.state_dict().items()}
     rec = dict(config=dict(model_name=model_name, pt_type=pt_type, pretrain=pretrain, input_size=V, num_fields=F,
                            embed_size=D, hidden_size=H, proj_size=P, pt_neg_num=K, num_hidden_layers=3,
-                           num_cross_layers=3, mask_ratio=mask_ratio),
+                           num_cross_layers=3, mask_ratio=mask_ratio, **(extra or {})),
                feat_count=feat_count, X_train=X, state_dict0=sd0, steps=[],
                optim=dict(lr=1e-3, weight_decay=5e-2, eps=1e-8, betas=(0.9, 0.999), sched="cosine", t_total=10, t_warmup=2))
     gi = torch.Generator().manual_seed(3)
@@ -305,6 +305,8 @@ def _final(model, ids):
     dnn = model.dnn(fe.flatten(start_dim=1))
     if model.model_name == "DNN":   # DNN.forward models.py:183-186
         return dnn
+    if model.model_name == "xDeepFM":   # xDeepFM.forward models.py:262-269
+        return torch.cat([model.cin(fe), dnn], dim=1)
     return torch.cat([dnn, model.lr_layer(ids)[0] + model.ip_layer(fe)], dim=1)
 
 
@@ -321,3 +323,7 @@ if __name__ == "__main__":
     golden_model("dnn_mfp", "DNN", "MFP")          # models.py:164-193
     golden_model("dnn_rfd", "DNN", "RFD")
     golden_model("dnn_ctr", "DNN", "MFP", pretrain=False)
+    xd = dict(cin_layer_units="5,4", use_lr=True)  # models.py:235-279, layers.py:696-721; use_lr adds the LR term to the CTR logits
+    golden_model("xdeepfm_mfp", "xDeepFM", "MFP", extra=xd)
+    golden_model("xdeepfm_rfd", "xDeepFM", "RFD", extra=xd)
+    golden_model("xdeepfm_ctr", "xDeepFM", "MFP", pretrain=False, extra=xd)

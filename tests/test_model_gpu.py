@@ -19,6 +19,7 @@ from oracle import map_oracle as O
 pytestmark = pytest.mark.gpu
 
 CASES = ["dcnv2_mfp", "dcnv2_rfd", "dcnv2_ctr", "deepfm_mfp", "deepfm_ctr", "dnn_mfp", "dnn_rfd", "dnn_ctr"]
+MODULE_ONLY_CASES = ["xdeepfm_mfp", "xdeepfm_rfd", "xdeepfm_ctr"]   # backbones without a fused schedule (module path: autograd over our kernels)
 
 
 def make_config(g, table_grad_mode="dense", tmp=None):
@@ -64,10 +65,10 @@ def tf32_tol_for(case):
 
 
 @pytest.mark.parametrize("backend", ["simt", "tcgen05", "bf16s"])
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + MODULE_ONLY_CASES)
 def test_modules_vs_reference_golden(golden, case, backend, monkeypatch):
     """model(**inputs) -> loss.backward() -> AdamW.step() through the reference-shaped module API, three steps."""
-    if backend == "tcgen05" and case.startswith("dnn"):
+    if backend == "tcgen05" and (case.startswith("dnn") or case.startswith("xdeepfm")):
         pytest.skip("TF32 is the A/B backend only; at batch 12 the all-ReLU DNN backbone amplifies its operand truncation to 1e-1")
     monkeypatch.setenv("MAP_B200_GEMM", backend)
     from map_code_b200.optim import AdamW
@@ -172,6 +173,30 @@ def test_fused_step_vs_reference_golden(golden, case, backend):
         if backend == "simt":
             for k, pref in st["state_dict_after"].items():
                 torch.testing.assert_close(named[k].detach().cpu(), pref, rtol=2e-4, atol=2e-6, msg=lambda m, k=k: f"param {k}: {m}")
+
+
+@pytest.mark.parametrize("backend", ["simt", "bf16s"])
+def test_cin_vs_reference_formulation(backend, monkeypatch):
+    """layers.CIN (pair-major GEMMs, csrc/cin.cu) at the Criteo shape against the reference's einsum + Conv1d formulation
+    (oracle.cin_forward, fp64): output and every gradient."""
+    monkeypatch.setenv("MAP_B200_GEMM", backend)
+    from map_code_b200.layers import CIN
+    torch.manual_seed(3)
+    B, F, D, units = 96, 39, 16, [50, 50]
+    cin = CIN(F, units).cuda()
+    x = (torch.randn(B, F, D) * 0.3).cuda().requires_grad_(True)
+    out = cin(x)
+    gout = torch.randn(B, sum(units), device="cuda")
+    out.backward(gout)
+    params = {"cin." + k: v.detach().double().cpu().requires_grad_(True) for k, v in cin.state_dict().items()}
+    x64 = x.detach().double().cpu().requires_grad_(True)
+    ref = O.cin_forward(params, "cin", x64, units)
+    ref.backward(gout.double().cpu())
+    tol = 2e-5 if backend == "simt" else 3e-4
+    assert relerr(out, ref) < tol, relerr(out, ref)
+    assert relerr(x.grad, x64.grad) < tol, relerr(x.grad, x64.grad)
+    for k, p in cin.named_parameters():
+        assert relerr(p.grad, params["cin." + k].grad) < tol, (k, relerr(p.grad, params["cin." + k].grad))
 
 
 def _synthetic_setup(pt_type, pretrain=True, F=39, D=16, H=64, P=32, K=25, B=512, n_train=4096, seed=0):

@@ -29,7 +29,8 @@ def make(pt_type="MFP", pretrain=True, model_name="DCNv2", tmp="."):
     cfg = Config.from_dict(dict(model_name=model_name, embed_size=16, hidden_size=64, num_hidden_layers=3, num_cross_layers=3,
                                 hidden_act="relu", hidden_dropout_rate=0.0, embed_dropout_rate=0.0, embed_norm=False, layer_norm_eps=1e-12,
                                 pt_neg_num=25, proj_size=32, input_size=V, num_fields=F, pretrain=pretrain, pt_type=pt_type,
-                                RFD_replace="Unigram", feat_count=S.feat_count(X, V), data_dir=None, seed=42, table_grad_mode="sparse"))
+                                RFD_replace="Unigram", feat_count=S.feat_count(X, V), data_dir=None, seed=42, table_grad_mode="sparse",
+                                cin_layer_units="20,12", use_lr=True))
     args = TrainingArguments(output_dir=str(tmp), per_gpu_train_batch_size=256, per_gpu_eval_batch_size=512, learning_rate=1e-3,
                              weight_decay=5e-2, num_train_epochs=2, lr_sched="cosine", logging_steps=2, sampling_method="randint",
                              mask_ratio=0.1, pretrain=pretrain, pt_type=pt_type, seed=42)
@@ -39,7 +40,7 @@ def make(pt_type="MFP", pretrain=True, model_name="DCNv2", tmp="."):
     return model, cfg, args, train, valid
 
 
-@pytest.mark.parametrize("model_name", ["DCNv2", "DeepFM"])
+@pytest.mark.parametrize("model_name", ["DCNv2", "DeepFM", "xDeepFM"])   # xDeepFM: module path (autograd over our kernels), no fused schedule
 @pytest.mark.parametrize("pt_type", ["MFP", "RFD"])
 def test_pretrain_loop_runs_and_learns(pt_type, model_name, tmp_path):
     from map_code_b200.trainer import Trainer
@@ -59,7 +60,7 @@ def test_pretrain_loop_runs_and_learns(pt_type, model_name, tmp_path):
     assert torch.equal(m2.embed.embedding.weight.detach().cpu(), sd["embed.embedding.weight"])
 
 
-@pytest.mark.parametrize("model_name", ["DCNv2", "DeepFM"])
+@pytest.mark.parametrize("model_name", ["DCNv2", "DeepFM", "xDeepFM"])
 def test_ctr_train_eval_test(model_name, tmp_path):
     from map_code_b200.trainer import Trainer
     model, cfg, args, train, valid = make("MFP", False, model_name, tmp_path)
@@ -89,7 +90,7 @@ def test_dynamic_mask_api_and_errors(tmp_path):
     with pytest.raises(NotImplementedError):
         tr.dynamic_mask({"input_ids": X.clone()}, "randint")
     from map_code_b200.models import BaseModel
-    cfg.model_name = "xdeepfm"
+    cfg.model_name = "autoint"   # backbones outside SURVEY §8 raise like an unknown name would
     with pytest.raises(NotImplementedError):
         BaseModel.from_config(cfg)
 
