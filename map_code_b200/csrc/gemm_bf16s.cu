@@ -63,6 +63,10 @@ struct SGroupArgs {
     int seq[kSMaxGroup], seq_end[kSMaxGroup];
     int stages, stage_bytes;            // one ring geometry for the whole launch (the largest problem's planes)
     unsigned long long* trace;          // optional per-CTA timeline (map_gemm_bf16s_set_trace), nullptr in production
+    // dynamic tile scheduler: sched[0] = next sequence position to hand out, sched[1] = clusters that have run dry.  Both are 0
+    // between launches (the last cluster to run dry resets them), so a captured launch can be replayed without a memset node.
+    // nullptr = static snake order (MAP_B200_GEMM_SCHED=static, A/B)
+    unsigned* sched;
 };
 
 // trace record of one CTA: 64 x u64 = {globaltimer at entry, clock after setup, globaltimer at exit, smid | tiles << 32,
@@ -130,6 +134,67 @@ __device__ __forceinline__ int snake_tile(int i, int c, int n, int total) {
     return t < total ? t : -1;
 }
 
+// ---- tile scheduler.  The pair's leader CTA decides which sequence position the cluster works on next and publishes it through
+// a small ring (one copy in each CTA's shared memory) to every role of both CTAs: its own TMA producer, the peer's producer, the
+// MMA issuer, the 8 + 8 epilogue warps.  Dynamic mode: positions come from a global counter in the launch's sequence order
+// (descending per-tile cost = longest-processing-time-first list scheduling), so a cluster that starts late — its SMs were still
+// held by a kernel of another stream — or that drew tiles with long epilogues simply takes fewer tiles; the static snake order
+// made the whole launch wait for the unluckiest cluster (r02c traces: per-CTA lifetime median 86 us, max 112 us on the 4-problem
+// backward levels).  -1 closes the sequence.
+constexpr int kSchedDepth = 4;
+constexpr int kSchedConsumers = 2 * kSEpiWarps + 2;   // leader: MMA issuer + epilogue warps; peer: TMA producer + epilogue warps
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquires what a thread of the OTHER CTA released
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+// one lane of the (converged) warp; the same lane every time
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+// consumer side: the j-th tile of this cluster (all calling threads get it); `arrive` = this thread reports the slot as read
+__device__ __forceinline__ int sched_read(const uint64_t* full, const uint64_t* empty, const int* tiles, int j, bool arrive) {
+    const int slot = j % kSchedDepth;
+    mbar_wait_cluster(smem_u32(&full[slot]), (uint32_t)(j / kSchedDepth) & 1u);
+    const int t = *reinterpret_cast<const volatile int*>(&tiles[slot]);
+    if (arrive) mbar_arrive_cta0(smem_u32(&empty[slot]));
+    return t;
+}
+// leader's producer: publish the cluster's j-th tile to both CTAs
+__device__ __forceinline__ void sched_publish(uint64_t* full, uint64_t* empty, int* tiles, int j, int t) {
+    const int slot = j % kSchedDepth;
+    if (j >= kSchedDepth) mbar_wait_quiet(smem_u32(&empty[slot]), (uint32_t)(j / kSchedDepth - 1) & 1u);
+    *reinterpret_cast<volatile int*>(&tiles[slot]) = t;
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_rank(smem_u32(&tiles[slot]), 1u)), "r"(t) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(smem_u32(&full[slot]), 0u)) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(smem_u32(&full[slot]), 1u)) : "memory");
+}
+
 template <int E0, int E1, int E2, int E3>
 __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_constant__ SGroupArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -139,8 +204,12 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(8) uint64_t sched_full[kSchedDepth];
+    __shared__ __align__(8) uint64_t sched_empty[kSchedDepth];   // the leader's copy is the one in use
+    __shared__ int sched_tile[kSchedDepth];
+    __shared__ int sched_count;   // tiles this cluster processed (trace only)
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // (the shuffle makes it provably warp-uniform)
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
     const int cluster_id = (int)(blockIdx.x >> 1);
@@ -151,6 +220,10 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
     unsigned long long* trace = g.trace != nullptr ? g.trace + (size_t)kSTraceWords * blockIdx.x : nullptr;
     if (trace != nullptr && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
+    // the cluster's first sequence position is requested before the setup below: the atomic's round trip hides behind it
+    int t_first = 0;
+    if (warp == 0 && lane == 0 && cta_rank == 0)
+        t_first = g.sched != nullptr ? (int)atomicAdd(g.sched, 1u) : snake_tile(0, cluster_id, n_clusters, total);
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 2 * g.count; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmap[i]) : "memory");
         for (int s = 0; s < stages; ++s) {
@@ -160,6 +233,10 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tmem_full_bar[b]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[b]), 2 * kSEpiWarps);   // the epilogue warps of both CTAs of the pair (leader's barrier)
+        }
+        for (int d = 0; d < kSchedDepth; ++d) {
+            mbar_init(smem_u32(&sched_full[d]), 1);
+            mbar_init(smem_u32(&sched_empty[d]), kSchedConsumers);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,9 +255,22 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
         if (lane == 0) {  // ===================== TMA producer (each CTA: its A rows, its half of B) =====================
             int s = 0;
             uint32_t ph = 0;
-            int tj = 0;
-            for (int t; (t = snake_tile(tj, cluster_id, n_clusters, total)) >= 0; ++tj) {
+            // leader: source of the cluster's tile sequence (global counter or snake order); t_next = position of the tile after this one
+            const bool dynamic = g.sched != nullptr;
+            int t_next = t_first;
+            for (int tj = 0;; ++tj) {
+                int t;
+                if (cta_rank == 0) {
+                    t = (t_next >= 0 && t_next < total) ? t_next : -1;
+                    sched_publish(sched_full, sched_empty, sched_tile, tj, t);
+                } else {
+                    t = sched_read(sched_full, sched_empty, sched_tile, tj, true);
+                }
+                if (t < 0) break;
                 const TileInfo ti = decode_tile(g, t);
+                // the next position is requested a few k-blocks before this tile's loads end: late enough that a cluster does not
+                // sit on a tile it will not start for a long time, early enough to hide the atomic's round trip
+                const int fetch_at = ti.nkb > 3 ? ti.nkb - 3 : 0;
                 const CUtensorMap* tmap_a = &g.tmap[2 * ti.gi];
                 const CUtensorMap* tmap_b = tmap_a + 1;
                 const int m0 = (ti.m_pair * 2 + (int)cta_rank) * kBlockM;
@@ -188,6 +278,8 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
                 const uint32_t tx_bytes = (uint32_t)(ti.pa * kSPlaneA + ti.pb * ti.b_plane_bytes);
                 const int b_chunks = ti.half_n >> 6;
                 for (int i = 0; i < ti.nkb; ++i) {
+                    if (cta_rank == 0 && i == fetch_at)
+                        t_next = dynamic ? (int)atomicAdd(g.sched, 1u) : snake_tile(tj + 1, cluster_id, n_clusters, total);
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                     if (trace != nullptr && i == 0 && tj < kSTraceTiles) trace[4 + 6 * tj] = (unsigned long long)clock64();
                     // both CTAs' loads complete on the LEADER's full barrier (its MMA reads both shared memories)
@@ -216,61 +308,87 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
+            if (cta_rank == 0 && dynamic) {   // this cluster has drawn its one position past the end; the last one to do so re-arms the counters
+                if (atomicAdd(g.sched + 1, 1u) == (unsigned)(n_clusters - 1)) {
+                    g.sched[0] = 0u;
+                    g.sched[1] = 0u;
+                    __threadfence();
+                }
+            }
         }
     } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {  // ===================== MMA issuer (the pair's leader) =====================
+        if (cta_rank == 0) {  // ===================== MMA issuer (the pair's leader) =====================
+            // The WHOLE warp walks the loop with warp-uniform control flow and one elected lane issues: tcgen05.mma / commit take
+            // their descriptors from uniform registers, and inside an `if (lane == 0)` region the compiler cannot prove uniformity —
+            // it wrapped every MMA in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY loop (~170 clk per MMA issued, r02c traces: the
+            // main loop ran at the issue rate of this one thread, not at the tensor pipe's 128 clk).  Everything the descriptors
+            // depend on is made provably uniform: the warp index and the values read from shared memory go through a shuffle.
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             int s = 0;
             uint32_t ph = 0;
             AccState acc{{0u, 0u}, 0u};
-            int tj = 0;
-            for (int t; (t = snake_tile(tj, cluster_id, n_clusters, total)) >= 0; ++tj) {
+            for (int tj = 0;; ++tj) {
+                int t = sched_read(sched_full, sched_empty, sched_tile, tj, lane == 0);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t < 0) break;
                 const TileInfo ti = decode_tile(g, t);
                 const bool dual = ti.terms == 6;
                 const uint32_t buf = acc_pick(acc, dual);
                 // the epilogue of the tile that last used this accumulator has drained it
-                mbar_wait(smem_u32(&tmem_empty_bar[buf]), (acc.uses[buf] & 1u) ^ 1u);
-                if (dual) mbar_wait(smem_u32(&tmem_empty_bar[1]), (acc.uses[1] & 1u) ^ 1u);
+                mbar_wait_quiet(smem_u32(&tmem_empty_bar[buf]), (acc.uses[buf] & 1u) ^ 1u);
+                if (dual) mbar_wait_quiet(smem_u32(&tmem_empty_bar[1]), (acc.uses[1] & 1u) ^ 1u);
                 tcgen05_fence_after();
-                if (trace != nullptr && tj < kSTraceTiles) trace[5 + 6 * tj] = (unsigned long long)clock64();
+                if (trace != nullptr && tj < kSTraceTiles && lane == 0) trace[5 + 6 * tj] = (unsigned long long)clock64();
                 const uint32_t idesc = make_idesc_bf16(ti.block_n, ti.trans_a, ti.trans_b, 2 * kBlockM);
                 // K-major  (SWIZZLE_128B): 8-row groups 1024 B apart (SBO); one MMA consumes 32 B of every row -> +32 B per K step
                 // MN-major (SWIZZLE_128B): 64-element chunks 8192 B apart (LBO); 8-k-row groups 1024 B apart (SBO); one MMA
                 //                          consumes 16 k-rows -> +2048 B per K step
-                const uint32_t a_lbo = ti.trans_a ? (uint32_t)kSChunk : 16u, a_adv = ti.trans_a ? 2048u : 32u;
-                const uint32_t b_lbo = ti.trans_b ? (uint32_t)kSChunk : 16u, b_adv = ti.trans_b ? 2048u : 32u;
-                const uint32_t d_tmem = tmem_base + buf * (uint32_t)kSAccCols;
-                const uint32_t d_corr = tmem_base + (uint32_t)kSAccCols;   // two-accumulator tiles: corrections in buffer 1
-                const uint32_t a_planes_bytes = (uint32_t)(ti.pa * kSPlaneA);
+                // descriptor = constant high word | low word {start >> 4, LBO >> 4 << 16}: only the start address moves
+                const uint32_t a_lbo = ti.trans_a ? (uint32_t)kSChunk : 16u, a_adv16 = ti.trans_a ? (2048u >> 4) : (32u >> 4);
+                const uint32_t b_lbo = ti.trans_b ? (uint32_t)kSChunk : 16u, b_adv16 = ti.trans_b ? (2048u >> 4) : (32u >> 4);
+                const uint32_t d_hi = (uint32_t)(make_smem_desc(0u, 0u, 1024u, 2u) >> 32);
+                const uint32_t a_lo0 = (uint32_t)make_smem_desc(0u, a_lbo, 0u, 0u), b_lo0 = (uint32_t)make_smem_desc(0u, b_lbo, 0u, 0u);
+                const uint32_t d_tmem = tmem_u + buf * (uint32_t)kSAccCols;
+                const uint32_t d_corr = tmem_u + (uint32_t)kSAccCols;   // two-accumulator tiles: corrections in buffer 1
+                const uint32_t a_planes16 = (uint32_t)(ti.pa * kSPlaneA) >> 4;
+                const uint32_t b_plane16 = (uint32_t)ti.b_plane_bytes >> 4;
+                const int terms = ti.terms;
                 for (int i = 0; i < ti.nkb; ++i) {
-                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    mbar_wait_quiet(smem_u32(&full_bar[s]), ph);
                     tcgen05_fence_after();
-                    if (trace != nullptr && i == 0 && tj < kSTraceTiles) trace[6 + 6 * tj] = (unsigned long long)clock64();
-                    const uint32_t a_src = smem_base + (uint32_t)s * stage_bytes;
-                    const uint32_t b_src = a_src + a_planes_bytes;
-                    // products ordered (a plane, b plane): (0,0) (0,1) (1,0) | (1,1) (0,2) (2,0)
-                    for (int term = 0; term < ti.terms; ++term) {
-                        const int ia = (term == 2 || term == 3) ? 1 : (term == 5 ? 2 : 0);
-                        const int ib = (term == 1 || term == 3) ? 1 : (term == 4 ? 2 : 0);
-                        const uint32_t a_pl = a_src + (uint32_t)(ia * kSPlaneA);
-                        const uint32_t b_pl = b_src + (uint32_t)(ib * ti.b_plane_bytes);
+                    __syncwarp();
+                    if (trace != nullptr && i == 0 && tj < kSTraceTiles && lane == 0) trace[6 + 6 * tj] = (unsigned long long)clock64();
+                    const uint32_t a16 = (smem_base + (uint32_t)s * stage_bytes) >> 4;   // (all offsets are multiples of 16 bytes)
+                    const uint32_t b16 = a16 + a_planes16;
+                    if (elect_one()) {
+                        // products ordered (a plane, b plane): (0,0) (0,1) (1,0) | (1,1) (0,2) (2,0)
+                        for (int term = 0; term < terms; ++term) {
+                            const uint32_t ia = (term == 2 || term == 3) ? 1u : (term == 5 ? 2u : 0u);
+                            const uint32_t ib = (term == 1 || term == 3) ? 1u : (term == 4 ? 2u : 0u);
+                            const uint32_t a_pl = a16 + ia * (uint32_t)(kSPlaneA >> 4);
+                            const uint32_t b_pl = b16 + ib * b_plane16;
+                            const uint32_t d = (dual && term > 0) ? d_corr : d_tmem;
+                            const uint32_t first = (dual && term > 0) ? (uint32_t)(i | (term - 1)) : (uint32_t)(i | term);
 #pragma unroll
-                        for (int k = 0; k < kSBlockK / kSUmmaK; ++k) {
-                            const uint64_t da = make_smem_desc(a_pl + k * a_adv, a_lbo, 1024u, 2u);
-                            const uint64_t db = make_smem_desc(b_pl + k * b_adv, b_lbo, 1024u, 2u);
-                            if (dual && term > 0) umma_bf16_pair(d_corr, da, db, idesc, (i | (term - 1) | k) != 0 ? 1u : 0u);
-                            else umma_bf16_pair(d_tmem, da, db, idesc, (i | term | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < kSBlockK / kSUmmaK; ++k) {
+                                const uint64_t da = ((uint64_t)d_hi << 32) | (uint64_t)(a_lo0 | ((a_pl + k * a_adv16) & 0x3FFFu));
+                                const uint64_t db = ((uint64_t)d_hi << 32) | (uint64_t)(b_lo0 | ((b_pl + k * b_adv16) & 0x3FFFu));
+                                umma_bf16_pair(d, da, db, idesc, (first | (uint32_t)k) != 0u ? 1u : 0u);
+                            }
                         }
+                        tcgen05_commit_pair(smem_u32(&empty_bar[s]));   // frees the stage in both CTAs when these MMAs have read it
                     }
-                    tcgen05_commit_pair(smem_u32(&empty_bar[s]));   // frees the stage in both CTAs when these MMAs have read it
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                tcgen05_commit_pair(smem_u32(&tmem_full_bar[buf]));  // accumulator complete (both CTAs' epilogues)
-                if (trace != nullptr && tj < kSTraceTiles) trace[7 + 6 * tj] = (unsigned long long)clock64();
-                ++acc.uses[buf];
-                if (dual) {
-                    tcgen05_commit_pair(smem_u32(&tmem_full_bar[1]));
-                    ++acc.uses[1];
+                if (elect_one()) {
+                    tcgen05_commit_pair(smem_u32(&tmem_full_bar[buf]));  // accumulator complete (both CTAs' epilogues)
+                    if (dual) tcgen05_commit_pair(smem_u32(&tmem_full_bar[1]));
                 }
+                __syncwarp();
+                if (trace != nullptr && tj < kSTraceTiles && lane == 0) trace[7 + 6 * tj] = (unsigned long long)clock64();
+                ++acc.uses[buf];
+                if (dual) ++acc.uses[1];
             }
         }
     } else {
@@ -280,7 +398,14 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
         float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stages * stage_bytes) + (warp - 2) * (32 * kStageLd16);
         AccState acc{{0u, 0u}, 0u};
         int tj = 0;
-        for (int t; (t = snake_tile(tj, cluster_id, n_clusters, total)) >= 0; ++tj) {
+        for (;; ++tj) {
+            const int t = sched_read(sched_full, sched_empty, sched_tile, tj, false);
+            __syncwarp();   // every lane has read the slot before lane 0 hands it back
+            if (lane == 0) mbar_arrive_cta0(smem_u32(&sched_empty[tj % kSchedDepth]));
+            if (t < 0) {
+                if (threadIdx.x == 64) sched_count = tj;
+                break;
+            }
             const TileInfo ti = decode_tile(g, t);
             const bool dual = ti.terms == 6;
             const uint32_t buf = acc_pick(acc, dual);
@@ -318,8 +443,12 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
     if (trace != nullptr && threadIdx.x == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        int my_tiles = 0;
-        while (snake_tile(my_tiles, cluster_id, n_clusters, total) >= 0) ++my_tiles;
+        int my_tiles = 0;   // (the closing -1 has been published by now: the ring still holds the last kSchedDepth entries)
+        if (g.sched == nullptr) {
+            while (snake_tile(my_tiles, cluster_id, n_clusters, total) >= 0) ++my_tiles;
+        } else {
+            my_tiles = *reinterpret_cast<volatile int*>(&sched_count);
+        }
         trace[2] = globaltimer_ns();
         trace[3] = (unsigned long long)smid | ((unsigned long long)my_tiles << 32);
     }
@@ -472,7 +601,8 @@ static int find_scombo(const int* e, int count) {
 // busiest cluster.  K-major B takes any multiple of 16 (<= 256); MN-major B whole 64-column chunks per CTA half: 128 or 256.
 struct TileModel {
     int block_n, n_tiles, m_pairs, split, nkb, tiles;
-    double cost;
+    double cost;      // time a cluster is busy with one tile when its epilogue overlaps the next tile's main loop
+    double latency;   // main loop + the whole epilogue: what a tile costs when it is a cluster's LAST one
 };
 static const double kEpiCol[] = {15, 23, 25, 45, 60, 45, 60, 150, 47};   // epilogue clk per column: NONE, BIAS, BIAS_RELU, CROSS, RELUMASK, ADD, ADD_MUL, CROSS_BWD, ADD3
 
@@ -508,13 +638,30 @@ static TileModel model_tile(const map_gemm_split_args* a, int bn) {
     const double per_kb = bytes / 30.0 > mma ? bytes / 30.0 : mma;
     const double epi = kEpiCol[g->epilogue] * bn + (a->c_planes ? 10.0 * a->c_nplanes * bn : 0.0);
     t.cost = t.nkb * per_kb * (a->terms == 6 ? 1.1 : 1.0) + (a->terms == 6 ? epi : 0.35 * epi) + 1500.0;
+    t.latency = t.nkb * per_kb * (a->terms == 6 ? 1.1 : 1.0) + epi + 1500.0;
     return t;
 }
 
+// MAP_B200_GEMM_SCHED=static: snake order instead of the global tile counter (A/B)
+static bool sched_dynamic() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MAP_B200_GEMM_SCHED");
+        v = (e != nullptr && strcmp(e, "static") == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// position of a problem's tiles in the launch's sequence (descending).  Static snake: per-tile busy time.  Dynamic: the tile's whole
+// latency — longest-processing-time-first, and the tiles that close the launch are the ones with the shortest exposed epilogue
+// (split-K weight gradients: plain stores) instead of a CrossNet-backward tile with six streamed operands
+static double seq_key(const TileModel& t, bool dynamic) { return dynamic ? t.latency : t.cost; }
+
 static double simulate_makespan(const TileModel* tm, int count, int clusters) {
     int order[kSMaxGroup] = {0, 1, 2, 3};
+    const bool dynamic = sched_dynamic();
     for (int i = 1; i < count; ++i)
-        for (int j = i; j > 0 && tm[order[j]].cost > tm[order[j - 1]].cost; --j) {
+        for (int j = i; j > 0 && seq_key(tm[order[j]], dynamic) > seq_key(tm[order[j - 1]], dynamic); --j) {
             const int tmp = order[j]; order[j] = order[j - 1]; order[j - 1] = tmp;
         }
     double load[kNumSMs / 2] = {};
@@ -522,8 +669,14 @@ static double simulate_makespan(const TileModel* tm, int count, int clusters) {
     for (int oi = 0; oi < count; ++oi) {
         const TileModel& t = tm[order[oi]];
         for (int k = 0; k < t.tiles; ++k, ++pos) {
-            const int round = pos / clusters, c = pos % clusters;
-            load[(round & 1) ? clusters - 1 - c : c] += t.cost;
+            if (dynamic) {   // list scheduling: the next tile of the sequence goes to the cluster that runs dry first
+                int c = 0;
+                for (int i = 1; i < clusters; ++i) c = load[i] < load[c] ? i : c;
+                load[c] += t.cost;
+            } else {
+                const int round = pos / clusters, c = pos % clusters;
+                load[(round & 1) ? clusters - 1 - c : c] += t.cost;
+            }
         }
     }
     double mx = 0;
@@ -618,11 +771,36 @@ static void plan_block_n_search(const map_gemm_split_args* sorted, int count, in
 static unsigned long long* g_strace_buf = nullptr;
 static int64_t g_strace_words = 0;
 
+// counters of the dynamic tile scheduler: one {next, done} pair per launch, handed out round-robin.  A pair is 0 whenever no launch
+// is using it (the kernel re-arms it), so captured launches replay without a memset; kSchedPairs launches later the pair is reused.
+constexpr int kSchedPairs = 1024;
+static unsigned* g_sched_buf = nullptr;
+static int g_sched_pos = 0;
+
+static int sched_counters(cudaStream_t st, unsigned** out) {
+    *out = nullptr;
+    if (!sched_dynamic()) return MAP_OK;
+    if (g_sched_buf == nullptr) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        MAP_REQUIRE(cs == cudaStreamCaptureStatusNone,
+                    "map_gemm_bf16s: the first launch of the process allocates the tile-scheduler counters and cannot be captured; run it once eagerly");
+        if (cudaMalloc(&g_sched_buf, kSchedPairs * 2 * sizeof(unsigned)) != cudaSuccess ||
+            cudaMemset(g_sched_buf, 0, kSchedPairs * 2 * sizeof(unsigned)) != cudaSuccess) {
+            set_error("map_gemm_bf16s: cannot allocate the tile-scheduler counters: %s", cudaGetErrorString(cudaGetLastError()));
+            g_sched_buf = nullptr;
+            return MAP_ECUDA;
+        }
+    }
+    *out = g_sched_buf + 2 * (g_sched_pos++ % kSchedPairs);
+    return MAP_OK;
+}
+
 static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo, cudaStream_t st) {
     SGroupArgs ga{};
     ga.count = count;
     int total = 0, stage_bytes = 0;
-    double cost[kSMaxGroup] = {0, 0, 0, 0};
+    double cost[kSMaxGroup] = {0, 0, 0, 0};   // sequence key of every problem (seq_key)
     int clusters = kNumSMs / 2;
     if (const char* e = getenv("MAP_B200_GEMM_CLUSTERS")) {
         const int c = atoi(e);
@@ -670,7 +848,7 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
         pr.n_tiles = (int)ceil_div(g->N, p.block_n);
         pr.n_pair_tiles = pr.m_pairs * pr.n_tiles * p.split_k;
         total += pr.n_pair_tiles;
-        cost[i] = model_tile(a, p.block_n).cost;
+        cost[i] = seq_key(model_tile(a, p.block_n), sched_dynamic());
         int rc;
         // A planes: K-major [M rows][K contiguous] box {64, 128}; MN-major [K rows][M contiguous] box {64, 64}
         if (!p.trans_a) rc = make_tmap_planes(&ga.tmap[2 * i], a->a_planes, g->K, g->M, a->a_ld, a->a_plane_stride, pr.pa, kBlockM);
@@ -721,6 +899,10 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
     }
     if (clusters > total) clusters = total;
     ga.trace = ((int64_t)2 * clusters * kSTraceWords <= g_strace_words) ? g_strace_buf : nullptr;
+    {
+        const int rc = sched_counters(st, &ga.sched);
+        if (rc != MAP_OK) return rc;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
     cfg.blockDim = dim3(kSThreads);
