@@ -79,6 +79,10 @@ constexpr int kSTraceTiles = 10;
 struct TileInfo {
     int gi, m_pair, n_tile, ks;
     int block_n, half_n, trans_a, trans_b, pa, pb, terms, nkb, kb0, b_plane_bytes;
+    // two-accumulator tile (terms = 6) wider than 128 columns: main and corrections take one 256-column buffer each, so the tile
+    // owns ALL of TMEM and its epilogue cannot overlap the next tile's MMAs.  Up to 128 columns both live in ONE buffer
+    // (corrections 128 columns after the main accumulator) and the tile double-buffers like a single-accumulator one.
+    bool wide_dual;
 };
 
 // TMEM accumulator buffers: a single-accumulator tile takes ONE of the two 256-column buffers (alternating, so its epilogue
@@ -125,6 +129,7 @@ __device__ __forceinline__ TileInfo decode_tile(const SGroupArgs& g, int t) {
     int nkb = kbt - ti.kb0;
     if (nkb > nkb_split) nkb = nkb_split;
     ti.nkb = nkb;
+    ti.wide_dual = ti.terms == 6 && ti.block_n > kSAccCols / 2;
     return ti;
 }
 
@@ -177,12 +182,20 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "=r"(pred));
     return pred != 0;
 }
-// consumer side: the j-th tile of this cluster (all calling threads get it); `arrive` = this thread reports the slot as read
-__device__ __forceinline__ int sched_read(const uint64_t* full, const uint64_t* empty, const int* tiles, int j, bool arrive) {
+// consumer side: the j-th tile of this cluster (all calling threads get it); `arrive` = this thread reports the slot as read.
+// `leader`: the caller runs in the leader CTA — publisher and barrier are in its own shared memory, CTA-scope ordering is enough
+// (cluster-scope acquire / release on every tile boundary showed up as ~2k clk in the per-tile traces)
+__device__ __forceinline__ void sched_release(const uint64_t* empty, int j, bool leader) {
+    const uint32_t bar = smem_u32(&empty[j % kSchedDepth]);
+    if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    else mbar_arrive_cta0(bar);
+}
+__device__ __forceinline__ int sched_read(const uint64_t* full, const uint64_t* empty, const int* tiles, int j, bool arrive, bool leader) {
     const int slot = j % kSchedDepth;
-    mbar_wait_cluster(smem_u32(&full[slot]), (uint32_t)(j / kSchedDepth) & 1u);
+    if (leader) mbar_wait_quiet(smem_u32(&full[slot]), (uint32_t)(j / kSchedDepth) & 1u);
+    else mbar_wait_cluster(smem_u32(&full[slot]), (uint32_t)(j / kSchedDepth) & 1u);
     const int t = *reinterpret_cast<const volatile int*>(&tiles[slot]);
-    if (arrive) mbar_arrive_cta0(smem_u32(&empty[slot]));
+    if (arrive) sched_release(empty, j, leader);
     return t;
 }
 // leader's producer: publish the cluster's j-th tile to both CTAs
@@ -252,25 +265,31 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
     if (trace != nullptr && threadIdx.x == 0) trace[1] = (unsigned long long)clock64();
 
     if (warp == 0) {
-        if (lane == 0) {  // ===================== TMA producer (each CTA: its A rows, its half of B) =====================
+        {   // ===================== TMA producer (each CTA: its A rows, its half of B) =====================
+            // whole warp, warp-uniform control flow, one elected lane issues (see the MMA issuer below: UTMALDG takes its operands from
+            // uniform registers too)
             int s = 0;
             uint32_t ph = 0;
             // leader: source of the cluster's tile sequence (global counter or snake order); t_next = position of the tile after this one
             const bool dynamic = g.sched != nullptr;
-            int t_next = t_first;
+            int t_next = __shfl_sync(0xffffffffu, t_first, 0);
             for (int tj = 0;; ++tj) {
                 int t;
                 if (cta_rank == 0) {
                     t = (t_next >= 0 && t_next < total) ? t_next : -1;
-                    sched_publish(sched_full, sched_empty, sched_tile, tj, t);
+                    if (lane == 0) sched_publish(sched_full, sched_empty, sched_tile, tj, t);
+                    __syncwarp();
                 } else {
-                    t = sched_read(sched_full, sched_empty, sched_tile, tj, true);
+                    t = sched_read(sched_full, sched_empty, sched_tile, tj, lane == 0, false);
+                    t = __shfl_sync(0xffffffffu, t, 0);
                 }
                 if (t < 0) break;
                 const TileInfo ti = decode_tile(g, t);
                 // the next position is requested a few k-blocks before this tile's loads end: late enough that a cluster does not
-                // sit on a tile it will not start for a long time, early enough to hide the atomic's round trip
+                // sit on a tile it will not start for a long time, early enough to hide the atomic's round trip (the value stays in
+                // lane 0 until the loads are out: broadcasting it at once would stall the warp on the atomic)
                 const int fetch_at = ti.nkb > 3 ? ti.nkb - 3 : 0;
+                int fetched = -1;
                 const CUtensorMap* tmap_a = &g.tmap[2 * ti.gi];
                 const CUtensorMap* tmap_b = tmap_a + 1;
                 const int m0 = (ti.m_pair * 2 + (int)cta_rank) * kBlockM;
@@ -278,37 +297,42 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
                 const uint32_t tx_bytes = (uint32_t)(ti.pa * kSPlaneA + ti.pb * ti.b_plane_bytes);
                 const int b_chunks = ti.half_n >> 6;
                 for (int i = 0; i < ti.nkb; ++i) {
-                    if (cta_rank == 0 && i == fetch_at)
-                        t_next = dynamic ? (int)atomicAdd(g.sched, 1u) : snake_tile(tj + 1, cluster_id, n_clusters, total);
-                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                    if (trace != nullptr && i == 0 && tj < kSTraceTiles) trace[4 + 6 * tj] = (unsigned long long)clock64();
-                    // both CTAs' loads complete on the LEADER's full barrier (its MMA reads both shared memories)
-                    if (cta_rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * tx_bytes);
+                    if (cta_rank == 0 && i == fetch_at && lane == 0)
+                        fetched = dynamic ? (int)atomicAdd(g.sched, 1u) : snake_tile(tj + 1, cluster_id, n_clusters, total);
+                    mbar_wait_quiet(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    __syncwarp();
+                    if (trace != nullptr && i == 0 && tj < kSTraceTiles && lane == 0) trace[4 + 6 * tj] = (unsigned long long)clock64();
                     const uint32_t fb = mapa_cta0(smem_u32(&full_bar[s]));
                     const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t b_dst = a_dst + (uint32_t)(ti.pa * kSPlaneA);
                     const int k0 = (ti.kb0 + i) * kSBlockK;
-                    for (int pl = 0; pl < ti.pa; ++pl) {
-                        if (!ti.trans_a) {
-                            tma_load_3d_pair(a_dst + pl * kSPlaneA, tmap_a, fb, k0, m0, pl);                      // box {64 k, 128 m}
-                        } else {
+                    if (elect_one()) {
+                        // both CTAs' loads complete on the LEADER's full barrier (its MMA reads both shared memories)
+                        if (cta_rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * tx_bytes);
+                        for (int pl = 0; pl < ti.pa; ++pl) {
+                            if (!ti.trans_a) {
+                                tma_load_3d_pair(a_dst + pl * kSPlaneA, tmap_a, fb, k0, m0, pl);                      // box {64 k, 128 m}
+                            } else {
 #pragma unroll
-                            for (int c = 0; c < kBlockM / 64; ++c)
-                                tma_load_3d_pair(a_dst + pl * kSPlaneA + c * kSChunk, tmap_a, fb, m0 + c * 64, k0, pl);   // box {64 m, 64 k}
+                                for (int c = 0; c < kBlockM / 64; ++c)
+                                    tma_load_3d_pair(a_dst + pl * kSPlaneA + c * kSChunk, tmap_a, fb, m0 + c * 64, k0, pl);   // box {64 m, 64 k}
+                            }
+                        }
+                        for (int pl = 0; pl < ti.pb; ++pl) {
+                            if (!ti.trans_b) {
+                                tma_load_3d_pair(b_dst + pl * ti.b_plane_bytes, tmap_b, fb, k0, nb, pl);              // box {64 k, half_n n}
+                            } else {
+                                for (int c = 0; c < b_chunks; ++c)
+                                    tma_load_3d_pair(b_dst + pl * ti.b_plane_bytes + c * kSChunk, tmap_b, fb, nb + c * 64, k0, pl);  // box {64 n, 64 k}
+                            }
                         }
                     }
-                    for (int pl = 0; pl < ti.pb; ++pl) {
-                        if (!ti.trans_b) {
-                            tma_load_3d_pair(b_dst + pl * ti.b_plane_bytes, tmap_b, fb, k0, nb, pl);              // box {64 k, half_n n}
-                        } else {
-                            for (int c = 0; c < b_chunks; ++c)
-                                tma_load_3d_pair(b_dst + pl * ti.b_plane_bytes + c * kSChunk, tmap_b, fb, nb + c * 64, k0, pl);  // box {64 n, 64 k}
-                        }
-                    }
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
+                t_next = __shfl_sync(0xffffffffu, fetched, 0);
             }
-            if (cta_rank == 0 && dynamic) {   // this cluster has drawn its one position past the end; the last one to do so re-arms the counters
+            if (cta_rank == 0 && dynamic && lane == 0) {   // this cluster has drawn its one position past the end; the last one to do so re-arms the counters
                 if (atomicAdd(g.sched + 1, 1u) == (unsigned)(n_clusters - 1)) {
                     g.sched[0] = 0u;
                     g.sched[1] = 0u;
@@ -328,15 +352,16 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
             uint32_t ph = 0;
             AccState acc{{0u, 0u}, 0u};
             for (int tj = 0;; ++tj) {
-                int t = sched_read(sched_full, sched_empty, sched_tile, tj, lane == 0);
+                int t = sched_read(sched_full, sched_empty, sched_tile, tj, lane == 0, true);
                 t = __shfl_sync(0xffffffffu, t, 0);
                 if (t < 0) break;
                 const TileInfo ti = decode_tile(g, t);
                 const bool dual = ti.terms == 6;
-                const uint32_t buf = acc_pick(acc, dual);
+                const bool wide = ti.wide_dual;
+                const uint32_t buf = acc_pick(acc, wide);
                 // the epilogue of the tile that last used this accumulator has drained it
                 mbar_wait_quiet(smem_u32(&tmem_empty_bar[buf]), (acc.uses[buf] & 1u) ^ 1u);
-                if (dual) mbar_wait_quiet(smem_u32(&tmem_empty_bar[1]), (acc.uses[1] & 1u) ^ 1u);
+                if (wide) mbar_wait_quiet(smem_u32(&tmem_empty_bar[1]), (acc.uses[1] & 1u) ^ 1u);
                 tcgen05_fence_after();
                 if (trace != nullptr && tj < kSTraceTiles && lane == 0) trace[5 + 6 * tj] = (unsigned long long)clock64();
                 const uint32_t idesc = make_idesc_bf16(ti.block_n, ti.trans_a, ti.trans_b, 2 * kBlockM);
@@ -349,7 +374,8 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
                 const uint32_t d_hi = (uint32_t)(make_smem_desc(0u, 0u, 1024u, 2u) >> 32);
                 const uint32_t a_lo0 = (uint32_t)make_smem_desc(0u, a_lbo, 0u, 0u), b_lo0 = (uint32_t)make_smem_desc(0u, b_lbo, 0u, 0u);
                 const uint32_t d_tmem = tmem_u + buf * (uint32_t)kSAccCols;
-                const uint32_t d_corr = tmem_u + (uint32_t)kSAccCols;   // two-accumulator tiles: corrections in buffer 1
+                // two-accumulator tiles: corrections in buffer 1 (wide) or in the upper half of the tile's own buffer
+                const uint32_t d_corr = wide ? tmem_u + (uint32_t)kSAccCols : d_tmem + (uint32_t)(kSAccCols / 2);
                 const uint32_t a_planes16 = (uint32_t)(ti.pa * kSPlaneA) >> 4;
                 const uint32_t b_plane16 = (uint32_t)ti.b_plane_bytes >> 4;
                 const int terms = ti.terms;
@@ -383,12 +409,12 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
                 }
                 if (elect_one()) {
                     tcgen05_commit_pair(smem_u32(&tmem_full_bar[buf]));  // accumulator complete (both CTAs' epilogues)
-                    if (dual) tcgen05_commit_pair(smem_u32(&tmem_full_bar[1]));
+                    if (wide) tcgen05_commit_pair(smem_u32(&tmem_full_bar[1]));
                 }
                 __syncwarp();
                 if (trace != nullptr && tj < kSTraceTiles && lane == 0) trace[7 + 6 * tj] = (unsigned long long)clock64();
                 ++acc.uses[buf];
-                if (dual) ++acc.uses[1];
+                if (wide) ++acc.uses[1];
             }
         }
     } else {
@@ -399,15 +425,15 @@ __global__ void __launch_bounds__(kSThreads, 1) gemm_bf16s_kernel(const __grid_c
         AccState acc{{0u, 0u}, 0u};
         int tj = 0;
         for (;; ++tj) {
-            const int t = sched_read(sched_full, sched_empty, sched_tile, tj, false);
+            const int t = sched_read(sched_full, sched_empty, sched_tile, tj, false, cta_rank == 0);
             __syncwarp();   // every lane has read the slot before lane 0 hands it back
-            if (lane == 0) mbar_arrive_cta0(smem_u32(&sched_empty[tj % kSchedDepth]));
+            if (lane == 0) sched_release(sched_empty, tj, cta_rank == 0);
             if (t < 0) {
                 if (threadIdx.x == 64) sched_count = tj;
                 break;
             }
             const TileInfo ti = decode_tile(g, t);
-            const bool dual = ti.terms == 6;
+            const bool dual = ti.wide_dual;   // (buffer bookkeeping only: the epilogue finds the corrections through p.corr_cols)
             const uint32_t buf = acc_pick(acc, dual);
             unsigned long long* ttr = (trace != nullptr && tj < kSTraceTiles) ? trace + 4 + 6 * tj : nullptr;   // epi_tile stamps [5], [6]
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)kSAccCols;
@@ -637,7 +663,8 @@ static TileModel model_tile(const map_gemm_split_args* a, int bn) {
     const double mma = a->terms * 4 * 128.0 * bn / 256.0;
     const double per_kb = bytes / 30.0 > mma ? bytes / 30.0 : mma;
     const double epi = kEpiCol[g->epilogue] * bn + (a->c_planes ? 10.0 * a->c_nplanes * bn : 0.0);
-    t.cost = t.nkb * per_kb * (a->terms == 6 ? 1.1 : 1.0) + (a->terms == 6 ? epi : 0.35 * epi) + 1500.0;
+    const bool wide_dual = a->terms == 6 && bn > kSAccCols / 2;   // owns all of TMEM: its whole epilogue is exposed
+    t.cost = t.nkb * per_kb * (a->terms == 6 ? 1.1 : 1.0) + (wide_dual ? epi : 0.35 * epi) + 1500.0;
     t.latency = t.nkb * per_kb * (a->terms == 6 ? 1.1 : 1.0) + epi + 1500.0;
     return t;
 }
@@ -729,13 +756,17 @@ static void plan_block_n_search(const map_gemm_split_args* sorted, int count, in
     for (int i = 0; i < count; ++i) {
         const map_gemm_args* g = &sorted[i].g;
         ncand[i] = 0;
+        static const bool dual_wide = getenv("MAP_B200_DUAL_WIDE") != nullptr && atoi(getenv("MAP_B200_DUAL_WIDE")) != 0;
+        // two-accumulator problems: at most 128 columns, so that main + corrections fit one TMEM buffer and the epilogue overlaps the
+        // next tile's main loop (MAP_B200_DUAL_WIDE=1 lifts the limit: A/B)
+        const int bn_max = (sorted[i].terms == 6 && !dual_wide) ? kSAccCols / 2 : 256;
         if (g->trans_b) {
-            cand[i][ncand[i]++] = 256;
+            if (bn_max == 256) cand[i][ncand[i]++] = 256;
             cand[i][ncand[i]++] = 128;
         } else if (g->N <= 64) {
             cand[i][ncand[i]++] = (int)ceil_div(g->N, 16) * 16;
         } else {
-            for (int bn = 256; bn >= 64; bn -= 16) {   // one candidate per distinct tile count: the narrowest width that still covers N
+            for (int bn = bn_max; bn >= 64; bn -= 16) {   // one candidate per distinct tile count: the narrowest width that still covers N
                 const int nt = (int)ceil_div(g->N, bn);
                 const int tight = (int)ceil_div((int)ceil_div(g->N, nt), 16) * 16;
                 bool seen = false;
@@ -830,7 +861,7 @@ static int launch_sgroup(const map_gemm_split_args* sorted, int count, int combo
         p.acc_out = g->acc_out; p.ld_acc_out = g->ld_acc_out;
         p.acc_accumulate = g->acc_accumulate;
         p.colsum_out = g->colsum_out;
-        p.corr_cols = (a->terms == 6) ? kSAccCols : 0;
+        p.corr_cols = (a->terms == 6) ? (p.block_n > kSAccCols / 2 ? kSAccCols : kSAccCols / 2) : 0;
         p.c_planes = reinterpret_cast<__nv_bfloat16*>(a->c_planes);
         p.ld_cp = a->c_ld; p.cp_stride = a->c_plane_stride; p.pc = a->c_planes ? a->c_nplanes : 0;
         p.b_tile_bytes = p.trans_b ? (pr.half_n / 64) * kSChunk : pr.half_n * 128;
