@@ -135,7 +135,7 @@ class FusedStep:
         # high 0.6604 / 0.6607; sorting the NCE ids under the forward pass instead (MAP_B200_NCE_SORT=early): 0.632 / 0.638.
         import os
         tab_prio = int(os.environ.get("MAP_B200_TAB_PRIO", "0"))
-        self.streams = ({k: torch.cuda.Stream(device=self.dev, priority=(tab_prio if k == "tab" else 0)) for k in ("tab", "mlp", "dw")}
+        self.streams = ({k: torch.cuda.Stream(device=self.dev, priority=(tab_prio if k == "tab" else 0)) for k in ("tab", "mlp", "dw", "opt")}
                         if multi_stream else {})
         # where the sort of the NCE ids runs on one GPU: "late" = after the NCE kernel, under the backward GEMMs; "early" = right
         # after the embedding sort, under the forward GEMMs (the ids = [labels | noise] are known once the noise is drawn)
@@ -300,6 +300,17 @@ class FusedStep:
         entries = [(self.opt_param[n], self.grad_flat[offs[n]:offs[n] + self.opt_param[n].numel()].view_as(self.opt_param[n]),
                     self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None, self.wplanes.get(n)) for n in self.dense]
         self.adam_table, self.adam_n, self.adam_max = ops.make_adamw_tensor_list(entries, dev)
+        # The same update in two launches for the fused single-GPU schedule: the weights of tower layers >= 1 and of the head have
+        # their gradients two GEMM levels before the backward ends (nothing reads them again in this step), so their AdamW (most of
+        # the 7 x 4 bytes per parameter) runs on the 'opt' stream under the last two levels, whose launches leave SMs idle; only
+        # layer 0 and the 1-D parameters (column sums that finish with the last epilogues) are left for the end of the step.
+        names = list(self.dense)
+        early = [i for i, n in enumerate(names) if self.dense[n].dim() == 2 and self._layer_depth(n) >= 1]
+        late = [i for i in range(len(names)) if i not in set(early)]
+        self.adam_early = ops.make_adamw_tensor_list([entries[i] for i in early], dev) if early and late else None
+        self.adam_late = ops.make_adamw_tensor_list([entries[i] for i in late], dev) if early and late else None
+        self._adam_early_done = False
+        self._ev_hyper = None
         self._param_versions = None
         self.refresh_weight_planes()
         # backward scratch
@@ -503,6 +514,9 @@ class FusedStep:
             self._draw_noise()   # first: the NCE head waits for the noise, nothing waits for the sort until the backward
             if self._early:      # every Philox consumer of this step has been issued: the step counter may advance
                 self._hyper_step()
+                if self.multi_stream:
+                    self._ev_hyper = torch.cuda.Event()
+                    self._ev_hyper.record(self.streams["tab"])
             self.tables["embed.embedding.weight"].plan.run(ids.view(-1))
             if self.nce_sort_early and self.mode == "MFP":
                 ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
@@ -605,6 +619,10 @@ class FusedStep:
                               acc_out=self.dX0_acc, acc_accumulate=False, colsum_out=self.grads[f"{pref_c}.{nc - 1}.bias"],
                               Ap=dHeadp, Bp=hw(self.cross_off, self.cross_off + in_dim), Cp=self.dUsp[nc - 1]))
         self._gemm_group(probs)
+        if self.has_fm and self.cfg.pretrain and not from_fold:
+            # d(lr_fm) = dHead . W[:, fm_col]: here, with the head level, because the head weight is updated before the backward ends
+            # (_early_dense_adamw); its consumers (FM backward, first-order table) run after dE below
+            self._gemm(dHead, head_W[:, self.fm_col:self.fm_col + 1], self.d_lrfm, B, 1, n_head, trans_b=True)
         last = []   # the final level: dE needs dX0_mlp, which the last MLP dgrad of the loop below produces
         for s_ in range(max(nc, nh)):
             ic, im = nc - 1 - s_, nh - 1 - s_
@@ -638,13 +656,13 @@ class FusedStep:
                 else:
                     probs.append(dict(A=dZ, B=layer.weight.data, C_out=self.dX0_mlp, M=B, N=k_in, K=H, trans_b=True, Ap=dZp, Bp=self._wp(wname)))
             self._gemm_group(probs)
+            if s_ == max(nc, nh) - 2:
+                self._early_dense_adamw()
         if nc:
             self._gemm_group(last)
         else:
             ops.copy2d(self.dX0_mlp, self.dE)
         if self.has_fm:  # d(lr_fm) flows into the embeddings (FM term) and into the first-order table + its bias
-            if self.cfg.pretrain and not from_fold:
-                self._gemm(dHead, head_W[:, self.fm_col:self.fm_col + 1], self.d_lrfm, B, 1, n_head, trans_b=True)
             ops.fm_lr_bwd(self.X0.view(B, self.F, self.D), self.d_lrfm, 1, self.dE.view(B, self.F, self.D), self.d_w_occ, accumulate=True)
             ops.reduce_sum(self.d_lrfm.view(-1), 1.0, out=self.grads["lr_layer.bias"], ws=self.red_ws2)
         self._embed_backward()
@@ -797,6 +815,8 @@ class FusedStep:
         been joined back into the current stream."""
         self._forked.clear()
         self._tables_done.clear()
+        self._adam_early_done = False
+        self._ev_hyper = None
         if self.bias_grad_flat.numel():
             self.bias_grad_flat.zero_()
         self.ids_cur = self._draw_and_mask()
@@ -820,13 +840,36 @@ class FusedStep:
         b1, b2 = self.betas
         ops.adamw_hyper_step(self.hyper, self.step_counter, self.lr, b1, b2, self.eps, self.sched, self.warmup_steps, self.total_steps)
 
+    def _early_dense_adamw(self):
+        """AdamW of the dense weights whose gradients are complete once the level just issued has run (see _alloc): on the 'opt'
+        stream, behind that level, the side-stream weight gradients issued so far and the hyper-parameter step."""
+        import os
+        if not (self._early and self.multi_stream and self.adam_early is not None and self._ev_hyper is not None) or os.environ.get("MAP_B200_EARLY_ADAM", "1") == "0":
+            return
+        opt = self.streams["opt"]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        opt.wait_event(ev)
+        if "dw" in self._forked:
+            ev_dw = torch.cuda.Event()
+            ev_dw.record(self.streams["dw"])
+            opt.wait_event(ev_dw)
+        opt.wait_event(self._ev_hyper)
+        self._forked.add("opt")
+        with torch.cuda.stream(opt):
+            ops.adamw_multi_tensor(*self.adam_early, self.hyper)
+        self._adam_early_done = True
+
     def optimizer_step(self):
         if not self._early:
             self._hyper_step()
         # dense parameters on the 'dw' stream, next to the table updates on the main stream
         self._fork("dw")
         with self._on("dw"):
-            ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
+            if self._adam_early_done:
+                ops.adamw_multi_tensor(*self.adam_late, self.hyper)
+            else:
+                ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
         for t in self.tables.values():
             if t.name in self._tables_done:
                 continue
