@@ -433,6 +433,17 @@ int map_p2p_barrier(const void* const* flag_ptrs, int R, int rank, int site, int
 int map_owned_compact(const void* const* uniq_ptrs, const void* const* n_unique_ptrs, int R, int rank, int64_t cap, int64_t* keys,
                       int32_t* src, int32_t* n_out, map_stream_t stream);
 
+/* Dense-gradient all-reduce over NVLink peer memory (the data-parallel gradient exchange the reference's NCCL initialisation at
+ * code/arguments.py:74 stands for; replaces ncclAllReduce on the gradient buckets of the sharded step).  send_ptrs[q] = rank q's
+ * peer-visible copy of the flat gradient.  map_p2p_reduce_f32: out[i] = sum over q = 0..R-1 (in that order on every rank: the
+ * result is bit-identical everywhere) of send_ptrs[q][first + i], i in [0, count).  One shot: every rank reduces the whole range
+ * into its local gradient.  Two shot: rank r reduces slice r in place (out = its own send buffer + first), then, after a barrier,
+ * map_p2p_gather_slices_f32 collects out[i] = send_ptrs[i / slice][first + i].  first / count / slice in floats, multiples of 4.
+ * The caller brackets the calls with map_p2p_barrier (copies complete before, reduced slices complete between). */
+int map_p2p_reduce_f32(const void* const* send_ptrs, int R, int64_t first, int64_t count, float* out, map_stream_t stream);
+int map_p2p_gather_slices_f32(const void* const* send_ptrs, int R, int64_t first, int64_t count, int64_t slice, float* out,
+                              map_stream_t stream);
+
 /* column sums: out[n] = sum_m X[m,n]  (bias gradients).  deterministic two-stage. */
 int map_colsum_f32(const float* X, int64_t ldx, int64_t M, int N, float* out, void* workspace, size_t workspace_bytes,
                    map_stream_t stream);

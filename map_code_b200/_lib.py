@@ -149,6 +149,8 @@ PROTOTYPES = {
     "map_nce_ids_concat": (_i, [_p, _p, _l, _i, _p, _p]),
     "map_p2p_barrier": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "map_owned_compact": (_i, [_p, _p, _i, _i, _l, _p, _p, _p, _p]),
+    "map_p2p_reduce_f32": (_i, [_p, _i, _l, _l, _p, _p]),
+    "map_p2p_gather_slices_f32": (_i, [_p, _i, _l, _l, _l, _p, _p]),
     "map_colsum_f32": (_i, [_p, _l, _l, _i, _p, _p, _sz, _p]),
     "map_colsum_workspace_bytes": (_sz, [_l, _i]),
     "map_cross_bwd_pre": (_i, [_p, _l, _p, _l, _p, _l, _l, _i, _i, _p, _p, _p]),

@@ -622,12 +622,17 @@ static DedupLayout dedup_layout(int64_t n) {
     // MAP_B200_DEDUP_CTAS caps the persistent grid: beside the one-CTA-per-SM persistent GEMMs a sort that wants every SM would
     // spin at its grid barriers on the SMs it got while the rest of its CTAs wait for a GEMM launch to end (and the next GEMM
     // launch waits for the spinning ones); a small grid fits on the SMs the GEMMs leave free (MAP_B200_GEMM_CLUSTERS)
-    static int cap = -1;
-    if (cap < 0) {
+    static int env_cap = -1;
+    if (env_cap < 0) {
         const char* e = getenv("MAP_B200_DEDUP_CTAS");
-        cap = (e != nullptr && atoi(e) >= 1) ? atoi(e) : kPersistMaxCtas;
-        if (cap > kPersistMaxCtas) cap = kPersistMaxCtas;
+        env_cap = (e != nullptr && atoi(e) >= 1) ? atoi(e) : 0;
+        if (env_cap > kPersistMaxCtas) env_cap = kPersistMaxCtas;
     }
+    // Up to 1 M keys (the id streams of a batch-4096 step: L2-resident, bound by the grid barriers, not by bandwidth) the sort
+    // takes at most 96 CTAs: it then holds a third of the SMs instead of all of them while the dynamically scheduled GEMM launches
+    // of the other streams keep working on the rest (C2 step 0.903 -> 0.881 ms, scripts/rounds/r2_36.sh; 64 CTAs: 0.890, 32: 0.920).
+    // Larger streams (C5: 2.5 M keys, HBM-bound) keep the full grid.
+    const int cap = env_cap > 0 ? env_cap : (n <= ((int64_t)1 << 20) ? 96 : kPersistMaxCtas);
     L.persist_ctas = ntiles < cap ? (int)ntiles : cap;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;

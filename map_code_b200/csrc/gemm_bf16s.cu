@@ -588,6 +588,7 @@ struct SCombo {
 // the epilogue combinations the step issues (engine.py), plus every single problem
 static const SCombo kSCombos[] = {
     MAP_SCOMBO(MAP_EPI_CROSS, MAP_EPI_BIAS_RELU, -1, -1),
+    MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, -1, -1),   // head level of the by-field MFP encoder (its weight gradient is not a GEMM)
     MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, -1),
     MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_MUL_RELUMASK, MAP_EPI_NONE, MAP_EPI_NONE),
     MAP_SCOMBO(MAP_EPI_CROSS_BWD, MAP_EPI_NONE, -1, -1),

@@ -156,6 +156,73 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(const PeerTable flags, 
     if (threadIdx.x == 0) epochs[site] = e;
 }
 
+// ---- dense-gradient all-reduce over peer memory (replaces the NCCL all-reduce of the gradient buckets).  Every rank copies its
+// range of the flat gradient into a peer-visible send buffer; after a barrier
+//   one shot : every rank sums the R copies of the whole range itself                         (small ranges: one barrier, R x bytes)
+//   two shot : rank r sums the R copies of slice r IN PLACE in its own send buffer, barrier,
+//              then every rank collects the R reduced slices from their owners                 (large ranges: 2 x bytes)
+// The sum runs over the ranks in the same order (0 .. R-1) on every rank: the reduced gradient is bit-identical everywhere, so the
+// replicated dense parameters stay bit-identical without a broadcast.  16-byte loads, kReduceUnroll independent peer loads in
+// flight per thread and per rank (a remote load is a ~2-4 us round trip through the NVSwitch).
+constexpr int kReduceUnroll = 4;
+
+// peer data rewritten every step: never through the non-coherent path, never from a stale L1 line
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+__global__ void __launch_bounds__(512) p2p_reduce_kernel(const PeerTable send, int R, int64_t first4, int64_t count4, float4* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride * kReduceUnroll) {
+        float4 acc[kReduceUnroll];
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < R; ++q) {
+            const float4* src = reinterpret_cast<const float4*>(send.p[q]) + first4;
+            float4 v[kReduceUnroll];
+#pragma unroll
+            for (int u = 0; u < kReduceUnroll; ++u) {
+                const int64_t iu = i + u * stride;
+                v[u] = iu < count4 ? ld_volatile_f4(src + iu) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kReduceUnroll; ++u) {
+                acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            const int64_t iu = i + u * stride;
+            if (iu < count4) out[iu] = acc[u];
+        }
+    }
+}
+
+// out[i] = send[i / slice4][first4 + i]: the reduced slices from their owners
+__global__ void __launch_bounds__(512) p2p_gather_slices_kernel(const PeerTable send, int R, int64_t first4, int64_t count4, int64_t slice4,
+                                                                float4* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride * kReduceUnroll) {
+        float4 v[kReduceUnroll];
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            const int64_t iu = i + u * stride;
+            if (iu < count4) {
+                int q = (int)(iu / slice4);
+                if (q >= R) q = R - 1;
+                v[u] = ld_volatile_f4(reinterpret_cast<const float4*>(send.p[q]) + first4 + iu);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kReduceUnroll; ++u) {
+            const int64_t iu = i + u * stride;
+            if (iu < count4) out[iu] = v[u];
+        }
+    }
+}
+
 }  // namespace mapb
 
 extern "C" int map_p2p_barrier(const void* const* flag_ptrs, int R, int rank, int site, int n_sites, uint32_t* epochs,
@@ -289,3 +356,39 @@ extern "C" int map_owned_compact(const void* const* uniq_ptrs, const void* const
     owned_compact_kernel<<<dim3((unsigned)bx, (unsigned)R), 256, 0, st>>>(l, R, rank, shift, cap, keys, src, n_out);
     return check_launch("map_owned_compact");
 }
+
+
+static unsigned p2p_reduce_grid(int64_t count4) {
+    int64_t blocks = mapb::ceil_div(count4, (int64_t)512 * mapb::kReduceUnroll);
+    if (blocks > 64) blocks = 64;   // a small grid finds room beside the persistent GEMM CTAs (one per SM) and still keeps ~1 MB of peer loads in flight
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+extern "C" int map_p2p_reduce_f32(const void* const* send_ptrs, int R, int64_t first, int64_t count, float* out, map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(first >= 0 && count >= 0 && first % 4 == 0 && count % 4 == 0 && out != nullptr && ((uintptr_t)out & 15) == 0,
+                "map_p2p_reduce_f32: first / count must be multiples of 4 floats and out 16-byte aligned");
+    PeerTable t;
+    const int rc = fill_peer_table(&t, send_ptrs, R, "map_p2p_reduce_f32");
+    if (rc != MAP_OK) return rc;
+    if (count == 0) return MAP_OK;
+    p2p_reduce_kernel<<<p2p_reduce_grid(count / 4), 512, 0, as_stream(stream)>>>(t, R, first / 4, count / 4, reinterpret_cast<float4*>(out));
+    return check_launch("map_p2p_reduce_f32");
+}
+
+extern "C" int map_p2p_gather_slices_f32(const void* const* send_ptrs, int R, int64_t first, int64_t count, int64_t slice, float* out,
+                                         map_stream_t stream) {
+    using namespace mapb;
+    MAP_REQUIRE(first >= 0 && count >= 0 && slice > 0 && first % 4 == 0 && count % 4 == 0 && slice % 4 == 0 && out != nullptr &&
+                    ((uintptr_t)out & 15) == 0,
+                "map_p2p_gather_slices_f32: first / count / slice must be multiples of 4 floats and out 16-byte aligned");
+    PeerTable t;
+    const int rc = fill_peer_table(&t, send_ptrs, R, "map_p2p_gather_slices_f32");
+    if (rc != MAP_OK) return rc;
+    if (count == 0) return MAP_OK;
+    p2p_gather_slices_kernel<<<p2p_reduce_grid(count / 4), 512, 0, as_stream(stream)>>>(t, R, first / 4, count / 4, slice / 4,
+                                                                                       reinterpret_cast<float4*>(out));
+    return check_launch("map_p2p_gather_slices_f32");
+}
+

@@ -336,7 +336,8 @@ class ShardedFusedStep(FusedStep):
     row, so the R-rank run reproduces the single-GPU run on the concatenated batch."""
 
     # barrier sites of one step: ids sorted everywhere / NCE values complete / embedding values complete / end of step
-    BAR_KEYS, BAR_NCE, BAR_EMBED, BAR_END, N_BARRIER_SITES = 0, 1, 2, 3, 4
+    # (+ the two barriers of the peer-memory gradient all-reduce: copies complete / reduced slices complete)
+    BAR_KEYS, BAR_NCE, BAR_EMBED, BAR_END, BAR_GRAD, BAR_GRAD2, N_BARRIER_SITES = 0, 1, 2, 3, 4, 5, 6
 
     def __init__(self, model, *, world: int, rank: int, group=None, **kw):
         self.world, self.rank, self.group = world, rank, group
@@ -368,6 +369,16 @@ class ShardedFusedStep(FusedStep):
         if os.environ.get("MAP_B200_NCCL_PRIO", "1") == "1":
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             self.grad_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+        # Dense gradients: NCCL all-reduce per bucket (default), or MAP_B200_GRAD_AR=p2p: our own all-reduce over peer memory
+        # (map_p2p_reduce_f32 / map_p2p_gather_slices_f32: one-shot for small ranges, two-shot above; deterministic rank order, so
+        # the replicas stay bit-identical).  Measured (profiles/r02f_*): equal at 2 GPUs (1.048 vs 1.050 ms / step), SLOWER at 8
+        # (1.348 vs 1.218 ms): the persistent GEMM CTAs hold every register of every SM, so the copy / barrier / reduce launches of
+        # a bucket only start in the gaps between two GEMM launches and the two-shot form needs two such gaps per bucket, while
+        # NCCL reduces in the switch with one kernel.  Kept as an option and as the tested building block for a reduce fused into
+        # the weight-gradient epilogues.
+        self.grad_ar = os.environ.get("MAP_B200_GRAD_AR", "nccl")
+        if self.grad_ar == "p2p":
+            self.grad_send = self.pm.alloc((self.grad_flat.numel(),), torch.float32)
         if self.multi_stream:
             # all table-side streams of the sharded step are high-priority (the configuration the N > 1 numbers were measured in;
             # the 1-GPU step runs its 'tab' stream at normal priority, see engine.py)
@@ -513,6 +524,12 @@ class ShardedFusedStep(FusedStep):
             self._draw_noise()
             if mfp:
                 ops.nce_ids_concat(self.labels.view(-1), self.noise, out=self.ids_all)
+            # every Philox consumer of the step has been issued (masks on the main stream before the fork, the noise draw above): the
+            # step counter may advance and this step's AdamW coefficients exist from here on — the optimizer kernels of whatever
+            # finishes early (NCE tables, reduced gradient buckets) wait for this event, not for the end of the backward
+            self._hyper_step()
+            self._ev_hyper = torch.cuda.Event()
+            self._ev_hyper.record(torch.cuda.current_stream())
             self._fork("keys")
             with self._on("keys"):
                 te = self.tables["mfp_criterion.emb.weight"] if mfp else None
@@ -554,10 +571,16 @@ class ShardedFusedStep(FusedStep):
             # complete: owners pull now, off the critical path of the backward pass
             self._barrier(self.BAR_NCE)
             self._merge_values([te, tb])
+            # no rank reads the NCE tables again in this step (the barrier above) and the owner-side sums are complete: update the
+            # shard here, under the backward GEMMs, instead of at the end of the step
+            torch.cuda.current_stream().wait_event(self._ev_hyper)
+            for t in (te, tb):
+                self._table_adamw(t)
+                self._tables_done.add(t.name)
 
     def _join_streams(self):
         for name in self.streams:   # the NCE merge chain and the gradient buckets keep running; the optimizer joins them
-            if name not in ("nce", "comm"):
+            if name not in ("nce", "comm", "opt"):
                 self._join(name)
 
     # -- dense gradients: bucketed all-reduce under the backward pass.  grad_flat is laid out so that the weight gradients the
@@ -570,6 +593,8 @@ class ShardedFusedStep(FusedStep):
         self._ar_hi = self.grad_flat.numel()      # [_ar_hi, end) has been handed to NCCL
         self._ar_done = set()
         self._ar_wait = []                        # events of gradients finished on side streams (by-field encoder wgrad on 'dw')
+        self._adam_done = set()                   # dense parameters already updated behind their gradient bucket
+        self._ev_hyper = None
         self._xr_event = None                     # the chain of cross-rank operations restarts with every step
         super().forward_backward()
 
@@ -579,8 +604,80 @@ class ShardedFusedStep(FusedStep):
             for ev in getattr(self, "_ar_wait", ()):
                 torch.cuda.current_stream().wait_event(ev)
             self._ar_wait = []
-            dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.grad_group)
-            _lib.mark("nccl_all_reduce", ("bytes", (hi - lo) * 4))
+            if self.grad_ar == "p2p":
+                self._peer_all_reduce(lo, hi)
+            else:
+                dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.grad_group)
+                _lib.mark("nccl_all_reduce", ("bytes", (hi - lo) * 4))
+        if getattr(self, "_ev_hyper", None) is not None:
+            # the parameters whose gradients this range holds are final and nothing of the step reads them again (their layers'
+            # backward has run: that is why the range could go out): their AdamW follows the collective on the 'comm' stream, so
+            # the end of the step only updates what the last bucket carries
+            names = tuple(n for n, (plo, phi) in self.grad_offsets.items() if lo <= plo and phi <= hi and n not in self._adam_done)
+            if names:
+                from . import ops
+                # (on the 'opt' stream: the 'comm' stream goes on with the next bucket's exchange at once)
+                if self.multi_stream:
+                    ev = torch.cuda.Event()
+                    ev.record(self.streams["comm"])
+                    self.streams["opt"].wait_event(ev)
+                    self._forked.add("opt")
+                with self._on("opt"):
+                    torch.cuda.current_stream().wait_event(self._ev_hyper)
+                    ops.adamw_multi_tensor(*self._adam_subset(names), self.hyper)
+                self._adam_done.update(names)
+
+    # one-shot (every rank sums all R copies) up to this many bytes of peer reads per rank, two-shot (reduce-scatter in place,
+    # barrier, gather) above: R x bytes against 2 x bytes + one more barrier
+    ONE_SHOT_MAX_PEER_BYTES = 6 << 20
+
+    def _peer_all_reduce(self, lo: int, hi: int):
+        """grad_flat[lo:hi] <- sum over the ranks, through the peer-visible send buffer (called on the 'comm' stream inside the
+        cross-rank chain; the chain context is re-entered around each barrier by _barrier itself)."""
+        from . import ops
+        R, n = self.world, hi - lo
+        send = self.grad_send
+        send.local[lo:hi].copy_(self.grad_flat[lo:hi])
+        self._barrier_nochain(self.BAR_GRAD)          # every rank's copy of the range is complete
+        if n * 4 * (R - 1) <= self.ONE_SHOT_MAX_PEER_BYTES or n < 4 * R:
+            ops.p2p_reduce(send.ptrs, R, lo, n, self.grad_flat[lo:hi])
+        else:
+            sl = ((n + R - 1) // R + 3) // 4 * 4      # slice of rank r: [lo + r * sl, lo + min(n, (r + 1) * sl))
+            first = min(n, self.rank * sl)
+            cnt = min(n, first + sl) - first
+            if cnt > 0:
+                ops.p2p_reduce(send.ptrs, R, lo + first, cnt, send.local[lo + first:lo + first + cnt])
+            self._barrier_nochain(self.BAR_GRAD2)     # every rank's reduced slice is complete
+            ops.p2p_gather_slices(send.ptrs, R, lo, n, sl, self.grad_flat[lo:hi])
+
+    def _barrier_nochain(self, site: int):
+        """barrier issued from INSIDE a _cross_rank() block (the caller already waited for the previous cross-rank operation and
+        records the chain event when it leaves)"""
+        from . import ops
+        if self.barrier_kind == "nccl":
+            dist.all_reduce(self._bar, op=dist.ReduceOp.SUM, group=self.bar_group)
+            _lib.mark("nccl_barrier")
+        else:
+            ops.p2p_barrier(self.bar_flags.ptrs, self.world, self.rank, site, self.N_BARRIER_SITES, self.bar_epochs, self.bar_error)
+
+    def _adam_subset(self, names):
+        """device descriptor table of the dense AdamW restricted to `names` (built once per distinct set: the bucket boundaries
+        are the same every step; the first step runs eagerly, so nothing is built under graph capture)"""
+        from . import ops
+        cache = self.__dict__.setdefault("_adam_subsets", {})
+        if names not in cache:
+            off = {n: self.grad_offsets[n][0] for n in names}
+            entries = [(self.opt_param[n], self.grad_flat[off[n]:off[n] + self.opt_param[n].numel()].view_as(self.opt_param[n]),
+                        self.exp_avg[n], self.exp_avg_sq[n], 0.0 if is_no_decay(n) else self.wd, None, self.wplanes.get(n)) for n in names]
+            cache[names] = ops.make_adamw_tensor_list(entries, self.dev)
+        return cache[names]
+
+    def _table_adamw(self, t):
+        from . import ops
+        if self.optimizer_mode == "sparse":
+            ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
+        else:
+            ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
 
     def _field_wgrad(self, W, Kd):
         """by-field encoder: its weight gradient is produced on the 'dw' stream, not by a grouped GEMM launch: mark it finished for
@@ -615,7 +712,6 @@ class ShardedFusedStep(FusedStep):
 
     def reduce_gradients(self):
         # every side stream that produced gradients was joined into the current stream by forward_backward()
-        self._hyper_step()              # every Philox consumer of the step has been issued: the step counter may advance
         self._barrier(self.BAR_EMBED)   # all ranks: embedding gathers done (tables may change), compact embedding gradients complete
         # the rest of the dense gradients (biases, first layers) on the 'comm' stream, beside the embedding merge below
         self._all_reduce_range(0, self._ar_hi)
@@ -624,18 +720,21 @@ class ShardedFusedStep(FusedStep):
 
     def optimizer_step(self):
         from . import ops
-        with self._on("comm"):          # dense AdamW behind the last gradient bucket, beside the table updates
-            ops.adamw_multi_tensor(self.adam_table, self.adam_n, self.adam_max, self.hyper)
+        rest = tuple(n for n in self.dense if n not in self._adam_done)
+        if rest:                        # (everything went out with its bucket unless the step runs on a single stream)
+            with self._on("comm"):
+                ops.adamw_multi_tensor(*self._adam_subset(rest), self.hyper)
         self._join("nce")
+        self._join("opt")
         for t in self.tables.values():
-            if self.optimizer_mode == "sparse":
-                ops.adamw_sparse_rows(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
-            else:
-                ops.adamw_dense_rows_sparse_grad(t.p.data, t.m, t.v, t.merge.plan, t.grad_owned, self.hyper, t.wd)
+            if t.name not in self._tables_done:
+                self._table_adamw(t)
         # end-of-step barrier: every rank's pulls are complete (compact gradients may be overwritten) and every shard is
         # up to date (the next step's gathers may read it)
-        self._barrier(self.BAR_END)
+        # (the 'comm' stream first: a rank that has passed the last barrier may overwrite its gradient send buffer in the next step,
+        #  so every rank's peer reads of this step must be behind that barrier)
         self._join("comm")
+        self._barrier(self.BAR_END)
 
     def dense_table_grad(self, name: str) -> torch.Tensor:
         """[shard_rows, D] dense view of the merged gradient of this rank's shard"""

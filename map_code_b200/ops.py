@@ -68,6 +68,20 @@ def p2p_barrier(flag_ptrs, R: int, rank: int, site: int, n_sites: int, epochs: t
     call("map_p2p_barrier", flag_ptrs, R, rank, site, n_sites, epochs.data_ptr(), _ptr(error_word), _stream())
 
 
+def p2p_reduce(send_ptrs, R: int, first: int, count: int, out: torch.Tensor):
+    """out[i] = sum_q send[q][first + i] over the ranks in order 0..R-1 (peer loads); out: fp32 view of `count` floats"""
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
+        _lib.CURRENT_TAG = ("bytes", count * 4)
+    call("map_p2p_reduce_f32", send_ptrs, R, first, count, out.data_ptr(), _stream())
+
+
+def p2p_gather_slices(send_ptrs, R: int, first: int, count: int, slice_len: int, out: torch.Tensor):
+    """out[i] = send[i // slice_len][first + i] (peer loads): second half of the two-shot all-reduce"""
+    if _lib.PROFILE is not None or _lib.TIMELINE is not None or _lib.RECORD is not None:
+        _lib.CURRENT_TAG = ("bytes", count * 4)
+    call("map_p2p_gather_slices_f32", send_ptrs, R, first, count, slice_len, out.data_ptr(), _stream())
+
+
 def owned_compact(uniq_ptrs, n_unique_ptrs, R: int, rank: int, cap: int, keys: torch.Tensor, src: torch.Tensor, n_out: torch.Tensor):
     call("map_owned_compact", uniq_ptrs, n_unique_ptrs, R, rank, cap, keys.data_ptr(), src.data_ptr(), n_out.data_ptr(), _stream())
 

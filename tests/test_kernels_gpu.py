@@ -993,3 +993,42 @@ def test_nce_shared_noise_batched_vs_reference(golden, loss_type):
     torch.testing.assert_close(inp.grad.cpu(), o["d_input"], rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(il.emb.weight.grad.cpu(), o["d_emb"], rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(il.bias.weight.grad.cpu(), o["d_bias"], rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ K13c peer-memory gradient all-reduce
+@pytest.mark.parametrize("R", [1, 2, 3, 8])
+@pytest.mark.parametrize("n", [4, 1000, 262144 + 12])
+def test_peer_all_reduce_single_process(ops, R, n):
+    """map_p2p_reduce_f32 / map_p2p_gather_slices_f32 with the R 'ranks' emulated on one GPU: one-shot == the sum over the ranks
+    in rank order (bit-exact: fixed summation order), two-shot (every rank reduces its slice in place, then the slices are
+    collected) == one-shot, at an offset inside a larger flat buffer (bucket [lo, hi) of the gradient)."""
+    import ctypes as C
+    g = torch.Generator().manual_seed(100 * R + n % 97)
+    lo, tot = 64, n + 128
+    send = [torch.randn(tot, generator=g).cuda() for _ in range(R)]
+    ref = send[0][lo:lo + n].clone()
+    for q in range(1, R):
+        ref = ref + send[q][lo:lo + n]
+    ptrs = (C.c_void_p * R)(*[t.data_ptr() for t in send])
+    out = torch.full((tot,), -7.0, device="cuda")
+    ops.p2p_reduce(ptrs, R, lo, n, out[lo:lo + n])
+    assert torch.equal(out[lo:lo + n], ref)
+    assert bool((out[:lo] == -7.0).all()) and bool((out[lo + n:] == -7.0).all())
+    # two shot
+    sl = ((n + R - 1) // R + 3) // 4 * 4
+    before = [t.clone() for t in send]
+    for r in range(R):
+        first = min(n, r * sl)
+        cnt = min(n, first + sl) - first
+        if cnt > 0:
+            ops.p2p_reduce(ptrs, R, lo + first, cnt, send[r][lo + first:lo + first + cnt])
+    for r in range(R):   # a rank only writes its own slice of its own buffer
+        first = min(n, r * sl)
+        cnt = min(n, first + sl) - first
+        mask = torch.ones(tot, dtype=torch.bool, device="cuda")
+        mask[lo + first:lo + first + cnt] = False
+        assert torch.equal(send[r][mask], before[r][mask])
+    out2 = torch.full((tot,), -7.0, device="cuda")
+    ops.p2p_gather_slices(ptrs, R, lo, n, sl, out2[lo:lo + n])
+    assert torch.equal(out2[lo:lo + n], ref)
+    assert bool((out2[:lo] == -7.0).all()) and bool((out2[lo + n:] == -7.0).all())
