@@ -756,7 +756,7 @@ def main_ours(args):
                     (f"c2 DCNv2 {args.task} mask_ratio 0.3 sparse (the reference's own run scripts)", args.task, "sparse", 0.3, None),
                     (f"c2 DCNv2 {args.task} mask_ratio {MASK_RATIO:g} sparse, TF32 single-pass GEMMs (fails the 1e-3 gradient tolerance: A/B only)", args.task, "sparse", MASK_RATIO, {"MAP_B200_GEMM": "tf32"})]
             if args.task == "MFP":
-                plan.append((f"c2 DCNv2 MFP mask_ratio {MASK_RATIO:g} sparse, dense encoder GEMM over all fields + gather (A/B of the by-field encoder)", "MFP", "sparse", MASK_RATIO, {"MAP_B200_FIELD_ENC": "0"}))
+                plan.append((f"c2 DCNv2 MFP mask_ratio {MASK_RATIO:g} sparse, encoder by field (forward + weight gradient for the L masked slices only, csrc/fieldenc.cu; A/B of the dense encoder GEMM)", "MFP", "sparse", MASK_RATIO, {"MAP_B200_FIELD_ENC": "1"}))
             for name, task_, mode_, ratio_, env_ in plan:
                 try:
                     secondary[name] = quick_measure(task_, mode_, ratio_, args.batch, dev, run.data, env=env_)

@@ -99,7 +99,8 @@ class FusedStep:
         self.cross_terms = int(_os.environ.get("MAP_B200_CROSS_TERMS", "3"))
         self.x_train, self.idx_low, self.idx_high = x_train, idx_low, idx_high
         # MFP head: evaluate feat_encoder only for the L masked fields of every sample (csrc/fieldenc.cu, K16) instead of all F
-        # fields + gather (models.py:73-78).  "hybrid" (default whenever the kernels take the shape and F >= 8 L): forward and
+        # fields + gather (models.py:73-78).  "hybrid" (default when the kernels take the shape, F >= 8 L and the backbone has no
+        # CrossNet tower — see below): forward and
         # weight gradient by field (13x fewer flops at mask_ratio 0.1; the weight gradient leaves the critical path), the input
         # gradient stays a dense tensor-core GEMM over the expanded d_enc, whose epilogues already carry the first backward stage
         # of the towers (measured r02e: a by-field dgrad has to write one [Kd] row per POSITION and fold them afterwards — 80 MB
@@ -116,7 +117,11 @@ class FusedStep:
         if field_encoder and not fe_ok:
             raise NotImplementedError(f"by-field encoder: needs MFP, F <= 256 and proj_size in (8, 16, 32, 64); got {self.mode}, F={self.F}, P={cfg.proj_size}")
         if field_encoder is None:
-            field_encoder = "hybrid" if (fe_ok and self.F >= 8 * self.L) else False
+            # Measured at HEAD of round 2 (scripts/rounds/r2_38.sh, same box): since the tensor-core GEMMs issue at the pipe's rate the
+            # DENSE encoder (13x the flops, but on tensor cores, its weight gradient grouped with the head level's dgrads) beats the
+            # SIMT by-field kernels again at C2 (DCNv2: 0.850 vs 0.876 ms / step), while DeepFM at the Avazu shape still gains from
+            # them (0.695 vs 0.701 ms)
+            field_encoder = "hybrid" if (fe_ok and self.F >= 8 * self.L and self.name != "dcnv2") else False
         self.field_enc = field_encoder
         self._collect_params()
         self._alloc()
