@@ -805,16 +805,18 @@ static int64_t g_strace_words = 0;
 
 // counters of the dynamic tile scheduler: one {next, done} pair per launch, handed out round-robin.  A pair is 0 whenever no launch
 // is using it (the kernel re-arms it), so captured launches replay without a memset; kSchedPairs launches later the pair is reused.
+// Captured launches (replayed for the life of their graph) and eager launches draw from separate halves, so an eager launch on one
+// stream can never share a pair with a graph replay that is in flight on another.
 constexpr int kSchedPairs = 1024;
 static unsigned* g_sched_buf = nullptr;
-static int g_sched_pos = 0;
+static int g_sched_pos[2] = {0, 0};   // [0] eager, [1] under stream capture
 
 static int sched_counters(cudaStream_t st, unsigned** out) {
     *out = nullptr;
     if (!sched_dynamic()) return MAP_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
     if (g_sched_buf == nullptr) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(st, &cs);
         MAP_REQUIRE(cs == cudaStreamCaptureStatusNone,
                     "map_gemm_bf16s: the first launch of the process allocates the tile-scheduler counters and cannot be captured; run it once eagerly");
         if (cudaMalloc(&g_sched_buf, kSchedPairs * 2 * sizeof(unsigned)) != cudaSuccess ||
@@ -824,7 +826,8 @@ static int sched_counters(cudaStream_t st, unsigned** out) {
             return MAP_ECUDA;
         }
     }
-    *out = g_sched_buf + 2 * (g_sched_pos++ % kSchedPairs);
+    const int half = cs == cudaStreamCaptureStatusNone ? 0 : 1;
+    *out = g_sched_buf + 2 * (half * (kSchedPairs / 2) + (g_sched_pos[half]++ % (kSchedPairs / 2)));
     return MAP_OK;
 }
 

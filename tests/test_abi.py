@@ -89,3 +89,17 @@ def test_alias_build_ignores_default_device_context():
         prob, alias = ops.alias_build(probs)
     assert prob.device.type == "cpu" and alias.device.type == "cpu"
     assert alias.tolist() == [11, 13, 14, 14, 15, 15, 15, 15, 0, 8, 9, 10, 11, 12, 13, 14]  # SURVEY.md §8c KAT
+
+
+def test_build_hook_and_makefile_compile_every_cuda_source():
+    """__graft_entry__.build() and csrc/Makefile must both compile every .cu under csrc/ (a hand-written list once missed two files and
+    a fresh checkout then failed to load the library)."""
+    import os
+    import re
+    import __graft_entry__ as g
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "map_code_b200", "csrc")
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith(".cu"))
+    assert sorted(g.SOURCES) == on_disk
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    srcs = re.search(r"^SRCS\s*:=\s*(.*)$", mk, re.M).group(1).split()
+    assert sorted(srcs) == on_disk
